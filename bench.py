@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""Benchmark of the batched kinematics hot path (BASELINE.json metric:
+"FK+Jacobian+IK poses/s (Fanuc165F, fp64)").
+
+One step = one pass of the hot path over one batch of synthetic joint vectors resident
+in HBM: K1 rk_fanuc_fk_jac_f64 (pose + 6x6 Jacobian + det J) followed by K2
+rk_fanuc_ik_f64 (all 8 Pieper branches + validity) on the poses K1 produced.  Default:
+15 steps x 2^26 poses = 1.0e9 poses (BASELINE config 2/3 sizes chunked for one GPU).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--workload fk_jac_ik|fk_jac|ik|calib|traj] [--batch B] [--layout soa|aos]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "FK+Jacobian+IK poses/s (Fanuc165F, fp64)"
+UNIT = "poses/s"
+BYTES_FK = 472        # 48 in + 128 + 288 + 8 out
+BYTES_IK = 520        # 128 in + 384 + 8 out
+BYTES_TRAJ = 352      # per sample: q,dq,ddq 72 + t 8 + T 128 + J 144
+BYTES_CALIB = 120     # per measurement: 6 q + 9 pts doubles in
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "50", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], [], set(), []
+        rows = [l for (t, l) in self.lines if t0 <= t <= t1 + 0.06] or [l for _, l in self.lines]
+        for l in rows:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])), smax.append(float(f[2])), power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the box's host cores
+# --------------------------------------------------------------------------------------
+def _cpu_fk_jac_ik(args):
+    seed, n = args
+    from oracle import np_oracle as O
+    c = O.FanucConst()
+    rng = np.random.default_rng(seed)
+    q = rng.uniform(c.lim[:, 0], c.lim[:, 1], size=(n, 6))
+    T = O.fanuc_fk(q, c)
+    J = O.fanuc_jacobian(q, c)
+    det = O.jac_det(J)
+    qb, vb = O.fanuc_ik_branches(T, O.CANONICAL_8, c)
+    return float(T[0, 0, 3] + det[0] + np.nansum(qb[0]))
+
+
+def cpu_poses_per_s(n_total, procs):
+    """Oracle FK + Jacobian + det + 8-branch IK over n_total poses on `procs` processes."""
+    chunk = 20000
+    tasks = [(i, min(chunk, n_total - i * chunk)) for i in range((n_total + chunk - 1) // chunk)]
+    t0 = time.perf_counter()
+    if procs <= 1:
+        for t in tasks:
+            _cpu_fk_jac_ik(t)
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(procs) as pool:
+            pool.map(_cpu_fk_jac_ik, tasks)
+    dt = time.perf_counter() - t0
+    return n_total / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm's CPU port (oracle/np_oracle.py, pinned to
+    the real reference by tests/golden) on all host cores, same metric/unit/config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = 20000 * cores          # poses per step
+    for _ in range(args.warmup):
+        cpu_poses_per_s(min(sample, 20000 * cores), cores)
+    times = []
+    for _ in range(args.steps):
+        _, dt = cpu_poses_per_s(sample, cores)
+        times.append(dt)
+    total = sample * args.steps
+    val = total / sum(times)
+    desc = (f"{sample} uniform-in-limits poses per step x {args.steps} steps: oracle "
+            f"fanuc_fk + fanuc_jacobian + det + 8-branch fanuc_ik, {cores} processes")
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(times) / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "fanuc165f_fk_jac_det_ik8", "batch_per_step": sample,
+                   "note": "NumPy restatement of the reference (the SymPy original runs "
+                           "~7.6 FK poses/s/core, BASELINE.md section 2)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": desc},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=15)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="fk_jac_ik",
+                    choices=["fk_jac_ik", "fk_jac", "ik", "calib", "traj"])
+    ap.add_argument("--batch", type=int, default=1 << 26, help="poses per GPU per step")
+    ap.add_argument("--e2e-batch", type=int, default=1 << 20)
+    ap.add_argument("--layout", default="soa", choices=["soa", "aos"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-sample", type=int, default=200000)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    from roboticmanipulators_b200 import _lib
+    import bench_workloads as W
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    _lib.load()
+
+    wl = W.make(args, rank, world)
+    for _ in range(max(args.warmup, 3) if args.warmup else 0):
+        wl.step(-1)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.12)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    ev0.record()
+    for s in range(args.steps):
+        wl.step(s)
+    ev1.record()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    if dist is not None:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    kern = wl.kernel_times_ms()          # {name: mean ms per launch} from events in the region
+    e2e = wl.e2e(args)                   # host buffers, copies inside the timed region
+    if dist is not None:
+        t = torch.tensor([e2e["seconds"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e["seconds"] = float(t.item())
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    units = wl.units_per_step * world
+    value = units * args.steps / (ms * 1e-3)
+    peak, peak_src = load_peaks()
+    dom = max(kern, key=lambda k: kern[k])
+    alg_bytes = wl.alg_bytes[dom] * wl.units_per_step
+    achieved = alg_bytes / (kern[dom] * 1e-3) / 1e9
+    out = {
+        "metric": METRIC if args.workload.startswith("fk") or args.workload == "ik" else wl.metric,
+        "value": value, "unit": wl.unit, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3) if args.warmup else 0,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": wl.config, "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": wl.traffic.get(dom),
+                     "peak_source": peak_src, "ms_per_launch": kern[dom],
+                     "algorithmic_bytes_per_unit": wl.alg_bytes[dom]},
+        "kernels": {k: {"ms_per_launch": v,
+                        "units_per_s": wl.units_per_step / (v * 1e-3),
+                        "achieved_gbs": wl.alg_bytes[k] * wl.units_per_step / (v * 1e-3) / 1e9,
+                        "hbm_frac": wl.alg_bytes[k] * wl.units_per_step / (v * 1e-3) / 1e9 / peak,
+                        "share_of_step": v / sum(kern.values())}
+                    for k, v in kern.items()},
+        "e2e": {"value": e2e["units"] * world / e2e["seconds"], "unit": wl.unit,
+                "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                "batch_per_step": e2e["batch"], "steps": e2e["steps"]},
+        "gpu_launches": wl.launches_per_step * args.steps,
+    }
+    out["fp64"] = W.fp64_probe()
+    if not args.no_cpu:
+        procs = 1
+        v, dt = cpu_poses_per_s(args.cpu_sample, procs) if wl.cpu is None else wl.cpu(args)
+        out["cpu_baseline"] = {
+            "value": v, "unit": wl.unit, "cores": procs, "kind": "port",
+            "sample": wl.cpu_sample_desc(args, dt)}
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

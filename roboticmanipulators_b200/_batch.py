@@ -1,0 +1,53 @@
+"""Layout helpers for the batched entry points.
+
+Batched arrays come in two storage layouts (include/rk_b200.h):
+  'aos'  pose-major, the reference's shapes on a leading batch axis ([N,6], [N,4,4], ...)
+  'soa'  component-major planes ([6,N], [16,N], ...) -- the fast layout on B200: every
+         warp access is a contiguous 256-byte segment.  SOA results are returned as
+         strided VIEWS with the logical reference shape ([N,4,4] etc.), so indexing code
+         written against the reference keeps working; `.contiguous()` gives AOS.
+"""
+import torch
+
+from . import _lib
+
+
+def detect_layout(x, ncomp):
+    """'soa' if x ([N, ncomp] logical) is a transposed view of a contiguous [ncomp, ld]."""
+    if x.dim() == 2 and x.shape[1] == ncomp and x.stride(0) == 1 and x.shape[0] > 1 \
+            and x.stride(1) >= x.shape[0]:
+        return "soa"
+    return "aos"
+
+
+def prep_input(x, ncomp, layout, dtype):
+    """Return (tensor, ld) with storage in the requested layout (copying if needed).
+    x logical shape [N, ncomp]."""
+    _lib.require_cuda(x, "input")
+    x = x.to(dtype).reshape(x.shape[0], ncomp)
+    n = x.shape[0]
+    if layout == "soa":
+        if n > 1 and x.stride(0) == 1 and x.stride(1) >= n:
+            return x, x.stride(1)
+        store = x.t().contiguous()          # [ncomp, N]
+        return store.t(), n
+    return x.contiguous(), n
+
+
+def alloc_out(n, shape, layout, dtype, device):
+    """Allocate an output with logical shape [n, *shape]; returns (logical_view, storage)."""
+    ncomp = 1
+    for s in shape:
+        ncomp *= s
+    if layout == "soa":
+        store = torch.empty((ncomp, n), dtype=dtype, device=device)
+        view = store.view(*shape, n).permute(len(shape), *range(len(shape)))
+        return view, store
+    store = torch.empty((n, *shape), dtype=dtype, device=device)
+    return store, store
+
+
+def flags_of(layout):
+    if layout not in ("aos", "soa"):
+        raise ValueError("layout must be 'aos', 'soa' or 'auto'")
+    return _lib.RK_SOA if layout == "soa" else _lib.RK_AOS

@@ -1,0 +1,164 @@
+// Shared device helpers for librk_b200 (sm_100a).  No torch, no third-party headers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rk_b200.h"
+
+namespace rk {
+
+constexpr int kBlock = 128;  // threads per CTA for the pose-per-thread kernels
+constexpr int kWarp = 32;
+
+// Set by launch helpers when a CUDA runtime call fails (reported by rk_last_cuda_error()).
+extern thread_local cudaError_t g_last_cuda;
+
+inline int check_launch() {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    g_last_cuda = e;
+    return RK_ERR_CUDA;
+  }
+  return RK_OK;
+}
+
+// Grid for a grid-stride kernel: enough CTAs to fill every SM at the kernel's occupancy,
+// never more than the work needs ("a multiple of 148 x resident CTAs per SM").
+template <typename K>
+inline int persistent_grid(K kernel, int block, size_t smem, int64_t work_items) {
+  int dev = 0, sms = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess ||
+      per_sm < 1)
+    per_sm = 1;
+  int64_t need = (work_items + block - 1) / block;
+  int64_t cap = (int64_t)sms * per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// ---------------------------------------------------------------------------------
+// Scalar traits: correctly rounded, never-contracted primitives (the reference's
+// threshold expressions are plain IEEE mul/add sequences) and libm-grade transcendentals.
+// ---------------------------------------------------------------------------------
+template <typename S>
+struct Sc;
+
+template <>
+struct Sc<double> {
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+  static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
+  static __device__ __forceinline__ void sincos(double x, double* s, double* c) { ::sincos(x, s, c); }
+  static __device__ __forceinline__ double sin(double x) { return ::sin(x); }
+  static __device__ __forceinline__ double cos(double x) { return ::cos(x); }
+  static __device__ __forceinline__ double acos(double x) { return ::acos(x); }
+  static __device__ __forceinline__ double atan2(double y, double x) { return ::atan2(y, x); }
+  static __device__ __forceinline__ double abs(double x) { return ::fabs(x); }
+  static __device__ __forceinline__ double pi() { return 3.141592653589793; }
+};
+
+template <>
+struct Sc<float> {
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+  static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+  static __device__ __forceinline__ void sincos(float x, float* s, float* c) { ::sincosf(x, s, c); }
+  static __device__ __forceinline__ float sin(float x) { return ::sinf(x); }
+  static __device__ __forceinline__ float cos(float x) { return ::cosf(x); }
+  static __device__ __forceinline__ float acos(float x) { return ::acosf(x); }
+  static __device__ __forceinline__ float atan2(float y, float x) { return ::atan2f(y, x); }
+  static __device__ __forceinline__ float abs(float x) { return ::fabsf(x); }
+  static __device__ __forceinline__ float pi() { return 3.14159265358979323846f; }
+};
+
+// 3-vectors as plain scalars keep everything in registers.
+template <typename S>
+struct V3 {
+  S x, y, z;
+};
+
+template <typename S>
+__device__ __forceinline__ V3<S> cross(const V3<S>& a, const V3<S>& b) {
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+template <typename S>
+__device__ __forceinline__ V3<S> sub(const V3<S>& a, const V3<S>& b) {
+  return {a.x - b.x, a.y - b.y, a.z - b.z};
+}
+template <typename S>
+__device__ __forceinline__ V3<S> axpy(S a, const V3<S>& x, const V3<S>& y) {  // a*x + y
+  return {a * x.x + y.x, a * x.y + y.y, a * x.z + y.z};
+}
+template <typename S>
+__device__ __forceinline__ V3<S> lin2(S a, const V3<S>& x, S b, const V3<S>& y) {  // a*x + b*y
+  return {a * x.x + b * y.x, a * x.y + b * y.y, a * x.z + b * y.z};
+}
+// R (row-major 3x3) * v
+template <typename S>
+__device__ __forceinline__ V3<S> rot(const S* R, const V3<S>& v) {
+  return {R[0] * v.x + R[1] * v.y + R[2] * v.z, R[3] * v.x + R[4] * v.y + R[5] * v.z,
+          R[6] * v.x + R[7] * v.y + R[8] * v.z};
+}
+
+// C(3x4) = A(3x4) * B(3x4) as homogeneous transforms, row-major, last row implied.
+template <typename S>
+__device__ __forceinline__ void xf_mul(const S* A, const S* B, S* C) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      S acc = A[i * 4 + 0] * B[0 * 4 + j] + A[i * 4 + 1] * B[1 * 4 + j] + A[i * 4 + 2] * B[2 * 4 + j];
+      if (j == 3) acc += A[i * 4 + 3];
+      C[i * 4 + j] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Warp-private staging between the per-thread register layout and pose-major (AOS)
+// global arrays: lane t owns NC consecutive components of item (warp_base + t).  The
+// staging row stride is odd (in elements) so the per-lane accesses are bank-conflict
+// free, and the global side is walked as one contiguous run -> full 128-byte lines.
+// ---------------------------------------------------------------------------------
+template <int NC>
+struct Stride {
+  static constexpr int value = (NC % 2 == 0) ? NC + 1 : NC;
+};
+
+template <typename S, int NC>
+__device__ __forceinline__ void warp_store_aos(S* stage, const S (&v)[NC], S* g_warp_base,
+                                               int n_items, int lane) {
+  constexpr int ST = Stride<NC>::value;
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < NC; ++c) stage[lane * ST + c] = v[c];
+  __syncwarp();
+  const int total = n_items * NC;
+  for (int idx = lane; idx < total; idx += kWarp) {
+    int item = idx / NC, c = idx - item * NC;
+    g_warp_base[idx] = stage[item * ST + c];
+  }
+}
+
+template <typename S, int NC>
+__device__ __forceinline__ void warp_load_aos(S* stage, S (&v)[NC], const S* g_warp_base,
+                                              int n_items, int lane) {
+  constexpr int ST = Stride<NC>::value;
+  __syncwarp();
+  const int total = n_items * NC;
+  for (int idx = lane; idx < total; idx += kWarp) {
+    int item = idx / NC, c = idx - item * NC;
+    stage[item * ST + c] = g_warp_base[idx];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < NC; ++c) v[c] = stage[lane * ST + c];
+}
+
+}  // namespace rk

@@ -1,0 +1,538 @@
+// Fanuc165F batched kernels: K1 fk+jacobian+det, K2 Pieper IK over all branches.
+// One thread owns one pose (K1) or one (pose, elbow/root branch) pair (K2); the screw
+// chain is unrolled in registers.  See include/rk_b200.h for the reference citations.
+#include "rk_common.cuh"
+
+namespace rk {
+
+template <typename S>
+struct FanucP {
+  S l[7], off[6], dir[6], lo[6], hi[6];
+  S d, dq, eps;
+  S Tb[12], Tt[12], Tbi[12], Tti[12];
+  int has_base, has_tool, user_jac;
+};
+
+template <typename S>
+static FanucP<S> make_params(const RkFanuc* r, int flags) {
+  FanucP<S> p;
+  for (int i = 0; i < 7; ++i) p.l[i] = (S)r->l[i];
+  for (int i = 0; i < 6; ++i) {
+    p.off[i] = (S)r->offsets[i];
+    p.dir[i] = (S)r->directions[i];
+    p.lo[i] = (S)r->lim_lo[i];
+    p.hi[i] = (S)r->lim_hi[i];
+  }
+  p.d = (S)r->d;
+  p.dq = (S)r->dq;
+  p.eps = (S)r->eps;
+  for (int i = 0; i < 12; ++i) {
+    p.Tb[i] = (S)r->T_base[i];
+    p.Tt[i] = (S)r->T_tool[i];
+    p.Tbi[i] = (S)r->T_base_inv[i];
+    p.Tti[i] = (S)r->T_tool_inv[i];
+  }
+  p.has_base = r->has_base;
+  p.has_tool = r->has_tool;
+  p.user_jac = (flags & RK_JAC_USER_ANGLES) ? 1 : 0;
+  return p;
+}
+
+// -----------------------------------------------------------------------------------
+// K1: forward kinematics + screw Jacobian + det J for one pose.
+//
+// Chain (robots/fanuc.py:122-125, :173):
+//   T_base Tz(l0) Rz(q0) Tz(l1) Tx(l2) Ry(q1) Tx(l3) Ry(q2) Tz(l4) Tx(l5) Rx(q3) Ry(q4) Rx(q5) Tx(l6) T_tool
+// Because every translation is along a frame axis, the frame columns follow from
+// Givens-style updates: joints 1,2 share the axis y1 and only the sum q1+q2 rotates
+// the arm plane; the wrist axes x3, y4, x5 intersect at the wrist centre O3.
+// Jacobian column k = [u_k x (O_n - O_k); u_k] (utils/jacobians.py:203-233).
+// det J: move the reference point to O3 (unimodular row operation): J becomes block
+// lower triangular, det J = det[u_k x (O3 - O_k)]_{k<3} * det[u3 u4 u5]
+//        = rho3 * l3 * (l5 s2 - l4 c2) * (-s4).
+// -----------------------------------------------------------------------------------
+template <typename S>
+__device__ __forceinline__ void fanuc_fk_jac_pose(const FanucP<S>& P, const S (&q)[6], S (&T)[16],
+                                                  S (&J)[36], S& det) {
+  using M = Sc<S>;
+  S c[6], s[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    S qm = M::add(M::mul(q[k], P.dir[k]), P.off[k]);  // fanuc.py:163
+    M::sincos(qm, &s[k], &c[k]);
+  }
+  const S l0 = P.l[0], l1 = P.l[1], l2 = P.l[2], l3 = P.l[3], l4 = P.l[4], l5 = P.l[5], l6 = P.l[6];
+  const S c12 = c[1] * c[2] - s[1] * s[2];
+  const S s12 = s[1] * c[2] + c[1] * s[2];
+  // arm plane coordinates (rho along x1, h along z)
+  const S rho2 = l2 + l3 * c[1];
+  const S h1 = l0 + l1;
+  const S h2 = h1 - l3 * s[1];
+  const S rho3 = rho2 + l4 * s12 + l5 * c12;
+  const S h3 = h2 + l4 * c12 - l5 * s12;
+
+  const V3<S> y1 = {-s[0], c[0], S(0)};
+  const V3<S> x3 = {c12 * c[0], c12 * s[0], -s12};
+  const V3<S> z3 = {s12 * c[0], s12 * s[0], c12};
+  const V3<S> O3 = {rho3 * c[0], rho3 * s[0], h3};
+  const V3<S> y4 = lin2(c[3], y1, s[3], z3);
+  const V3<S> z4 = lin2(-s[3], y1, c[3], z3);
+  const V3<S> x5 = lin2(c[4], x3, -s[4], z4);
+  const V3<S> z5 = lin2(s[4], x3, c[4], z4);
+  const V3<S> y6 = lin2(c[5], y4, s[5], z5);
+  const V3<S> z6 = lin2(-s[5], y4, c[5], z5);
+  V3<S> On = axpy(l6, x5, O3);
+  // R6 = [x5 y6 z6] (columns)
+  S R[9] = {x5.x, y6.x, z6.x, x5.y, y6.y, z6.y, x5.z, y6.z, z6.z};
+  if (P.has_tool) {
+    const S* Tt = P.Tt;
+    V3<S> pt = {Tt[3], Tt[7], Tt[11]};
+    V3<S> dv = rot(R, pt);
+    On = {On.x + dv.x, On.y + dv.y, On.z + dv.z};
+    S Rn[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        Rn[i * 3 + j] = R[i * 3 + 0] * Tt[0 * 4 + j] + R[i * 3 + 1] * Tt[1 * 4 + j] + R[i * 3 + 2] * Tt[2 * 4 + j];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = Rn[i];
+  }
+
+  // Jacobian columns in the base-local frame
+  const V3<S> O1 = {l2 * c[0], l2 * s[0], h1};
+  const V3<S> O2 = {rho2 * c[0], rho2 * s[0], h2};
+  V3<S> jv[6], jw[6];
+  jw[0] = {S(0), S(0), S(1)};
+  jv[0] = {-On.y, On.x, S(0)};
+  jw[1] = y1;
+  jv[1] = cross(y1, sub(On, O1));
+  jw[2] = y1;
+  jv[2] = cross(y1, sub(On, O2));
+  const V3<S> rw = sub(On, O3);
+  jw[3] = x3;
+  jv[3] = cross(x3, rw);
+  jw[4] = y4;
+  jv[4] = cross(y4, rw);
+  jw[5] = x5;
+  jv[5] = cross(x5, rw);
+
+  S dt = -s[4] * rho3 * l3 * (l5 * s[2] - l4 * c[2]);
+
+  if (P.has_base) {
+    const S* Tb = P.Tb;
+    const S Rb[9] = {Tb[0], Tb[1], Tb[2], Tb[4], Tb[5], Tb[6], Tb[8], Tb[9], Tb[10]};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      jv[k] = rot(Rb, jv[k]);
+      jw[k] = rot(Rb, jw[k]);
+    }
+    V3<S> p = rot(Rb, On);
+    On = {p.x + Tb[3], p.y + Tb[7], p.z + Tb[11]};
+    S Rn[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        Rn[i * 3 + j] = Rb[i * 3 + 0] * R[0 * 3 + j] + Rb[i * 3 + 1] * R[1 * 3 + j] + Rb[i * 3 + 2] * R[2 * 3 + j];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = Rn[i];
+  }
+  if (P.user_jac) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const S dk = P.dir[k];
+      jv[k] = {jv[k].x * dk, jv[k].y * dk, jv[k].z * dk};
+      jw[k] = {jw[k].x * dk, jw[k].y * dk, jw[k].z * dk};
+      dt *= dk;
+    }
+  }
+  T[0] = R[0], T[1] = R[1], T[2] = R[2], T[3] = On.x;
+  T[4] = R[3], T[5] = R[4], T[6] = R[5], T[7] = On.y;
+  T[8] = R[6], T[9] = R[7], T[10] = R[8], T[11] = On.z;
+  T[12] = S(0), T[13] = S(0), T[14] = S(0), T[15] = S(1);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    J[0 * 6 + k] = jv[k].x;
+    J[1 * 6 + k] = jv[k].y;
+    J[2 * 6 + k] = jv[k].z;
+    J[3 * 6 + k] = jw[k].x;
+    J[4 * 6 + k] = jw[k].y;
+    J[5 * 6 + k] = jw[k].z;
+  }
+  det = dt;
+}
+
+// SOA: component planes, every warp access is one contiguous 256-byte (f64) segment.
+template <typename S>
+__global__ void __launch_bounds__(kBlock, 4)
+fanuc_fk_jac_soa_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict__ q, int64_t n,
+                        int64_t ld, S* __restrict__ T, S* __restrict__ J, S* __restrict__ det) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    S qv[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) qv[k] = __ldcs(q + k * ld + i);
+    S Tv[16], Jv[36], dv;
+    fanuc_fk_jac_pose(P, qv, Tv, Jv, dv);
+    if (T) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) __stcs(T + k * ld + i, Tv[k]);
+    }
+    if (J) {
+#pragma unroll
+      for (int k = 0; k < 36; ++k) __stcs(J + k * ld + i, Jv[k]);
+    }
+    if (det) __stcs(det + i, dv);
+  }
+}
+
+// AOS: the reference's shapes ([n][6] -> [n][4][4], [n][6][6]); each warp stages its 32
+// poses through a private shared-memory tile so that global traffic is whole lines.
+template <typename S>
+__global__ void __launch_bounds__(kBlock)
+fanuc_fk_jac_aos_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict__ q, int64_t n,
+                        S* __restrict__ T, S* __restrict__ J, S* __restrict__ det) {
+  __shared__ S stage_all[(kBlock / kWarp) * kWarp * Stride<36>::value];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  S* stage = stage_all + warp * kWarp * Stride<36>::value;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + warp * kWarp; base < n; base += stride) {
+    const int64_t rem = n - base;
+    const int cnt = rem < kWarp ? (int)rem : kWarp;
+    S qv[6];
+    warp_load_aos<S, 6>(stage, qv, q + base * 6, cnt, lane);
+    if (lane >= cnt) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) qv[k] = S(0);
+    }
+    S Tv[16], Jv[36], dv;
+    fanuc_fk_jac_pose(P, qv, Tv, Jv, dv);
+    if (T) warp_store_aos<S, 16>(stage, Tv, T + base * 16, cnt, lane);
+    if (J) warp_store_aos<S, 36>(stage, Jv, J + base * 36, cnt, lane);
+    if (det && lane < cnt) det[base + lane] = dv;
+  }
+}
+
+// -----------------------------------------------------------------------------------
+// K2: Pieper inverse kinematics (robots/fanuc.py:196-302).
+// -----------------------------------------------------------------------------------
+
+// T_0 = Tz(l0)^-1 T_base^-1 T T_tool^-1 Tx(l6)^-1  (fanuc.py:222-225)
+template <typename S>
+__device__ __forceinline__ void fanuc_ik_t0(const FanucP<S>& P, const S (&Tin)[12], S (&R0)[9],
+                                            S (&p0)[3]) {
+  using M = Sc<S>;
+  S A[12], B[12];
+  if (P.has_base) {
+    xf_mul(P.Tbi, Tin, A);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) A[i] = Tin[i];
+  }
+  if (P.has_tool) {
+    xf_mul(A, P.Tti, B);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) B[i] = A[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) R0[i * 3 + j] = B[i * 4 + j];
+  const S ml6 = -P.l[6];
+  p0[0] = M::add(M::mul(B[0], ml6), B[3]);
+  p0[1] = M::add(M::mul(B[4], ml6), B[7]);
+  p0[2] = M::sub(M::add(M::mul(B[8], ml6), B[11]), P.l[0]);
+}
+
+// One (m, k) pair: position solve once, wrist solve once, then one solution per wrist
+// flag w in wl[0..NW).  Writes user-space angles or the all-zero failure sentinel.
+template <typename S, int NW>
+__device__ __forceinline__ void fanuc_ik_mk(const FanucP<S>& P, const S (&R0)[9], const S (&p0)[3],
+                                            int m, int k, const int (&wl)[NW], S (&qout)[NW][6],
+                                            bool (&valid)[NW]) {
+  using M = Sc<S>;
+  const S fm = (S)m, fk = (S)k;
+  const S l1 = P.l[1], l2 = P.l[2], l3 = P.l[3], d = P.d;
+  const S x = p0[0], y = p0[1], z = p0[2];
+  // fanuc.py:228-234, evaluated operation by operation (no contraction)
+  const S rxy = M::sqrt(M::add(M::mul(x, x), M::mul(y, y)));
+  const S xp = M::sub(M::mul(fk, rxy), l2);
+  const S zp = M::sub(l1, z);
+  const S num = M::sub(M::sub(M::add(M::mul(xp, xp), M::mul(zp, zp)), M::mul(d, d)), M::mul(l3, l3));
+  const S den = M::mul(M::mul(S(2), d), l3);
+  const S psi_cos = M::div(num, den);
+#pragma unroll
+  for (int i = 0; i < NW; ++i) {
+    valid[i] = false;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) qout[i][j] = S(0);
+  }
+  if (M::abs(psi_cos) > S(1)) return;  // fanuc.py:237-239
+
+  const S psi = -fm * M::acos(psi_cos);  // :241
+  S sp, cp;
+  M::sincos(psi, &sp, &cp);
+  const S beta = M::atan2(d * (fm * sp), l3 + d * cp);  // sin(m*psi) = m*sin(psi); :242-243
+  const S gamma = M::atan2(zp, xp);                      // :244
+  S q0 = M::atan2(y, x);                                 // :246
+  const S q1 = M::sub(gamma, M::mul(fm, beta));          // :247
+  const S q2 = M::add(psi, P.dq);                        // :248
+  const S A = d * M::cos(M::add(q1, psi)) + l2 + l3 * M::cos(q1);  // :250-251
+  if (M::abs(A) < P.eps) q0 = S(0);                      // :253-255
+
+  // T_rot = Ry(-dq) T_012^-1 T_0 (:262-264).  Its rotation is Ry(-(q1+q2)) Rz(-q0) R0.
+  S s0, c0, st, ct;
+  M::sincos(q0, &s0, &c0);
+  M::sincos(M::add(q1, q2), &st, &ct);
+  // rows of Rz(-q0) R0
+  const S a0 = c0 * R0[0] + s0 * R0[3], a1 = c0 * R0[1] + s0 * R0[4], a2 = c0 * R0[2] + s0 * R0[5];
+  const S b0 = c0 * R0[3] - s0 * R0[0];
+  const S r11 = ct * a0 - st * R0[6];
+  const S r12 = ct * a1 - st * R0[7];
+  const S r13 = ct * a2 - st * R0[8];
+  const S r21 = b0;
+  const S r31 = st * a0 + ct * R0[6];
+
+  const bool regular = M::abs(r11 - S(1)) > P.eps;  // :272
+  S a3 = S(0), a5 = S(0);
+  if (regular) {
+    a3 = M::atan2(r21, -r31);  // :273
+    a5 = M::atan2(r12, r13);   // :274
+  }
+  const bool use13 = M::abs(r13) > P.eps;  // :279
+#pragma unroll
+  for (int i = 0; i < NW; ++i) {
+    S q3 = S(0), q4 = S(0), q5 = S(0);
+    if (regular) {
+      const S wpi = (S)wl[i] * M::pi();
+      q3 = M::sub(a3, wpi);  // :276
+      q5 = M::sub(a5, wpi);  // :277
+      if (use13)
+        q4 = M::atan2(r13 / M::cos(q5), r11);  // :280
+      else
+        q4 = M::atan2(r12 / M::sin(q5), r11);  // :282
+    }
+    const S qs[6] = {q0, q1, q2, q3, q4, q5};
+    bool out = false;
+    S qu[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      qu[j] = M::mul(M::sub(qs[j], P.off[j]), P.dir[j]);   // :290
+      out = out || (qu[j] < P.lo[j]) || (qu[j] > P.hi[j]);  // :292-297 (NaN passes)
+    }
+    if (!out) {
+      valid[i] = true;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) qout[i][j] = qu[j];
+    }
+  }
+}
+
+template <typename S, bool SOA>
+__device__ __forceinline__ void load_T12(const S* __restrict__ T, int64_t i, int64_t ld, S (&Tin)[12]) {
+#pragma unroll
+  for (int k = 0; k < 12; ++k) Tin[k] = SOA ? T[k * ld + i] : T[i * 16 + k];
+}
+
+// Canonical 8 branches: 4 lanes per pose, lane = (pose, (m,k)); each lane emits w = 0, 1.
+// Branch index b = 4*[m==-1] + 2*[k==-1] + w.  Validity bits of the 4 lanes of a pose
+// are gathered with warp shuffles so one lane writes the pose's 8 validity bytes.
+template <typename S, bool SOA>
+__global__ void __launch_bounds__(kBlock)
+fanuc_ik8_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict__ T, int64_t n, int64_t ld,
+                 S* __restrict__ q_out, uint8_t* __restrict__ valid) {
+  constexpr int PPW = kWarp / 4;  // poses per warp
+  __shared__ S stage_all[SOA ? 1 : (kBlock / kWarp) * kWarp * Stride<12>::value];
+  const int lane = threadIdx.x & 31, warp_in_blk = threadIdx.x >> 5;
+  const int mk = lane & 3, pl = lane >> 2;
+  const int m = (mk & 2) ? -1 : 1, k = (mk & 1) ? -1 : 1;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t warp_id = (((int64_t)blockIdx.x * blockDim.x) >> 5) + warp_in_blk;
+  for (int64_t base = warp_id * PPW; base < n; base += warps * PPW) {
+    const int64_t i = base + pl;
+    const bool live = i < n;
+    S Tin[12];
+    if (live) {
+      load_T12<S, SOA>(T, i, ld, Tin);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 12; ++c) Tin[c] = (c % 5 == 0) ? S(1) : S(0);
+    }
+    S R0[9], p0[3];
+    fanuc_ik_t0(P, Tin, R0, p0);
+    const int wl[2] = {0, 1};
+    S qo[2][6];
+    bool ok[2];
+    fanuc_ik_mk<S, 2>(P, R0, p0, m, k, wl, qo, ok);
+
+    // validity: 2 bits per lane -> 8 bytes per pose via shuffles
+    const unsigned mine = (ok[0] ? 1u : 0u) | (ok[1] ? 2u : 0u);
+    unsigned long long packed = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      unsigned v = __shfl_sync(0xffffffffu, mine, (lane & ~3) + j);
+      packed |= (unsigned long long)(v & 1u) << (8 * (2 * j));
+      packed |= (unsigned long long)((v >> 1) & 1u) << (8 * (2 * j + 1));
+    }
+    if (SOA) {
+      if (live) {
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          const int b = mk * 2 + w;
+#pragma unroll
+          for (int j = 0; j < 6; ++j) q_out[(int64_t)(b * 6 + j) * ld + i] = qo[w][j];
+          valid[(int64_t)b * ld + i] = ok[w] ? 1 : 0;
+        }
+      }
+    } else {
+      // pose-major [n][8][6]: this warp owns a contiguous run of PPW*48 values
+      S flat[12];
+#pragma unroll
+      for (int w = 0; w < 2; ++w)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) flat[w * 6 + j] = qo[w][j];
+      const int64_t rem = n - base;
+      const int cnt = rem < PPW ? (int)rem : PPW;
+      S* stage = stage_all + warp_in_blk * kWarp * Stride<12>::value;
+      warp_store_aos<S, 12>(stage, flat, q_out + base * 48, cnt * 4, lane);
+      if (live && mk == 0) *reinterpret_cast<unsigned long long*>(valid + i * 8) = packed;
+    }
+  }
+}
+
+// Arbitrary branch list: one thread per (pose, branch).
+struct BranchList {
+  int8_t mkw[3 * 16];
+  int nb;
+};
+
+template <typename S, bool SOA>
+__global__ void __launch_bounds__(kBlock)
+fanuc_ik_list_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant__ BranchList BL,
+                     const S* __restrict__ T, int64_t n, int64_t ld, S* __restrict__ q_out,
+                     uint8_t* __restrict__ valid) {
+  const int nb = BL.nb;
+  const int64_t total = n * nb;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t tix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tix < total; tix += stride) {
+    const int64_t i = tix / nb;
+    const int b = (int)(tix - i * nb);
+    S Tin[12];
+    load_T12<S, SOA>(T, i, ld, Tin);
+    S R0[9], p0[3];
+    fanuc_ik_t0(P, Tin, R0, p0);
+    const int wl[1] = {BL.mkw[b * 3 + 2]};
+    S qo[1][6];
+    bool ok[1];
+    fanuc_ik_mk<S, 1>(P, R0, p0, BL.mkw[b * 3 + 0], BL.mkw[b * 3 + 1], wl, qo, ok);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      if (SOA)
+        q_out[(int64_t)(b * 6 + j) * ld + i] = qo[0][j];
+      else
+        q_out[(i * nb + b) * 6 + j] = qo[0][j];
+    }
+    if (SOA)
+      valid[(int64_t)b * ld + i] = ok[0] ? 1 : 0;
+    else
+      valid[i * nb + b] = ok[0] ? 1 : 0;
+  }
+}
+
+// -----------------------------------------------------------------------------------
+// host launchers
+// -----------------------------------------------------------------------------------
+template <typename S>
+static int launch_fk_jac(const RkFanuc* robot, const S* q, int64_t n, int64_t ld, int flags, S* T,
+                         S* J, S* det, void* stream) {
+  if (!robot || !q || n < 0) return RK_ERR_INVALID_ARG;
+  if (n == 0) return RK_OK;
+  const bool soa = (flags & RK_SOA) != 0;
+  if (soa && ld < n) return RK_ERR_INVALID_ARG;
+  FanucP<S> P = make_params<S>(robot, flags);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (soa) {
+    int grid = persistent_grid(fanuc_fk_jac_soa_kernel<S>, kBlock, 0, n);
+    fanuc_fk_jac_soa_kernel<S><<<grid, kBlock, 0, st>>>(P, q, n, ld, T, J, det);
+  } else {
+    int grid = persistent_grid(fanuc_fk_jac_aos_kernel<S>, kBlock, 0, n);
+    fanuc_fk_jac_aos_kernel<S><<<grid, kBlock, 0, st>>>(P, q, n, T, J, det);
+  }
+  return check_launch();
+}
+
+template <typename S>
+static int launch_ik(const RkFanuc* robot, const S* T, int64_t n, int64_t ld, int flags,
+                     const int8_t* branches, int nb, S* q_out, uint8_t* valid, void* stream) {
+  if (!robot || !T || !q_out || !valid || n < 0 || nb < 1 || nb > 16) return RK_ERR_INVALID_ARG;
+  if (!branches && nb != 8) return RK_ERR_INVALID_ARG;
+  if (n == 0) return RK_OK;
+  const bool soa = (flags & RK_SOA) != 0;
+  if (soa && ld < n) return RK_ERR_INVALID_ARG;
+  FanucP<S> P = make_params<S>(robot, flags);
+  cudaStream_t st = (cudaStream_t)stream;
+  bool canonical = (branches == nullptr);
+  if (branches && nb == 8) {
+    canonical = true;
+    int b = 0;
+    for (int m = 1; m >= -1; m -= 2)
+      for (int k = 1; k >= -1; k -= 2)
+        for (int w = 0; w <= 1; ++w, ++b)
+          if (branches[b * 3] != m || branches[b * 3 + 1] != k || branches[b * 3 + 2] != w)
+            canonical = false;
+  }
+  if (canonical) {
+    if (soa) {
+      int grid = persistent_grid(fanuc_ik8_kernel<S, true>, kBlock, 0, n * 4);
+      fanuc_ik8_kernel<S, true><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
+    } else {
+      int grid = persistent_grid(fanuc_ik8_kernel<S, false>, kBlock, 0, n * 4);
+      fanuc_ik8_kernel<S, false><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
+    }
+    return check_launch();
+  }
+  BranchList BL;
+  BL.nb = nb;
+  for (int b = 0; b < nb; ++b) {
+    int m = branches[b * 3], k = branches[b * 3 + 1], w = branches[b * 3 + 2];
+    if (m != 1 && m != -1) m = 1;               // fanuc.py:210-212
+    if (k != 1 && k != -1) k = 1;               // :214-216
+    if (w != 1 && w != -1 && w != 0) w = 1;     // :218-220
+    BL.mkw[b * 3] = (int8_t)m, BL.mkw[b * 3 + 1] = (int8_t)k, BL.mkw[b * 3 + 2] = (int8_t)w;
+  }
+  if (soa) {
+    int grid = persistent_grid(fanuc_ik_list_kernel<S, true>, kBlock, 0, n * nb);
+    fanuc_ik_list_kernel<S, true><<<grid, kBlock, 0, st>>>(P, BL, T, n, ld, q_out, valid);
+  } else {
+    int grid = persistent_grid(fanuc_ik_list_kernel<S, false>, kBlock, 0, n * nb);
+    fanuc_ik_list_kernel<S, false><<<grid, kBlock, 0, st>>>(P, BL, T, n, ld, q_out, valid);
+  }
+  return check_launch();
+}
+
+}  // namespace rk
+
+extern "C" {
+
+int rk_fanuc_fk_jac_f64(const RkFanuc* robot, const double* q, int64_t n, int64_t ld, int flags,
+                        double* T, double* J, double* det, void* stream) {
+  return rk::launch_fk_jac<double>(robot, q, n, ld, flags, T, J, det, stream);
+}
+int rk_fanuc_fk_jac_f32(const RkFanuc* robot, const float* q, int64_t n, int64_t ld, int flags,
+                        float* T, float* J, float* det, void* stream) {
+  return rk::launch_fk_jac<float>(robot, q, n, ld, flags, T, J, det, stream);
+}
+int rk_fanuc_ik_f64(const RkFanuc* robot, const double* T, int64_t n, int64_t ld, int flags,
+                    const int8_t* branches_mkw, int nb, double* q_out, uint8_t* valid,
+                    void* stream) {
+  return rk::launch_ik<double>(robot, T, n, ld, flags, branches_mkw, nb, q_out, valid, stream);
+}
+int rk_fanuc_ik_f32(const RkFanuc* robot, const float* T, int64_t n, int64_t ld, int flags,
+                    const int8_t* branches_mkw, int nb, float* q_out, uint8_t* valid,
+                    void* stream) {
+  return rk::launch_ik<float>(robot, T, n, ld, flags, branches_mkw, nb, q_out, valid, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,202 @@
+"""Fanuc165F: drop-in for robots/fanuc.py of the reference, with batched B200 kernels.
+
+Same constructor, attributes and single-pose methods as the reference
+(robots/fanuc.py:16-302); the single-pose methods run a 1-element batch through the
+same CUDA kernels (there is no CPU path).  New: `forward_kinematics_batch`,
+`inverse_kinematics_batch`, `jacobian_batch`.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _batch, _lib
+from .robot import Robot
+
+#: the canonical 8 branches, in the order every batched IK call returns them
+CANONICAL_8 = tuple((m, k, w) for m in (1, -1) for k in (1, -1) for w in (0, 1))
+#: all 12 combinations the reference's signature admits (w in {0, 1, -1})
+ALL_12 = tuple((m, k, w) for m in (1, -1) for k in (1, -1) for w in (0, 1, -1))
+
+_DTYPES = {torch.float64: "f64", torch.float32: "f32"}
+
+
+class Fanuc165F(Robot):
+    """Fanuc165F forward / inverse kinematics.
+
+    Attributes mirror the reference: qs_lim_deg, qs_lim_rad, qs_offsets, qs_directions,
+    d, dq, T_base, T_tool, epsilon (robots/fanuc.py:21-41)."""
+
+    qs_lim_deg = ((-185.0, 185.0),
+                  (-60.0, 76.0),
+                  (-156.0, 156.0),
+                  (-360.0, 360.0),
+                  (-125.0, 125.0),
+                  (-360.0, 360.0))
+
+    def __init__(self, T_base=None, T_tool=None,
+                 lengths=None, save=True, offsets=None, directions=None):
+        """Same arguments as robots/fanuc.py:43-44.  `save` is accepted for
+        compatibility: there is nothing to cache (the robot is a ~700-byte constant
+        block passed to each launch, not pickled SymPy matrices)."""
+        self.set_transforms(T_base, T_tool)
+        self.set_lengths(lengths)
+        self.set_joint_offsets(offsets)
+        self.set_joint_directions(directions)
+        self._generate_value_pairs()
+        self._calculate_limits_radians()
+        self._save = save
+
+    def set_lengths(self, lengths):
+        if lengths is None:
+            self._ls = (346.0, 324.0, 312.0, 1075.0, 225.0, 1280.0, 215.0)  # fanuc.py:73
+        else:
+            self._ls = lengths
+
+    def set_joint_offsets(self, offsets):
+        if offsets is None:
+            angle = np.pi / 2
+            self.qs_offsets = np.array([0.0, -angle, angle, 0.0, 0.0, 0.0])  # fanuc.py:79-80
+        else:
+            self.qs_offsets = offsets
+
+    def set_joint_directions(self, directions):
+        if directions is None:
+            self.qs_directions = np.array([1, 1, -1, -1, -1, -1])           # fanuc.py:86
+        else:
+            self.qs_directions = directions
+
+    def _generate_value_pairs(self):
+        """d, dq of the TzTx -> Ry Tx Ry^-1 substitution (fanuc.py:90-104)."""
+        self._value_pairs = [(f"l_{i}", self._ls[i]) for i in range(len(self._ls))]
+        self.d = np.sqrt(self._ls[4] * self._ls[4] + self._ls[5] * self._ls[5])
+        self.dq = np.arctan2(self._ls[4], self._ls[5])
+        self._value_pairs.append(("d", self.d))
+        self._value_pairs.append(("dq", self.dq))
+
+    def _calculate_limits_radians(self):
+        self.qs_lim_rad = tuple(
+            (np.deg2rad(x[0]), np.deg2rad(x[1])) for x in self.qs_lim_deg)   # fanuc.py:110-111
+
+    # ------------------------------------------------------------------ C-ABI struct
+    def _struct(self):
+        st = _lib.RkFanuc()
+        _lib.fill(st.l, self._ls)
+        _lib.fill(st.offsets, self.qs_offsets)
+        _lib.fill(st.directions, self.qs_directions)
+        lim = np.asarray(self.qs_lim_rad, dtype=np.float64)
+        _lib.fill(st.lim_lo, lim[:, 0])
+        _lib.fill(st.lim_hi, lim[:, 1])
+        st.d, st.dq, st.eps = float(self.d), float(self.dq), float(self.epsilon)
+        self._fill_transforms(st)
+        return st
+
+    # ------------------------------------------------------------------ batched API
+    def forward_kinematics_batch(self, q, *, jacobian=False, measure=False,
+                                 layout="auto", user_angles=False):
+        """FK (+ 6x6 Jacobian, + det J) for a batch of joint vectors.
+
+        q: CUDA tensor, logical shape [N, 6], float64 or float32.  A transposed view
+        of a contiguous [6, N] tensor is consumed as SOA without a copy.
+        Returns T [N,4,4]; with jacobian=True also J [N,6,6] (columns w.r.t. the
+        model angles q' = q*dir + off, the convention of fanuc_jacobians.py, unless
+        user_angles=True); with measure=True also det J [N] (|det| = manipulability).
+        """
+        _lib.require_cuda(q, "q")
+        if q.dtype not in _DTYPES:
+            raise TypeError("q must be float64 or float32")
+        if layout == "auto":
+            layout = _batch.detect_layout(q, 6)
+        qs, ld = _batch.prep_input(q, 6, layout, q.dtype)
+        n = qs.shape[0]
+        dev = qs.device
+        T, Ts = _batch.alloc_out(n, (4, 4), layout, q.dtype, dev)
+        J = Js = det = None
+        if jacobian:
+            J, Js = _batch.alloc_out(n, (6, 6), layout, q.dtype, dev)
+        if measure:
+            det = torch.empty(n, dtype=q.dtype, device=dev)
+        flags = _batch.flags_of(layout) | (_lib.RK_JAC_USER_ANGLES if user_angles else 0)
+        fn = getattr(_lib.load(), "rk_fanuc_fk_jac_" + _DTYPES[q.dtype])
+        with torch.cuda.device(dev):
+            _lib.check(fn(C.byref(self._struct()), _lib.ptr(qs), n, ld, flags, _lib.ptr(Ts),
+                          _lib.ptr(Js), _lib.ptr(det), _lib.stream_ptr(dev)))
+        out = (T,)
+        if jacobian:
+            out += (J,)
+        if measure:
+            out += (det,)
+        return out if len(out) > 1 else T
+
+    def jacobian_batch(self, q, *, layout="auto", user_angles=False):
+        """6x6 Jacobian and det J only (no pose traffic)."""
+        _lib.require_cuda(q, "q")
+        if layout == "auto":
+            layout = _batch.detect_layout(q, 6)
+        qs, ld = _batch.prep_input(q, 6, layout, q.dtype)
+        n, dev = qs.shape[0], qs.device
+        J, Js = _batch.alloc_out(n, (6, 6), layout, q.dtype, dev)
+        det = torch.empty(n, dtype=q.dtype, device=dev)
+        flags = _batch.flags_of(layout) | (_lib.RK_JAC_USER_ANGLES if user_angles else 0)
+        fn = getattr(_lib.load(), "rk_fanuc_fk_jac_" + _DTYPES[q.dtype])
+        with torch.cuda.device(dev):
+            _lib.check(fn(C.byref(self._struct()), _lib.ptr(qs), n, ld, flags, None,
+                          _lib.ptr(Js), _lib.ptr(det), _lib.stream_ptr(dev)))
+        return J, det
+
+    def inverse_kinematics_batch(self, T, branches=CANONICAL_8, *, layout="auto"):
+        """Pieper IK over `branches` (list of (m, k, w)) for a batch of poses.
+
+        T: CUDA tensor [N,4,4] (a permuted view of a contiguous [16, N] is SOA).
+        Returns (q [N, B, 6], valid [N, B] bool); branch order = `branches`; failed
+        branches hold the reference's all-zero sentinel."""
+        _lib.require_cuda(T, "T")
+        if T.dtype not in _DTYPES:
+            raise TypeError("T must be float64 or float32")
+        n = T.shape[0]
+        T2 = T.reshape(n, 16) if T.dim() == 3 else T
+        if layout == "auto":
+            layout = _batch.detect_layout(T2, 16)
+        Ts, ld = _batch.prep_input(T2, 16, layout, T.dtype)
+        dev = Ts.device
+        nb = len(branches)
+        br = (C.c_int8 * (3 * nb))(*[int(v) for b in branches for v in b])
+        if layout == "soa":
+            qstore = torch.empty((nb * 6, n), dtype=T.dtype, device=dev)
+            vstore = torch.empty((nb, n), dtype=torch.uint8, device=dev)
+            qv = qstore.view(nb, 6, n).permute(2, 0, 1)
+            vv = vstore.t()
+        else:
+            qstore = torch.empty((n, nb, 6), dtype=T.dtype, device=dev)
+            vstore = torch.empty((n, nb), dtype=torch.uint8, device=dev)
+            qv, vv = qstore, vstore
+        fn = getattr(_lib.load(), "rk_fanuc_ik_" + _DTYPES[T.dtype])
+        with torch.cuda.device(dev):
+            _lib.check(fn(C.byref(self._struct()), _lib.ptr(Ts), n, ld, _batch.flags_of(layout),
+                          br, nb, _lib.ptr(qstore), _lib.ptr(vstore), _lib.stream_ptr(dev)))
+        return qv, vv.bool()
+
+    # ------------------------------------------------------------- reference methods
+    def forward_kinematics(self, q_values, plot=True):
+        """robots/fanuc.py:151-179.  Returns a 4x4 np.ndarray.  `plot` is accepted and
+        ignored (plotting is outside the accelerated path)."""
+        q = torch.tensor(np.asarray(q_values, dtype=np.float64).reshape(1, 6), device="cuda")
+        T = self.forward_kinematics_batch(q, layout="aos")
+        return T[0].cpu().numpy()
+
+    def inverse_kinematics(self, T, m=1, k=1, w=0):
+        """robots/fanuc.py:196-302.  Returns np.ndarray[6], zeros on failure."""
+        if abs(m) != 1:
+            print("[WARNING] m can only be -1 or 1. Defaulting to 1")
+            m = 1
+        if abs(k) != 1:
+            print("[WARNING] k can only be -1 or 1. Defaulting to 1")
+            k = 1
+        if abs(w) != 1 and w != 0:
+            print("[WARNING] w can only be -1, 0 or 1. Defaulting to 1")
+            w = 1
+        Tt = torch.tensor(np.array(T, dtype=np.float64).reshape(1, 4, 4), device="cuda")
+        q, valid = self.inverse_kinematics_batch(Tt, [(m, k, w)], layout="aos")
+        if not bool(valid[0, 0]):
+            print("[INFO] The configuration is not reachable or a joint is out of limits")
+        return q[0, 0].cpu().numpy()

@@ -1,0 +1,243 @@
+"""GPU parity: Fanuc165F kernels (through the C ABI) vs the NumPy oracle and the golden
+vectors of the real reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TB = np.array([[1, 0, 0, 500], [0, 1, 0, 300], [0, 0, 1, -100], [0, 0, 0, 1.0]])
+TT = np.array([[1, 0, 0, 100], [0, 1, 0, 0], [0, 0, 1, -300], [0, 0, 0, 1.0]])
+
+
+def robots(golden):
+    from roboticmanipulators_b200.robots.fanuc import Fanuc165F
+    g = golden("fanuc_fk_ik.npz")
+    return [
+        ("default", Fanuc165F(), O.FanucConst()),
+        ("translated", Fanuc165F(T_base=TB, T_tool=TT), O.FanucConst(TB, TT)),
+        ("rotated", Fanuc165F(T_base=g["rotated_T_base"], T_tool=g["rotated_T_tool"]),
+         O.FanucConst(g["rotated_T_base"], g["rotated_T_tool"])),
+    ]
+
+
+def rand_q(n, seed=0):
+    c = O.FanucConst()
+    rng = np.random.default_rng(seed)
+    return rng.uniform(c.lim[:, 0], c.lim[:, 1], size=(n, 6))
+
+
+def scaled_err(a, b, scale):
+    return float(np.max(np.abs(a - b) / scale))
+
+
+def check_fk_jac(T, J, det, q, c, tol):
+    T_ref = O.fanuc_fk(q, c)
+    J_ref = O.fanuc_jacobian(q, c)
+    # parity metric of SURVEY section 7: per-block scaled max error
+    assert np.max(np.abs(T[:, :3, :3] - T_ref[:, :3, :3])) < tol
+    pscale = np.maximum(1.0, np.abs(T_ref[:, :3, 3]).max(axis=1))[:, None]
+    assert scaled_err(T[:, :3, 3], T_ref[:, :3, 3], pscale) < tol
+    assert np.array_equal(T[:, 3], np.tile([0, 0, 0, 1.0], (len(q), 1)))
+    vscale = np.maximum(1.0, np.abs(J_ref[:, :3]).max(axis=(1, 2)))[:, None, None]
+    assert scaled_err(J[:, :3], J_ref[:, :3], vscale) < tol
+    assert np.max(np.abs(J[:, 3:] - J_ref[:, 3:])) < tol
+    det_ref = np.linalg.det(J_ref)
+    colscale = np.prod(np.linalg.norm(J_ref, axis=1), axis=1)
+    assert np.all(np.abs(det - det_ref) <= tol * np.maximum(colscale, 1.0))
+
+
+@pytest.mark.parametrize("layout", ["aos", "soa"])
+def test_fk_jac_f64_parity(golden, layout):
+    q = rand_q(10000)                       # BASELINE config 1: 1e4 uniform-in-limit configs
+    for name, robot, c in robots(golden):
+        qt = torch.tensor(q, device="cuda")
+        T, J, det = robot.forward_kinematics_batch(qt, jacobian=True, measure=True, layout=layout)
+        assert T.shape == (10000, 4, 4) and J.shape == (10000, 6, 6)
+        check_fk_jac(T.cpu().numpy(), J.cpu().numpy(), det.cpu().numpy(), q, c, 1e-12)
+
+
+def test_fk_ragged_and_empty(golden):
+    _, robot, c = robots(golden)[2]
+    for n in (1, 2, 31, 33, 127, 129, 1000):
+        q = rand_q(n, seed=n)
+        for layout in ("aos", "soa"):
+            T, J, det = robot.forward_kinematics_batch(torch.tensor(q, device="cuda"),
+                                                       jacobian=True, measure=True, layout=layout)
+            check_fk_jac(T.cpu().numpy(), J.cpu().numpy(), det.cpu().numpy(), q, c, 1e-12)
+    T = robot.forward_kinematics_batch(torch.empty((0, 6), dtype=torch.float64, device="cuda"))
+    assert T.shape == (0, 4, 4)
+
+
+def test_fk_soa_view_is_zero_copy(golden):
+    _, robot, c = robots(golden)[0]
+    q = rand_q(4096, seed=3)
+    store = torch.tensor(q.T.copy(), device="cuda")        # [6, N] planes
+    T, J, det = robot.forward_kinematics_batch(store.t(), jacobian=True, measure=True)
+    assert T.stride(0) == 1                                 # SOA result view
+    check_fk_jac(T.cpu().numpy(), J.cpu().numpy(), det.cpu().numpy(), q, c, 1e-12)
+
+
+def test_fk_jac_f32_parity(golden):
+    q = rand_q(10000, seed=5)
+    for name, robot, c in robots(golden):
+        for layout in ("aos", "soa"):
+            qt = torch.tensor(q, device="cuda", dtype=torch.float32)
+            T, J, det = robot.forward_kinematics_batch(qt, jacobian=True, measure=True, layout=layout)
+            assert T.dtype == torch.float32
+            q32 = qt.cpu().numpy().astype(np.float64)
+            T_ref, J_ref = O.fanuc_fk(q32, c), O.fanuc_jacobian(q32, c)
+            T, J = T.cpu().numpy().astype(np.float64), J.cpu().numpy().astype(np.float64)
+            # north_star: 1e-5 in FP32 (scaled per block)
+            assert np.max(np.abs(T[:, :3, :3] - T_ref[:, :3, :3])) < 1e-5
+            ps = np.maximum(1.0, np.abs(T_ref[:, :3, 3]).max(axis=1))[:, None]
+            assert scaled_err(T[:, :3, 3], T_ref[:, :3, 3], ps) < 1e-5
+            vs = np.maximum(1.0, np.abs(J_ref[:, :3]).max(axis=(1, 2)))[:, None, None]
+            assert scaled_err(J[:, :3], J_ref[:, :3], vs) < 1e-5
+            assert np.max(np.abs(J[:, 3:] - J_ref[:, 3:])) < 1e-5
+
+
+def test_fk_golden_reference(golden):
+    g = golden("fanuc_fk_ik.npz")
+    for name, robot, c in robots(golden):
+        q, Tg = g[f"{name}_q"], g[f"{name}_T"]
+        T = robot.forward_kinematics_batch(torch.tensor(q, device="cuda")).cpu().numpy()
+        assert np.max(np.abs(T[:, :3, :3] - Tg[:, :3, :3])) < 1e-12
+        assert np.max(np.abs(T[:, :3, 3] - Tg[:, :3, 3]) / np.maximum(1, np.abs(Tg[:, :3, 3]))) < 1e-12
+
+
+def test_jacobian_golden_and_singular_configs(golden):
+    from roboticmanipulators_b200.robots.fanuc import Fanuc165F
+    g = golden("fanuc_jacobian.npz")
+    # goldens are in MODEL angles; a robot with zero offsets and unit directions maps q = q'
+    robot = Fanuc165F(offsets=np.zeros(6), directions=np.ones(6))
+    qm = g["qm"]
+    J, det = robot.jacobian_batch(torch.tensor(qm, device="cuda"))
+    J, det = J.cpu().numpy(), det.cpu().numpy()
+    Jg = g["default_J"]
+    assert np.max(np.abs(J[:, 3:] - Jg[:, 3:])) < 1e-12
+    assert np.max(np.abs(J[:, :3] - Jg[:, :3]) / np.maximum(1, np.abs(Jg[:, :3]).max())) < 1e-12
+    assert abs(det[0] - 270295653.8623566) / 270295653.8623566 < 1e-12
+    scale = np.prod(np.linalg.norm(Jg[:6], axis=1), axis=1)
+    assert np.all(np.abs(det[:6] - g["det_symbolic_first6"]) <= 1e-12 * scale)
+    assert det[1] == 0.0                                                     # rotation singularity
+
+
+def _cmp_ik(q, valid, q_ref, v_ref, tol=1e-12):
+    assert np.array_equal(valid, v_ref)
+    assert np.array_equal(np.isnan(q), np.isnan(q_ref))
+    assert not np.any(q[~valid])                      # zeros sentinel on failure
+    d = q - q_ref
+    d[..., [3, 5]] = (d[..., [3, 5]] + np.pi) % (2 * np.pi) - np.pi   # atan2 cut at +-pi
+    err = np.abs(d) / np.maximum(1.0, np.abs(q_ref))
+    return float(np.nanmax(err)) if err.size else 0.0
+
+
+@pytest.mark.parametrize("layout", ["aos", "soa"])
+def test_ik8_parity(golden, layout):
+    q = rand_q(10000, seed=2)
+    for name, robot, c in robots(golden):
+        T = O.fanuc_fk(q, c)
+        T[::100, :3, 3] *= 3.0                         # 1 % unreachable targets
+        q_ref, v_ref = O.fanuc_ik_branches(T, O.CANONICAL_8, c)
+        qg, vg = robot.inverse_kinematics_batch(torch.tensor(T, device="cuda"), layout=layout)
+        assert qg.shape == (10000, 8, 6) and vg.shape == (10000, 8)
+        err = _cmp_ik(qg.cpu().numpy(), vg.cpu().numpy(), q_ref, v_ref)
+        assert err < 1e-9, (name, err)
+        # the tight bound holds away from the acos/atan2 ill-conditioned corners
+        assert np.nanpercentile(np.abs(qg.cpu().numpy() - q_ref), 99) < 1e-12
+
+
+def test_ik12_list_and_ragged(golden):
+    from roboticmanipulators_b200.robots.fanuc import ALL_12
+    for name, robot, c in robots(golden):
+        for n in (1, 7, 8, 9, 250):
+            q = rand_q(n, seed=10 + n)
+            T = O.fanuc_fk(q, c)
+            q_ref, v_ref = O.fanuc_ik_branches(T, ALL_12, c)
+            for layout in ("aos", "soa"):
+                qg, vg = robot.inverse_kinematics_batch(torch.tensor(T, device="cuda"), ALL_12, layout=layout)
+                assert _cmp_ik(qg.cpu().numpy(), vg.cpu().numpy(), q_ref, v_ref) < 1e-9
+            q8, v8 = robot.inverse_kinematics_batch(torch.tensor(T, device="cuda"))
+            idx = [ALL_12.index(b) for b in O.CANONICAL_8]
+            assert _cmp_ik(q8.cpu().numpy(), v8.cpu().numpy(), q_ref[:, idx], v_ref[:, idx]) < 1e-9
+
+
+def test_ik_golden_reference(golden):
+    g = golden("fanuc_fk_ik.npz")
+    br = [tuple(int(v) for v in b) for b in g["branches12"]]
+    for name, robot, c in robots(golden):
+        for key in ([name] if name != "default" else ["default", "extra"]):
+            T, ref = g[f"{key}_T"], g[f"{key}_ik12"]
+            qg, vg = robot.inverse_kinematics_batch(torch.tensor(T, device="cuda"), br)
+            qg = qg.cpu().numpy()
+            assert np.array_equal(np.isnan(qg), np.isnan(ref))
+            d = qg - ref
+            d[..., [3, 5]] = (d[..., [3, 5]] + np.pi) % (2 * np.pi) - np.pi
+            assert np.nanmax(np.abs(d)) < 2e-10
+            ref_fail = ~np.any(ref != 0, axis=-1) & ~np.isnan(ref).any(-1)
+            assert np.array_equal(~vg.cpu().numpy() | ~np.any(qg != 0, -1), ref_fail | ~np.any(ref != 0, -1))
+
+
+def test_ik_f32_masks(golden):
+    _, robot, c = robots(golden)[0]
+    q = rand_q(5000, seed=4)
+    T = O.fanuc_fk(q, c)
+    T32 = torch.tensor(T, device="cuda", dtype=torch.float32)
+    qg, vg = robot.inverse_kinematics_batch(T32)
+    q_ref, v_ref = O.fanuc_ik_branches(T32.cpu().numpy().astype(np.float64), O.CANONICAL_8, c)
+    agree = (vg.cpu().numpy() == v_ref).mean()
+    assert agree > 0.995                               # FP32 thresholds: SURVEY section 7
+    both = vg.cpu().numpy() & v_ref
+    d = qg.cpu().numpy().astype(np.float64) - q_ref
+    d[..., [3, 5]] = (d[..., [3, 5]] + np.pi) % (2 * np.pi) - np.pi
+    assert np.nanpercentile(np.abs(d[both]), 99) < 2e-3
+
+
+def test_scalar_api_matches_reference_tests(golden, capsys):
+    """tests/test_robots.py of the reference, through the drop-in single-pose API."""
+    from roboticmanipulators_b200.robots.fanuc import Fanuc165F
+    robot = Fanuc165F()
+    T = robot.forward_kinematics([0, 0, 0, 0, 0, 0], plot=False)
+    assert np.allclose(T, [[1, 0, 0, 1807], [0, 1, 0, 0], [0, 0, 1, 1970], [0, 0, 0, 1]], atol=1e-9)
+    T = robot.forward_kinematics([np.pi / 2, 0, 0, 0, 0, 0], plot=False)
+    assert np.allclose(T, [[0, -1, 0, 0], [1, 0, 0, 1807], [0, 0, 1, 1970], [0, 0, 0, 1]], atol=1e-9)
+    T = robot.forward_kinematics([1.570796, -0.28, 0.1, 0, 0.2, 0], plot=False)
+    for m in (1, -1):
+        qs = robot.inverse_kinematics(T, m=m)
+        assert np.all(np.abs(robot.forward_kinematics(qs, plot=False) - T) <= robot.epsilon)
+    assert not robot.inverse_kinematics(robot.forward_kinematics([0] * 6, plot=False), m=1).any()
+    unreachable = np.array([[1, 0, 0, 100000], [0, 1, 0, 2882], [0, 0, 1, 895], [0, 0, 0, 1.0]])
+    assert not robot.inverse_kinematics(unreachable, m=1).any()
+    limit = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 100], [0, 0, 0, 1.0]])
+    assert not robot.inverse_kinematics(limit, m=1).any()
+    # fanuc_kinematics.py round trip with base/tool
+    r2 = Fanuc165F(T_base=TB, T_tool=TT)
+    qs = [-0.485, 0.5, -0.23, 0.23, 0.21, 0.213]
+    T = r2.forward_kinematics(qs, plot=False)
+    assert abs(T[0, 3] - 2281.1504233665910) < 1e-9
+    assert np.allclose(r2.inverse_kinematics(T, m=-1, w=1), qs, atol=1e-12)
+    assert not r2.inverse_kinematics(T, m=5, k=1, w=0).any()     # m defaults to 1 -> out of limits
+    assert "[WARNING] m can only be -1 or 1" in capsys.readouterr().out
+
+
+def test_large_batch_roundtrip_property():
+    """Size-independent property at 2^22 poses: every valid k=+1 branch FK-round-trips."""
+    from roboticmanipulators_b200.robots.fanuc import Fanuc165F
+    robot = Fanuc165F()
+    n = 1 << 22
+    g = torch.Generator(device="cuda").manual_seed(1)
+    lim = torch.tensor(np.asarray(robot.qs_lim_rad), device="cuda")
+    store = torch.rand((6, n), generator=g, device="cuda", dtype=torch.float64)
+    store = lim[:, :1] + store * (lim[:, 1:] - lim[:, :1])
+    T = robot.forward_kinematics_batch(store.t())
+    qb, vb = robot.inverse_kinematics_batch(T)
+    assert 0.8 < vb.any(dim=1).double().mean().item() < 0.95
+    for b in (0, 1, 4, 5):                                    # k = +1 branches
+        ok = vb[:, b] & ~torch.isnan(qb[:, b]).any(dim=1)
+        T2 = robot.forward_kinematics_batch(qb[:, b][ok].contiguous())
+        err = (T2 - T[ok]).abs().amax(dim=(1, 2))
+        assert err.max().item() < 1e-6
+        assert err.median().item() < 1e-9
