@@ -172,6 +172,21 @@ int rk_chain_fk_jac_f64(const RkChain* chain, const double* values, int nvals, i
  * ---------------------------------------------------------------------------------- */
 #define RK_MAX_TRAJ_JOINTS 8
 
+/* TrapezoidalGenerator.generate_coefficients (trapezoidal_generator.py:36-79) for n scalar
+ * moves: t1[i], tau[i] from (q0[i], qf[i]) under (v_max, a_max, control_freq). */
+int rk_trap_coefficients_f64(const double* q0, const double* qf, int64_t n, double v_max,
+                             double a_max, double control_freq, double* t1, double* tau,
+                             void* stream);
+
+/* TrapezoidalGenerator.get_q / get_dq / get_ddq / get_t (trapezoidal_generator.py:110-227)
+ * for nprof profiles with explicit state: q_init, the CURRENT velocity / acceleration
+ * limits (set_current_limits, :81-93), t_1 and tau.  Outputs [nprof][nsteps] padded with
+ * zeros; len[i] = the reference's sample count (0 when it raises).  Any of q, dq, ddq, t
+ * may be NULL. */
+int rk_trap_sample_f64(const double* q_init, const double* v_cur, const double* a_cur,
+                       const double* t1, const double* tau, int64_t nprof, int nsteps, double* q,
+                       double* dq, double* ddq, double* t, int32_t* len, void* stream);
+
 /* TrajectoryGenerator.generate_p2p_trajectory / _generate_equalized_profiles
  * (trajectory_generator.py:71-92,118-159) over ntraj trajectories of nj joints:
  * per-joint generate_coefficients (trapezoidal_generator.py:36-79), equalisation

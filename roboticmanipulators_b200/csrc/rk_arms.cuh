@@ -1,0 +1,177 @@
+// Device functions for the 3R spatial arm (RRRRobot) and the 2R planar arm (RRRobot),
+// shared by the pose kernels (rk_arms.cu) and the trajectory kernels (rk_traj.cu).
+#pragma once
+#include "rk_common.cuh"
+
+namespace rk {
+
+struct ArmP {
+  double l[3], lo[3], hi[3], eps;
+  double Tb[12], Tt[12], Tbi[12], Tti[12];
+  int has_base, has_tool;
+};
+
+ArmP make_arm_params(const RkArm* r);
+
+// Apply T_tool on the right and T_base on the left of a local pose (R columns-major
+// 3x3 row-major array, origin On) and of NC Jacobian columns; write T (16) and J (6 x NC).
+template <int NC>
+__device__ __forceinline__ void arm_finish(const ArmP& P, double (&R)[9], V3<double> On,
+                                           V3<double> (&jv)[NC], V3<double> (&jw)[NC],
+                                           const V3<double> (&Ok)[NC], double (&T)[16],
+                                           double (&J)[6 * NC]) {
+  if (P.has_tool) {
+    V3<double> pt = {P.Tt[3], P.Tt[7], P.Tt[11]};
+    V3<double> dv = rot(R, pt);
+    On = {On.x + dv.x, On.y + dv.y, On.z + dv.z};
+    double Rn[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        Rn[i * 3 + j] = R[i * 3] * P.Tt[j] + R[i * 3 + 1] * P.Tt[4 + j] + R[i * 3 + 2] * P.Tt[8 + j];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = Rn[i];
+  }
+#pragma unroll
+  for (int k = 0; k < NC; ++k) jv[k] = cross(jw[k], sub(On, Ok[k]));  // u x (O_n - O_k)
+  if (P.has_base) {
+    const double Rb[9] = {P.Tb[0], P.Tb[1], P.Tb[2], P.Tb[4], P.Tb[5], P.Tb[6], P.Tb[8], P.Tb[9], P.Tb[10]};
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      jv[k] = rot(Rb, jv[k]);
+      jw[k] = rot(Rb, jw[k]);
+    }
+    V3<double> p = rot(Rb, On);
+    On = {p.x + P.Tb[3], p.y + P.Tb[7], p.z + P.Tb[11]};
+    double Rn[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        Rn[i * 3 + j] = Rb[i * 3] * R[j] + Rb[i * 3 + 1] * R[3 + j] + Rb[i * 3 + 2] * R[6 + j];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = Rn[i];
+  }
+  T[0] = R[0], T[1] = R[1], T[2] = R[2], T[3] = On.x;
+  T[4] = R[3], T[5] = R[4], T[6] = R[5], T[7] = On.y;
+  T[8] = R[6], T[9] = R[7], T[10] = R[8], T[11] = On.z;
+  T[12] = 0.0, T[13] = 0.0, T[14] = 0.0, T[15] = 1.0;
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    J[0 * NC + k] = jv[k].x, J[1 * NC + k] = jv[k].y, J[2 * NC + k] = jv[k].z;
+    J[3 * NC + k] = jw[k].x, J[4 * NC + k] = jw[k].y, J[5 * NC + k] = jw[k].z;
+  }
+}
+
+// RRRRobot.forward_kinematics (rrr_robot.py:96-120): Rz(q0) Tz(l0) Ry(q1) Tx(l1) Ry(q2) Tx(l2)
+__device__ __forceinline__ void rrr_fk_jac_pose(const ArmP& P, const double (&q)[3], double (&T)[16],
+                                                double (&J)[18]) {
+  double s0, c0, s1, c1, s2, c2;
+  sincos(q[0], &s0, &c0);
+  sincos(q[1], &s1, &c1);
+  sincos(q[2], &s2, &c2);
+  const double c12 = c1 * c2 - s1 * s2, s12 = s1 * c2 + c1 * s2;
+  const double l0 = P.l[0], l1 = P.l[1], l2 = P.l[2];
+  const V3<double> y1 = {-s0, c0, 0.0};
+  const V3<double> x3 = {c12 * c0, c12 * s0, -s12};
+  const V3<double> z3 = {s12 * c0, s12 * s0, c12};
+  const double rho2 = l1 * c1, h2 = l0 - l1 * s1;
+  const double rho3 = rho2 + l2 * c12, h3 = h2 - l2 * s12;
+  V3<double> On = {rho3 * c0, rho3 * s0, h3};
+  double R[9] = {x3.x, y1.x, z3.x, x3.y, y1.y, z3.y, x3.z, y1.z, z3.z};
+  V3<double> jv[3], jw[3] = {{0.0, 0.0, 1.0}, y1, y1};
+  const V3<double> Ok[3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, l0}, {rho2 * c0, rho2 * s0, h2}};
+  arm_finish<3>(P, R, On, jv, jw, Ok, T, J);
+}
+
+// RRRobot.forward_kinematics (rr_robot.py:102-126): Rz(q0) Tx(l0) Rz(q1) Tx(l1)
+__device__ __forceinline__ void rr_fk_jac_pose(const ArmP& P, const double (&q)[2], double (&T)[16],
+                                               double (&J)[12]) {
+  double s0, c0, s1, c1;
+  sincos(q[0], &s0, &c0);
+  sincos(q[1], &s1, &c1);
+  const double c01 = c0 * c1 - s0 * s1, s01 = s0 * c1 + c0 * s1;
+  const double l0 = P.l[0], l1 = P.l[1];
+  V3<double> On = {l0 * c0 + l1 * c01, l0 * s0 + l1 * s01, 0.0};
+  double R[9] = {c01, -s01, 0.0, s01, c01, 0.0, 0.0, 0.0, 1.0};
+  V3<double> jv[2], jw[2] = {{0.0, 0.0, 1.0}, {0.0, 0.0, 1.0}};
+  const V3<double> Ok[2] = {{0.0, 0.0, 0.0}, {l0 * c0, l0 * s0, 0.0}};
+  arm_finish<2>(P, R, On, jv, jw, Ok, T, J);
+}
+
+// translation of T_0 = T_base^-1 T T_tool^-1 (rrr_robot.py:159, rr_robot.py:162)
+__device__ __forceinline__ void arm_ik_p0(const ArmP& P, const double (&Tin)[12], double (&p0)[3]) {
+  double A[12], B[12];
+  if (P.has_base) {
+    xf_mul(P.Tbi, Tin, A);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) A[i] = Tin[i];
+  }
+  if (P.has_tool) {
+    xf_mul(A, P.Tti, B);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) B[i] = A[i];
+  }
+  p0[0] = B[3], p0[1] = B[7], p0[2] = B[11];
+}
+
+// RRRRobot.inverse_kinematics (rrr_robot.py:137-201); zeros + false on failure.
+__device__ __forceinline__ bool rrr_ik_branch(const ArmP& P, const double (&p0)[3], int m, int k,
+                                              double (&qo)[3]) {
+  using M = Sc<double>;
+  const double fm = (double)m, fk = (double)k;
+  const double l0 = P.l[0], l1 = P.l[1], l2 = P.l[2];
+  const double x = p0[0], y = p0[1], z = p0[2];
+  qo[0] = qo[1] = qo[2] = 0.0;
+  const double xp = M::mul(fk, M::sqrt(M::add(M::mul(x, x), M::mul(y, y))));   // :162
+  const double zp = M::sub(l0, z);                                             // :163
+  const double num = M::sub(M::sub(M::add(M::mul(xp, xp), M::mul(zp, zp)), M::mul(l1, l1)),
+                            M::mul(l2, l2));                                   // :165-166
+  const double cc = M::div(num, M::mul(M::mul(2.0, l1), l2));                  // :167-168
+  if (fabs(cc) > 1.0) return false;                                            // :171
+  const double q2 = fm * acos(cc);                                             // :175
+  double s2, c2;
+  sincos(q2, &s2, &c2);
+  const double beta = atan2(l2 * (fm * s2), l1 + l2 * c2);                     // :177-178
+  const double q1 = M::sub(atan2(zp, xp), M::mul(fm, beta));                   // :179
+  const double A = l1 * cos(q1) + l2 * cos(M::add(q1, q2));                    // :181
+  const double q0 = (fabs(A) < P.eps) ? 0.0 : atan2(y, x);                     // :183-187
+  const double qs[3] = {q0, q1, q2};
+  bool out = false;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) out = out || (qs[j] < P.lo[j]) || (qs[j] > P.hi[j]);  // :191-196
+  if (out) return false;
+  qo[0] = q0, qo[1] = q1, qo[2] = q2;
+  return true;
+}
+
+// RRRobot.inverse_kinematics (rr_robot.py:147-195)
+__device__ __forceinline__ bool rr_ik_branch(const ArmP& P, const double (&p0)[3], int m,
+                                             double (&qo)[2]) {
+  using M = Sc<double>;
+  const double fm = (double)m;
+  const double l0 = P.l[0], l1 = P.l[1];
+  const double x = p0[0], y = p0[1];
+  qo[0] = qo[1] = 0.0;
+  const double num = M::sub(M::sub(M::add(M::mul(x, x), M::mul(y, y)), M::mul(l0, l0)),
+                            M::mul(l1, l1));                                   // :167
+  const double cc = M::div(num, M::mul(M::mul(2.0, l0), l1));                  // :168-169
+  if (fabs(cc) > 1.0) return false;                                            // :172
+  const double q1 = fm * acos(cc);                                             // :176
+  double s1, c1;
+  sincos(q1, &s1, &c1);
+  const double beta = atan2(l1 * (fm * s1), l0 + l1 * c1);                     // :177-178
+  const double q0 = M::sub(atan2(y, x), M::mul(fm, beta));                     // :179
+  const double qs[2] = {q0, q1};
+  bool out = false;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) out = out || (qs[j] < P.lo[j]) || (qs[j] > P.hi[j]);
+  if (out) return false;
+  qo[0] = q0, qo[1] = q1;
+  return true;
+}
+
+}  // namespace rk

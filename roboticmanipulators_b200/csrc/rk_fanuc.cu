@@ -447,8 +447,9 @@ fanuc_ik_list_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant_
 template <typename S>
 static int launch_fk_jac(const RkFanuc* robot, const S* q, int64_t n, int64_t ld, int flags, S* T,
                          S* J, S* det, void* stream) {
-  if (!robot || !q || n < 0) return RK_ERR_INVALID_ARG;
+  if (!robot || n < 0) return RK_ERR_INVALID_ARG;
   if (n == 0) return RK_OK;
+  if (!q) return RK_ERR_INVALID_ARG;
   const bool soa = (flags & RK_SOA) != 0;
   if (soa && ld < n) return RK_ERR_INVALID_ARG;
   FanucP<S> P = make_params<S>(robot, flags);
@@ -466,9 +467,10 @@ static int launch_fk_jac(const RkFanuc* robot, const S* q, int64_t n, int64_t ld
 template <typename S>
 static int launch_ik(const RkFanuc* robot, const S* T, int64_t n, int64_t ld, int flags,
                      const int8_t* branches, int nb, S* q_out, uint8_t* valid, void* stream) {
-  if (!robot || !T || !q_out || !valid || n < 0 || nb < 1 || nb > 16) return RK_ERR_INVALID_ARG;
+  if (!robot || n < 0 || nb < 1 || nb > 16) return RK_ERR_INVALID_ARG;
   if (!branches && nb != 8) return RK_ERR_INVALID_ARG;
   if (n == 0) return RK_OK;
+  if (!T || !q_out || !valid) return RK_ERR_INVALID_ARG;
   const bool soa = (flags & RK_SOA) != 0;
   if (soa && ld < n) return RK_ERR_INVALID_ARG;
   FanucP<S> P = make_params<S>(robot, flags);

@@ -1,0 +1,166 @@
+"""CPU tests of the host-side logic: token algebra (the reference's tests/test_robo_math.py
+cases), symbolic Jacobians (tests/test_jacobians.py), the model reducer against the real
+reference's outputs, constants of the robots, trapezoid coefficients."""
+import numpy as np
+import pytest
+import sympy as sp
+
+from roboticmanipulators_b200.robots import Fanuc165F, RRRobot, RRRRobot
+from roboticmanipulators_b200.utils.jacobians import JacobianCalculator
+from roboticmanipulators_b200.utils.model_calibration import ModelCalibrator
+from roboticmanipulators_b200.utils.polynomial_generator import PolynomialGenerator
+from roboticmanipulators_b200.utils.robo_math import SymbolicTransformation as st
+from roboticmanipulators_b200.utils.robo_math import TOKENS, Transformation as tf
+from roboticmanipulators_b200.utils.trapezoidal_generator import TrapezoidalGenerator
+
+
+def test_elementary_matrices_match_reference(golden):
+    g = golden("generic_chain.npz")
+    for tok in TOKENS:
+        assert np.allclose(np.array(tf(tok, [0.7]).transformation, dtype=float),
+                           g[f"elem_{tok}"], rtol=0, atol=1e-16), tok
+    assert np.array_equal(np.array(tf.get_Rx(0), dtype=float), np.eye(4))
+    assert np.allclose(np.array(tf.get_Rz_from_degrees(90), dtype=float),
+                       [[0, -1, 0, 0], [1, 0, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], atol=1e-15)
+    assert tf.get_Tx(3) == sp.Matrix([[1, 0, 0, 3], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]])
+    assert tf.get_Ty_inv(2)[1, 3] == -2
+    T = tf("TxTyTz", [1.0, 1.2, 0.7]).transformation        # reference test_robo_math.py:198-208
+    assert (T[0, 3], T[1, 3], T[2, 3]) == (1.0, 1.2, 0.7)
+    with pytest.raises(ValueError):
+        tf("TxTy", [1.0])
+    with pytest.raises(ValueError):
+        tf("Qx", [1.0])
+
+
+def test_chain_against_reference_golden(golden):
+    g = golden("generic_chain.npz")
+    for c in range(int(g["n_cases"])):
+        seq = str(g[f"c{c}_seq"])
+        for v, T in zip(g[f"c{c}_vals"], g[f"c{c}_T"]):
+            assert np.allclose(np.array(tf(seq, list(v)).transformation, dtype=float), T, atol=1e-13)
+
+
+def test_symbolic_transformation_api():
+    s = st("RzTx")
+    assert s.variables == ["q_0", "d_0"]
+    q, d = sp.symbols("q_0 d_0")
+    assert sp.simplify(s.transformation[0, 3] - d * sp.cos(q)) == 0
+    assert len(s.frames) == 2
+    inv = s.inv()
+    assert inv._seq == "TxiRzi" and inv.variables == ["d_0", "q_0"]
+    assert s.inv().inv()._seq == "RzTx"
+    assert np.allclose(np.array(sp.simplify(s.transformation * inv.transformation), dtype=float), np.eye(4))
+    s2 = st("TzRx", ["l", "a"])
+    s2.substitute([("l", 2.0)])
+    assert s2.transformation[2, 3] == 2.0
+    val = s2.evaluate_tuples([("a", 0.5)])
+    assert abs(float(val[1, 1]) - np.cos(0.5)) < 1e-15
+    assert (s * s2)._seq == "RzTxTzRx"
+    assert st.get_Rx_inv("a") == st.get_Rx("a").T
+    t = sp.Symbol("t")
+    assert st("Rz", f_of_t=[True]).transformation[0, 0] == sp.cos(sp.Function("q_0")(t))
+    with pytest.raises(ValueError):
+        st("RzTx", ["only_one"])
+    with pytest.raises(ValueError):
+        st("Wz")
+    assert st("RzTzTxRyTxRyRyiTx").inv()._seq == "TxiRyRyiTxiRyiTxiTziRzi"
+
+
+def test_symbolic_jacobian_methods_agree():
+    """tests/test_jacobians.py:10-57 of the reference."""
+    for seq, ind in (("RzTx", [1, 0]), ("RzTxRzTx", [1, 0, 1, 0]), ("RzTxRzTxTyRz", [1, 1, 1, 1, 0, 1])):
+        jc = JacobianCalculator(seq, ind, simplify=False)
+        diff = sp.simplify(jc.calculate_scew() - jc.calculate_numeric())
+        assert np.allclose(np.array(diff, dtype=float), 0)
+    T_base = sp.Matrix([[1, 0, 0, 3], [0, 1, 0, 6], [0, 0, 1, -9], [0, 0, 0, 1]])
+    T_tool = sp.Matrix([[0, 1, 0, 2], [1, 0, 0, -4], [0, 0, 1, 6], [0, 0, 0, 1]])
+    jc = JacobianCalculator("RzTxRzTx", [1, 0, 1, 0], T_base=T_base, T_tool=T_tool)
+    diff = sp.simplify(jc.calculate_scew() - jc.calculate_numeric())
+    assert np.allclose(np.array(diff, dtype=float), 0)
+    with pytest.raises(ValueError):
+        JacobianCalculator("RzTx", [1])
+
+
+def test_reduced_models_match_reference(golden):
+    g = golden("reduced_models.npz")
+    for nm, seq, ind in (("rr", "RzTxRzTx", [1, 0, 1, 0]),
+                         ("rrr", "RzTzRyTxRyTx", [1, 0, 1, 0, 1, 0]),
+                         ("fanuc13", "TzRzTzTxRyTxRyTzTxRxRyRxTx",
+                          [0, 1, 0, 0, 1, 0, 1, 0, 0, 1, 1, 1, 0])):
+        m = ModelCalibrator(seq, ind, None, None)
+        m.verbose = False
+        s, v = m.get_reduced_model()
+        assert s == str(g[f"{nm}_seq"])
+        assert v == list(g[f"{nm}_vars"])
+        assert m._r_par == list(g[f"{nm}_par"])
+        assert list(m._r_j_ind) == list(g[f"{nm}_j_ind"])
+        assert [str(x) for x in m._r_nom_par] == list(g[f"{nm}_nom"])
+
+
+def fanuc_calibrator():
+    mc = ModelCalibrator(
+        "TzRzTxRyTxRyTxTzRxRyRxTx", joint_indices=[0, 1, 0, 1, 0, 1, 0, 0, 1, 1, 1, 0],
+        variables=['d_1', 'q_1', 'd_2', 'q_2', 'd_3', 'q_3', 'd_4', 'd_5', 'q_4', 'q_5', 'q_6', 'd_6'],
+        link_lengths=[('d_1', 670), ('d_2', 312), ('d_3', 1075), ('d_5', 225), ('d_4', 1280), ("d_6", 215)],
+        offsets=np.array([0.0, -np.pi / 2, np.pi / 2, 0.0, 0.0, 0.0]),
+        directions=np.array([1, 1, -1, -1, -1, -1]))
+    mc.verbose = False
+    return mc
+
+
+def test_fanuc_calibration_model_and_compile(golden):
+    g = golden("calibration.npz")
+    mc = fanuc_calibrator()
+    assert mc.estimate_parameters(None, None) == ([], [])       # model not built yet
+    s, v = mc.get_reduced_model()
+    assert s == str(g["r_seq"]) == "RzTxTyRxRyRyTxRxRzRyRyTxTzRzRxRxTyTzRzRyRyTzRzRx"
+    assert v == list(g["r_vars"]) and mc._r_par == list(g["r_par"])
+    assert mc._to_base == ["Tz"] and mc._to_tool == ["Tx"]
+    assert mc._n_params == 18
+    m = mc._compile(np.zeros(18), np.eye(4), [np.eye(4)] * 3)
+    assert (m.njoints, m.nparams, m.ntools) == (6, 18, 3)
+    assert list(m.param_joint)[:18] == [0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4]
+    assert list(m.joint_axis)[:6] == [2, 1, 1, 0, 1, 0]
+    assert m.seg[0][3] == 312.0 and m.seg[2][3] == 1280.0 and m.seg[2][11] == 225.0
+    # nominal token values feed _prepare_evaluation exactly like the reference
+    vals = mc._prepare_evaluation(g["qs"][0])
+    assert len(vals) == 24 and vals[1] == 312.0
+
+
+def test_robot_constants_match_reference(golden):
+    g = golden("fanuc_fk_ik.npz")
+    r = Fanuc165F()
+    assert float(r.d) == float(g["d"]) and float(r.dq) == float(g["dq"])
+    assert np.array_equal(np.asarray(r.qs_lim_rad), g["qs_lim_rad"])
+    assert r.epsilon == 1e-5
+    assert r.T_base == sp.eye(4)
+    st_ = r._struct()
+    assert st_.has_base == 0 and st_.l[5] == 1280.0 and st_.directions[2] == -1.0
+    r2 = Fanuc165F(T_base=g["rotated_T_base"], T_tool=g["rotated_T_tool"])
+    s2 = r2._struct()
+    assert s2.has_base == 1 and s2.has_tool == 1
+    Tb = np.vstack([np.array(list(s2.T_base)).reshape(3, 4), [0, 0, 0, 1]])
+    Tbi = np.vstack([np.array(list(s2.T_base_inv)).reshape(3, 4), [0, 0, 0, 1]])
+    assert np.allclose(Tb @ Tbi, np.eye(4), atol=1e-12)
+    assert RRRRobot.ls == (1.0, 1.0, 1.0) and RRRobot()._ls == (0.8, 0.8)
+    assert RRRobot(lengths=(0.5, 1.25))._struct().l[1] == 1.25
+
+
+def test_trapezoid_coefficients_host(golden):
+    g = golden("trajectories.npz")
+    for (v, a, f, q0, qf), ref in zip(g["coef_cases"], g["coef_out"]):
+        tg = TrapezoidalGenerator(v, a, control_freq=int(f))
+        assert tuple(float(x) for x in tg.generate_coefficients(q0, qf)) == tuple(ref)
+    tg = TrapezoidalGenerator(dq_max=1, ddq_max=10)
+    tg.set_limits(2, 2)
+    assert np.allclose(tg.generate_coefficients(0, 5), (1.0, 2.5))     # reference test_generator
+    tg.set_frequency(5)
+    assert np.allclose(tg.generate_coefficients(0, 5), (1.0, 2.6))     # test_generator_frequency
+
+
+def test_polynomial_generator():
+    """tests/test_polynomial_generator.py of the reference."""
+    pg = PolynomialGenerator()
+    coefs = pg.generate_coefficients([0, 0, 0], [1, 0, 0], 1.0)
+    assert np.allclose(coefs, [0, 0, 0, 10, -15, 6])
+    assert np.allclose(pg.dpolynomial_from_coefs(0, coefs, 0, 1, 11), pg.polynomial_from_coefs(coefs, 0, 1, 11))
