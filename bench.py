@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=1 << 20)
     ap.add_argument("--layout", default="soa", choices=["soa", "aos"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--cpu-sample", type=int, default=200000)
+    ap.add_argument("--cpu-sample", type=int, default=500000)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -264,7 +264,8 @@ def main():
     out["fp64"] = W.fp64_probe()
     if not args.no_cpu:
         procs = 1
-        v, dt = cpu_poses_per_s(args.cpu_sample, procs) if wl.cpu is None else wl.cpu(args)
+        v, dt = cpu_poses_per_s(args.cpu_sample, procs) if getattr(wl, "cpu", None) is None \
+            else wl.cpu(args)
         out["cpu_baseline"] = {
             "value": v, "unit": wl.unit, "cores": procs, "kind": "port",
             "sample": wl.cpu_sample_desc(args, dt)}

@@ -167,7 +167,240 @@ class FanucWorkload:
                 f"{dt:.1f} s")
 
 
+class CalibWorkload:
+    """BASELINE config 5: one calibration iteration = J^T J / J^T r reduction over the
+    rank's shard of measurements (+ the 190-double all-reduce) + the 18x18 host solve."""
+    unit = "measurements/s"
+    metric = "calibration normal-equation measurements/s (Fanuc reduced model, fp64)"
+    cpu = None
+
+    def __init__(self, args, rank, world):
+        import torch.distributed as dist
+        from roboticmanipulators_b200.utils.model_calibration import ModelCalibrator
+        from roboticmanipulators_b200.utils.robo_math import chain_batch
+        self.args, self.world = args, world
+        self.m = m = args.batch if args.batch != (1 << 26) else (100_000_000 // world)
+        self.units_per_step = m
+        mc = ModelCalibrator(
+            "TzRzTxRyTxRyTxTzRxRyRxTx", [0, 1, 0, 1, 0, 1, 0, 0, 1, 1, 1, 0],
+            ['d_1', 'q_1', 'd_2', 'q_2', 'd_3', 'q_3', 'd_4', 'd_5', 'q_4', 'q_5', 'q_6', 'd_6'],
+            [('d_1', 670), ('d_2', 312), ('d_3', 1075), ('d_5', 225), ('d_4', 1280), ("d_6", 215)],
+            offsets=np.array([0.0, -np.pi / 2, np.pi / 2, 0.0, 0.0, 0.0]),
+            directions=np.array([1, 1, -1, -1, -1, -1]))
+        mc.verbose = False
+        mc.get_reduced_model()
+        self.mc = mc
+        # SURVEY G7 values: the calibrated base/tools and the parameter step of the real data set
+        self.true_p = np.array([1.30610510, -3.29297131, 5.31380935e-4, -2.10034074e-4, 0.545044972,
+                                2.54192873e-4, 6.39792394e-5, -4.30615152e-3, -0.272805100,
+                                -5.07970965, 1.94468834e-3, -2.39723149e-3, -0.358522920,
+                                0.197375190, 4.43141007e-4, 4.43439344e-4, -0.130112096,
+                                1.01596659e-3])
+        est = [-561.306307, -560.988903, 557.860232, -3.06694464e-3, 8.27619470e-3, 5.71090871e-3,
+               417.073077, -17.1212195, 59.7437387, 421.054034, 56.9970287, -15.7799788,
+               420.743893, -43.8505917, -42.4028750]
+        Tb, Tt = mc._compose_base_tools(est)
+        self.T_base = np.array(Tb, dtype=np.float64)
+        self.T_tools = [np.array(t, dtype=np.float64) for t in Tt]
+        dev = torch.device("cuda")
+        g = torch.Generator(device=dev).manual_seed(4 + 1000 * rank)
+        lim = torch.tensor(np.deg2rad(np.array(Fanuc165F.qs_lim_deg)), device=dev)
+        self.q = torch.empty((m, 6), dtype=torch.float64, device=dev)
+        self.pts = torch.empty((m, 9), dtype=torch.float64, device=dev)
+        off = torch.tensor(mc.qs_offsets, device=dev)
+        dirs = torch.tensor(np.asarray(mc.qs_directions, dtype=np.float64), device=dev)
+        pvals = torch.tensor(mc._nominal_values(self.true_p), device=dev)
+        chunk = 1 << 21
+        jpos = [i for i, j in enumerate(mc._r_j_ind) if j]
+        ppos = [i for i, j in enumerate(mc._r_j_ind) if not j]
+        for s in range(0, m, chunk):
+            e = min(m, s + chunk)
+            u = torch.rand((e - s, 6), generator=g, device=dev, dtype=torch.float64)
+            qc = lim[:, 0] + u * (lim[:, 1] - lim[:, 0])
+            self.q[s:e] = qc
+            vals = torch.empty((e - s, len(mc._r_tokens)), dtype=torch.float64, device=dev)
+            vals[:, jpos] = qc * dirs + off
+            vals[:, ppos] = pvals
+            for t, Tt_ in enumerate(self.T_tools):
+                T = chain_batch(mc._r_tokens, vals, T_base=self.T_base, T_tool=Tt_, layout="aos")
+                noise = torch.randn((e - s, 3), generator=g, device=dev, dtype=torch.float64) * 0.0439
+                self.pts[s:e, 3 * t:3 * t + 3] = T[:, :3, 3] + noise
+        torch.cuda.synchronize()
+        self.events, self.params = [], None
+        self.alg_bytes = {"calib_normal_eq": 120}
+        self.traffic = {}
+        self.launches_per_step = 1
+        self.config = {
+            "workload": "fanuc_calibration_normal_equations",
+            "baseline_config": "configs[4]: J^T J / J^T r over synthetic measurements "
+                               "(calibration_dataset.mat shape), all-reduce of 190 doubles, 18x18 solve",
+            "measurements_per_gpu": m, "tools": 3, "params": 18,
+            "l2": "inputs larger than L2 (12 GB of q/pts per pass at 1e8 measurements)",
+            "sharding": "measurements sharded across ranks; one NCCL all-reduce of the packed "
+                        "normal equations per iteration",
+        }
+
+    def step(self, s):
+        timed = s >= 0
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if timed else None
+        if timed:
+            ev[0].record()
+        out = self.mc.normal_equations(self.q, self.pts, self.T_base, self.T_tools,
+                                       parameters=np.zeros(18), process_group=False)
+        if timed:
+            ev[1].record()
+            self.events.append(ev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(out)
+        H, g, _ = self.mc.unpack_normal_equations(out.cpu().numpy(), 18)
+        self.params = np.linalg.inv(H).dot(g)
+
+    def kernel_times_ms(self):
+        return {"calib_normal_eq": float(np.mean([e[0].elapsed_time(e[1]) for e in self.events]))}
+
+    def e2e(self, args):
+        """ModelCalibrator.estimate_parameters with HOST (pinned) q/pts: upload + reduce + solve."""
+        n = min(self.m, 1 << 22)
+        hq = self.q[:n].cpu().pin_memory()
+        hp = self.pts[:n].cpu().pin_memory()
+        steps = 3
+
+        def one():
+            dq = hq.to("cuda", non_blocking=True)
+            dp = hp.to("cuda", non_blocking=True)
+            self.mc._params_iteration = 0
+            return self.mc.estimate_parameters(dq, dp, self.T_base, self.T_tools,
+                                               process_group=False)
+        one()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one()
+        dt = time.perf_counter() - t0
+        return {"seconds": dt, "units": n * steps, "h2d": n * 120, "d2h": 190 * 8, "batch": n,
+                "steps": steps}
+
+    def cpu(self, args):
+        from oracle import np_oracle as O
+        mc = self.mc
+        lens = [('d_1', 670), ('d_2', 312), ('d_3', 1075), ('d_5', 225), ('d_4', 1280), ("d_6", 215)]
+        model = O.CalibModel(mc._r_seq, mc._r_var, mc._r_j_ind, mc._r_nom_par, lens,
+                             mc.qs_offsets, mc.qs_directions)
+        n = 20000
+        q, p = self.q[:n].cpu().numpy(), self.pts[:n].cpu().numpy()
+        t0 = time.perf_counter()
+        O.calib_estimate_parameters(model, q, p, np.zeros(18), self.T_base, self.T_tools)
+        dt = time.perf_counter() - t0
+        self._cpu_n = n
+        return n / dt, dt
+
+    def cpu_sample_desc(self, args, dt):
+        return (f"{self._cpu_n} measurements x 3 tools, oracle calib_estimate_parameters "
+                f"(NumPy restatement of model_calibration.py:381-430), 1 process, {dt:.1f} s")
+
+
+class TrajWorkload:
+    """BASELINE config 4: equalised trapezoidal joint trajectories fused with the RRR forward
+    kinematics and 6x3 Jacobian of every sample."""
+    unit = "samples/s"
+    metric = "RRR trajectory samples/s (p2p trapezoid + FK + Jacobian per sample, fp64)"
+
+    def __init__(self, args, rank, world):
+        from roboticmanipulators_b200.robots import RRRRobot
+        self.args = args
+        self.ntraj = nt = args.batch if args.batch != (1 << 26) else (1 << 17)
+        self.n = 1000
+        self.units_per_step = nt * self.n
+        self.robot = RRRRobot()
+        self.st = self.robot._struct()
+        self.lib = _lib.load()
+        dev = torch.device("cuda")
+        g = torch.Generator(device=dev).manual_seed(3 + 1000 * rank)
+        self.q0 = (torch.rand((nt, 3), generator=g, device=dev, dtype=torch.float64) * 2 - 1) * np.pi
+        self.qf = (torch.rand((nt, 3), generator=g, device=dev, dtype=torch.float64) * 2 - 1) * np.pi
+        f64 = torch.float64
+        self.q, self.dq, self.ddq = (torch.empty((nt, self.n, 3), dtype=f64, device=dev) for _ in range(3))
+        self.t = torch.empty((nt, self.n), dtype=f64, device=dev)
+        self.len = torch.empty(nt, dtype=torch.int32, device=dev)
+        self.T = torch.empty((nt, self.n, 16), dtype=f64, device=dev)
+        self.J = torch.empty((nt, self.n, 18), dtype=f64, device=dev)
+        self.events = []
+        self.alg_bytes = {"rrr_p2p_fk": 352}
+        self.traffic = {}
+        self.launches_per_step = 1
+        self.config = {
+            "workload": "rrr_p2p_trapezoid_fk_jac",
+            "baseline_config": f"configs[3] chunked: {nt} trajectories x 1000 steps per GPU per step "
+                               "(dq_max=1, ddq_max=20, control_freq=10)",
+            "trajectories_per_gpu_per_step": nt, "samples_per_trajectory": self.n,
+            "l2": "outputs larger than L2 (46 GB written per step)",
+            "sharding": "independent trajectories, no collective",
+        }
+
+    def step(self, s):
+        timed = s >= 0
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if timed else None
+        if timed:
+            ev[0].record()
+        _lib.check(self.lib.rk_rrr_p2p_fk_f64(
+            C.byref(self.st), _lib.ptr(self.q0), _lib.ptr(self.qf), self.ntraj, self.n, 1.0, 20.0,
+            10.0, _lib.ptr(self.q), _lib.ptr(self.dq), _lib.ptr(self.ddq), _lib.ptr(self.t),
+            _lib.ptr(self.len), _lib.ptr(self.T), _lib.ptr(self.J), _lib.stream_ptr()))
+        if timed:
+            ev[1].record()
+            self.events.append(ev)
+
+    def kernel_times_ms(self):
+        return {"rrr_p2p_fk": float(np.mean([e[0].elapsed_time(e[1]) for e in self.events]))}
+
+    def e2e(self, args):
+        from roboticmanipulators_b200.utils.trajectory_generator import TrajectoryGenerator
+        tg = TrajectoryGenerator(1, 20, 1, 10, control_freq=10)
+        nt = min(self.ntraj, 2048)
+        h0, hf = self.q0[:nt].cpu().pin_memory(), self.qf[:nt].cpu().pin_memory()
+        hout = [torch.empty(shape, dtype=torch.float64).pin_memory() for shape in
+                [(nt, self.n, 3)] * 3 + [(nt, self.n), (nt, self.n, 4, 4), (nt, self.n, 6, 3)]]
+        hlen = torch.empty(nt, dtype=torch.int32).pin_memory()
+        steps = 3
+
+        def one():
+            a, b = h0.to("cuda", non_blocking=True), hf.to("cuda", non_blocking=True)
+            q, dq, ddq, t, L, T, J = tg.generate_p2p_trajectory_batch(a, b, self.n, robot=self.robot)
+            for h, d in zip(hout, (q, dq, ddq, t, T, J)):
+                h.copy_(d, non_blocking=True)
+            hlen.copy_(L, non_blocking=True)
+            torch.cuda.synchronize()
+        one()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one()
+        dt = time.perf_counter() - t0
+        return {"seconds": dt, "units": nt * self.n * steps, "h2d": nt * 48,
+                "d2h": nt * self.n * 352 + nt * 4, "batch": nt * self.n, "steps": steps}
+
+    def cpu(self, args):
+        from oracle import np_oracle as O
+        nt = 300
+        q0, qf = self.q0[:nt].cpu().numpy(), self.qf[:nt].cpu().numpy()
+        t0 = time.perf_counter()
+        q, dq, ddq, t, L = O.p2p_batch(q0, qf, self.n, 1, 20, 10)
+        O.rrr_fk(q)
+        O.rrr_jacobian(q)
+        dt = time.perf_counter() - t0
+        self._cpu_n = nt
+        return nt * self.n / dt, dt
+
+    def cpu_sample_desc(self, args, dt):
+        return (f"{self._cpu_n} trajectories x 1000 samples: oracle p2p_batch + rrr_fk + rrr_jacobian "
+                f"(NumPy restatement), 1 process, {dt:.1f} s")
+
+
 def make(args, rank, world):
     if args.workload in ("fk_jac_ik", "fk_jac", "ik"):
         return FanucWorkload(args, rank, world)
-    raise SystemExit(f"workload {args.workload} is not available in this build")
+    if args.workload == "calib":
+        return CalibWorkload(args, rank, world)
+    if args.workload == "traj":
+        return TrajWorkload(args, rank, world)
+    raise SystemExit(f"unknown workload {args.workload}")

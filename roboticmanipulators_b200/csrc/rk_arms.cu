@@ -31,7 +31,8 @@ __global__ void __launch_bounds__(kBlock)
 arm_fk_jac_kernel(const __grid_constant__ ArmP P, const double* __restrict__ q, int64_t n,
                   int64_t ld, double* __restrict__ T, double* __restrict__ J) {
   constexpr int NJ = 6 * NQ;
-  __shared__ double stage_all[SOA ? 1 : (kBlock / kWarp) * kWarp * Stride<NJ>::value];
+  constexpr int NST = Stride<NJ>::value > Stride<16>::value ? Stride<NJ>::value : Stride<16>::value;
+  __shared__ double stage_all[SOA ? 1 : (kBlock / kWarp) * kWarp * NST];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t base = (int64_t)blockIdx.x * blockDim.x + warp * kWarp; base < n; base += stride) {
@@ -39,7 +40,7 @@ arm_fk_jac_kernel(const __grid_constant__ ArmP P, const double* __restrict__ q, 
     const int64_t rem = n - base;
     const int cnt = rem < kWarp ? (int)rem : kWarp;
     double qv[NQ], Tv[16], Jv[NJ];
-    double* stage = stage_all + (SOA ? 0 : warp * kWarp * Stride<NJ>::value);
+    double* stage = stage_all + (SOA ? 0 : warp * kWarp * NST);
     if (SOA) {
 #pragma unroll
       for (int k = 0; k < NQ; ++k) qv[k] = (lane < cnt) ? q[k * ld + i] : 0.0;
