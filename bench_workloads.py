@@ -209,7 +209,7 @@ class CalibWorkload:
         self.pts = torch.empty((m, 9), dtype=torch.float64, device=dev)
         off = torch.tensor(mc.qs_offsets, device=dev)
         dirs = torch.tensor(np.asarray(mc.qs_directions, dtype=np.float64), device=dev)
-        pvals = torch.tensor(mc._nominal_values(self.true_p), device=dev)
+        pvals = torch.tensor(mc._nominal_values(self.true_p), dtype=torch.float64, device=dev)
         chunk = 1 << 21
         jpos = [i for i, j in enumerate(mc._r_j_ind) if j]
         ppos = [i for i, j in enumerate(mc._r_j_ind) if not j]

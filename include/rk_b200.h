@@ -296,6 +296,11 @@ int rk_calib_tool_base_eq_f64(const RkCalibModel* model, const double* q, const 
  * thread-lane) executed so the caller can divide by the event time. */
 int rk_probe_dfma(int64_t iters, double* sink, int64_t* total_fma, void* stream);
 
+/* out[i] = the library's internal FP64 atan2(y[i], x[i]) (octant reduction + degree-10
+ * polynomial, used by the IK kernels instead of libm); exposed so the accuracy tests can
+ * compare it against libm over the whole plane. */
+int rk_probe_atan2(const double* y, const double* x, int64_t n, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,11 @@ __global__ void __launch_bounds__(256) dfma_probe_kernel(int64_t iters, double* 
   double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
   if (r == 123.456) sink[0] = r;  // never true; keeps the loop alive
 }
+__global__ void atan2_probe_kernel(const double* y, const double* x, int64_t n, double* out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = fast_atan2(y[i], x[i]);
+}
 }  // namespace rk
 
 extern "C" {
@@ -43,6 +48,14 @@ int rk_probe_dfma(int64_t iters, double* sink, int64_t* total_fma, void* stream)
   const int blocks = sms * 8, threads = 256;
   rk::dfma_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink);
   if (total_fma) *total_fma = (int64_t)blocks * threads * iters * 8;
+  return rk::check_launch();
+}
+
+int rk_probe_atan2(const double* y, const double* x, int64_t n, double* out, void* stream) {
+  if (n < 0) return RK_ERR_INVALID_ARG;
+  if (n == 0) return RK_OK;
+  if (!y || !x || !out) return RK_ERR_INVALID_ARG;
+  rk::atan2_probe_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(y, x, n, out);
   return rk::check_launch();
 }
 

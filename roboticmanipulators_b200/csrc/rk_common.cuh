@@ -57,6 +57,8 @@ struct Sc<double> {
   static __device__ __forceinline__ double cos(double x) { return ::cos(x); }
   static __device__ __forceinline__ double acos(double x) { return ::acos(x); }
   static __device__ __forceinline__ double atan2(double y, double x) { return ::atan2(y, x); }
+  static __device__ __forceinline__ double atan2_fast(double y, double x);
+  static __device__ __forceinline__ double rsqrt_fast(double x);
   static __device__ __forceinline__ double abs(double x) { return ::fabs(x); }
   static __device__ __forceinline__ double pi() { return 3.141592653589793; }
 };
@@ -73,9 +75,84 @@ struct Sc<float> {
   static __device__ __forceinline__ float cos(float x) { return ::cosf(x); }
   static __device__ __forceinline__ float acos(float x) { return ::acosf(x); }
   static __device__ __forceinline__ float atan2(float y, float x) { return ::atan2f(y, x); }
+  static __device__ __forceinline__ float atan2_fast(float y, float x) { return ::atan2f(y, x); }
+  static __device__ __forceinline__ float rsqrt_fast(float x) { return ::rsqrtf(x); }
   static __device__ __forceinline__ float abs(float x) { return ::fabsf(x); }
   static __device__ __forceinline__ float pi() { return 3.14159265358979323846f; }
 };
+
+// ---------------------------------------------------------------------------------
+// Lean FP64 primitives for the FP64-pipe-bound kernels.  CUDA's libm atan2/acos cost
+// ~170 issue slots per call on sm_100a, two thirds of them UMOV/IMAD moves that
+// materialise 64-bit polynomial constants and special-case selects.  Here the polynomial
+// lives in constant memory (FFMA/DFMA take a constant-bank operand directly), the
+// reciprocal is MUFU.RCP64H + two Newton steps, and everything outside the finite,
+// normal range falls back to libm.
+// ---------------------------------------------------------------------------------
+__constant__ double kAtanPoly[11] = {
+    -0x1.5555555555555p-2, 0x1.999999999934ap-3, -0x1.24924924360cbp-3, 0x1.c71c7185314cbp-4,
+    -0x1.745d0b26b83e7p-4, 0x1.3b1262d95579ep-4, -0x1.10fa75382537fp-4, 0x1.dfe61e80903d2p-5,
+    -0x1.a098bb6ba4941p-5, 0x1.41603647c7a7cp-5, -0x1.3a2b7a07caea9p-6};
+
+// 1/x for normal finite x: hardware seed (2^-23) + two Newton iterations (<= 1 ulp).
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
+// 1/sqrt(x) for normal finite x > 0 (<= 1 ulp).
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double hx = 0.5 * x;
+  double e = fma(-hx * r, r, 0.5);
+  r = fma(r, e, r);
+  e = fma(-hx * r, r, 0.5);
+  return fma(r, e, r);
+}
+
+// atan2(y, x), <= 2 ulp for finite normal operands; zeros, infinities, NaN, denormals and
+// huge values take the libm path.  Octant reduction to |u| <= tan(pi/8) with ONE division:
+//   t = min/max;  t > tan(pi/8):  atan t = pi/4 + atan((min - max)/(min + max)).
+// atan(u) = u + u^3 g(u^2), g = degree-10 interpolant at Chebyshev nodes (error 8e-18).
+__device__ __forceinline__ double fast_atan2(double y, double x) {
+  const double ax = fabs(x), ay = fabs(y);
+  const bool swap = ay > ax;
+  const double mx = swap ? ay : ax, mn = swap ? ax : ay;
+  const bool big = mn > 0x1.a827999fcef32p-2 * mx;
+  const double num = big ? mn - mx : mn;
+  const double den = big ? mn + mx : mx;
+  if (!(den > 1e-280 && den < 1e280 && mn > 1e-280)) return ::atan2(y, x);
+  const double r = fast_rcp(den);
+  double u = num * r;
+  u = fma(fma(-den, u, num), r, u);
+  const double s = u * u, s2 = s * s;
+  // even / odd Horner chains in s^2 for instruction-level parallelism
+  double pe = kAtanPoly[10];
+  pe = fma(pe, s2, kAtanPoly[8]);
+  pe = fma(pe, s2, kAtanPoly[6]);
+  pe = fma(pe, s2, kAtanPoly[4]);
+  pe = fma(pe, s2, kAtanPoly[2]);
+  pe = fma(pe, s2, kAtanPoly[0]);
+  double po = kAtanPoly[9];
+  po = fma(po, s2, kAtanPoly[7]);
+  po = fma(po, s2, kAtanPoly[5]);
+  po = fma(po, s2, kAtanPoly[3]);
+  po = fma(po, s2, kAtanPoly[1]);
+  const double p = fma(po, s, pe);
+  double a = fma(u * s, p, u);
+  if (big) a += 0x1.921fb54442d18p-1;           // pi/4
+  if (swap) a = 0x1.921fb54442d18p+0 - a;       // pi/2
+  if (__double2hiint(x) < 0) a = 0x1.921fb54442d18p+1 - a;  // pi
+  return copysign(a, y);
+}
+
+__device__ __forceinline__ double Sc<double>::atan2_fast(double y, double x) { return fast_atan2(y, x); }
+__device__ __forceinline__ double Sc<double>::rsqrt_fast(double x) { return fast_rsqrt(x); }
 
 // 3-vectors as plain scalars keep everything in registers.
 template <typename S>

@@ -1,6 +1,8 @@
 // Fanuc165F batched kernels: K1 fk+jacobian+det, K2 Pieper IK over all branches.
 // One thread owns one pose (K1) or one (pose, elbow/root branch) pair (K2); the screw
 // chain is unrolled in registers.  See include/rk_b200.h for the reference citations.
+#include <cmath>
+
 #include "rk_common.cuh"
 
 namespace rk {
@@ -8,7 +10,7 @@ namespace rk {
 template <typename S>
 struct FanucP {
   S l[7], off[6], dir[6], lo[6], hi[6];
-  S d, dq, eps;
+  S d, dq, eps, cdq, sdq;
   S Tb[12], Tt[12], Tbi[12], Tti[12];
   int has_base, has_tool, user_jac;
 };
@@ -26,6 +28,8 @@ static FanucP<S> make_params(const RkFanuc* r, int flags) {
   p.d = (S)r->d;
   p.dq = (S)r->dq;
   p.eps = (S)r->eps;
+  p.cdq = (S)cos(r->dq);
+  p.sdq = (S)sin(r->dq);
   for (int i = 0; i < 12; ++i) {
     p.Tb[i] = (S)r->T_base[i];
     p.Tt[i] = (S)r->T_tool[i];
@@ -248,7 +252,21 @@ __device__ __forceinline__ void fanuc_ik_t0(const FanucP<S>& P, const S (&Tin)[1
 
 // One (m, k) pair: position solve once, wrist solve once, then one solution per wrist
 // flag w in wl[0..NW).  Writes user-space angles or the all-zero failure sentinel.
-template <typename S, int NW>
+//
+// Transcendental budget.  The reference evaluates acos, 7 atan2 and 8 sin/cos per branch.
+// Every sine/cosine it takes is of an angle that was itself produced by acos/atan2 of
+// known operands (or a sum of such angles), so here they are formed algebraically from
+// those operands (unit vectors + angle-addition products): cos(psi) = psi_cos,
+// sin(psi) = -m sqrt(1 - psi_cos^2), cos(gamma) = x'/|(x',z')|, ...; acos(c) is
+// atan2(sqrt((1-c)(1+c)), c); and r13 / cos(q5) is +-hypot(r12, r13), which makes
+// q4(w=+-1) = -q4(w=0).  That leaves 4 atan2 that depend only on (pose, k) -- acos(c),
+// beta, gamma, q0 -- and 3 per (m,k) -- the wrist.  With PAIRED the two lanes of a pose
+// that share k (m = +1 / -1) compute two of the four shared atan2 each and swap them with
+// one warp shuffle, so a lane evaluates 5 atan2 in total and nothing else transcendental.
+// Differences to the reference's literal evaluation are rounding-level (<= 1e-15), except
+// within 1e-11 of the measure-zero corners where the reference itself divides by
+// cos(a5 - pi) ~ 1e-5.
+template <typename S, int NW, bool PAIRED>
 __device__ __forceinline__ void fanuc_ik_mk(const FanucP<S>& P, const S (&R0)[9], const S (&p0)[3],
                                             int m, int k, const int (&wl)[NW], S (&qout)[NW][6],
                                             bool (&valid)[NW]) {
@@ -256,52 +274,75 @@ __device__ __forceinline__ void fanuc_ik_mk(const FanucP<S>& P, const S (&R0)[9]
   const S fm = (S)m, fk = (S)k;
   const S l1 = P.l[1], l2 = P.l[2], l3 = P.l[3], d = P.d;
   const S x = p0[0], y = p0[1], z = p0[2];
-  // fanuc.py:228-234, evaluated operation by operation (no contraction)
+  // fanuc.py:228-234, evaluated operation by operation (no contraction): these decide
+  // reachability
   const S rxy = M::sqrt(M::add(M::mul(x, x), M::mul(y, y)));
   const S xp = M::sub(M::mul(fk, rxy), l2);
   const S zp = M::sub(l1, z);
-  const S num = M::sub(M::sub(M::add(M::mul(xp, xp), M::mul(zp, zp)), M::mul(d, d)), M::mul(l3, l3));
+  const S rg2 = M::add(M::mul(xp, xp), M::mul(zp, zp));
+  const S num = M::sub(M::sub(rg2, M::mul(d, d)), M::mul(l3, l3));
   const S den = M::mul(M::mul(S(2), d), l3);
   const S psi_cos = M::div(num, den);
-#pragma unroll
-  for (int i = 0; i < NW; ++i) {
-    valid[i] = false;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) qout[i][j] = S(0);
-  }
-  if (M::abs(psi_cos) > S(1)) return;  // fanuc.py:237-239
+  const bool reach = !(M::abs(psi_cos) > S(1));  // fanuc.py:237-239 (NaN goes on, as there)
+  const S c = reach ? psi_cos : S(0);            // unreachable lanes keep computing (discarded)
 
-  const S psi = -fm * M::acos(psi_cos);  // :241
-  S sp, cp;
-  M::sincos(psi, &sp, &cp);
-  const S beta = M::atan2(d * (fm * sp), l3 + d * cp);  // sin(m*psi) = m*sin(psi); :242-243
-  const S gamma = M::atan2(zp, xp);                      // :244
-  S q0 = M::atan2(y, x);                                 // :246
-  const S q1 = M::sub(gamma, M::mul(fm, beta));          // :247
-  const S q2 = M::add(psi, P.dq);                        // :248
-  const S A = d * M::cos(M::add(q1, psi)) + l2 + l3 * M::cos(q1);  // :250-251
-  if (M::abs(A) < P.eps) q0 = S(0);                      // :253-255
+  const S sabs = M::sqrt((S(1) - c) * (S(1) + c));  // sin(acos c) >= 0
+  const S sb = -d * sabs, cb = l3 + d * c;          // beta = atan2(d sin(m psi), l3 + d cos psi)
+  S acosc, beta, gamma, q0;
+  if (PAIRED) {
+    const bool first = (m == 1);
+    const S r1 = M::atan2_fast(first ? sabs : zp, first ? c : xp);
+    const S r2 = M::atan2_fast(first ? sb : y, first ? cb : x);
+    const S o1 = __shfl_xor_sync(0xffffffffu, r1, 2);
+    const S o2 = __shfl_xor_sync(0xffffffffu, r2, 2);
+    acosc = first ? r1 : o1;
+    beta = first ? r2 : o2;
+    gamma = first ? o1 : r1;
+    q0 = first ? o2 : r2;
+  } else {
+    acosc = M::atan2_fast(sabs, c);   // :241  acos(psi_cos)
+    beta = M::atan2_fast(sb, cb);     // :242-243
+    gamma = M::atan2_fast(zp, xp);    // :244
+    q0 = M::atan2_fast(y, x);         // :246
+  }
+  const S psi = -fm * acosc;                      // :241
+  const S q1 = M::sub(gamma, M::mul(fm, beta));   // :247
+  const S q2 = M::add(psi, P.dq);                 // :248
+
+  // unit vectors of gamma, beta, q0
+  // |(sb, cb)|^2 = d^2 + l3^2 + 2 d l3 c = x'^2 + z'^2 (cosine rule), so one rsqrt serves both
+  const bool rg_ok = rg2 > S(1e-200);
+  const S irg = M::rsqrt_fast(rg_ok ? rg2 : S(1));
+  const S cg = rg_ok ? xp * irg : S(1), sg = rg_ok ? zp * irg : S(0);
+  const S cbn = rg_ok ? cb * irg : S(1), sbn = rg_ok ? sb * irg : S(0);
+  const S c1 = cg * cbn + fm * (sg * sbn);        // cos(q1), q1 = gamma - m beta
+  const S s1 = sg * cbn - fm * (cg * sbn);
+  const S sps = -fm * sabs;                        // sin(psi)
+  const S c1p = c1 * c - s1 * sps;                 // cos(q1 + psi)
+  const S s1p = s1 * c + c1 * sps;
+  const S A = d * c1p + l2 + l3 * c1;              // :250-251
+  const bool up = M::abs(A) < P.eps;               // :253-255
+  if (up) q0 = S(0);
+  const bool rxy_ok = rxy > S(1e-100);
+  const S irxy = M::rsqrt_fast(rxy_ok ? rxy * rxy : S(1));
+  const bool deg0 = up || !rxy_ok;
+  const S c0 = deg0 ? S(1) : x * irxy, s0 = deg0 ? S(0) : y * irxy;
+  const S ct = c1p * P.cdq - s1p * P.sdq;          // cos(q1 + q2), q2 = psi + dq
+  const S st = s1p * P.cdq + c1p * P.sdq;
 
   // T_rot = Ry(-dq) T_012^-1 T_0 (:262-264).  Its rotation is Ry(-(q1+q2)) Rz(-q0) R0.
-  S s0, c0, st, ct;
-  M::sincos(q0, &s0, &c0);
-  M::sincos(M::add(q1, q2), &st, &ct);
-  // rows of Rz(-q0) R0
   const S a0 = c0 * R0[0] + s0 * R0[3], a1 = c0 * R0[1] + s0 * R0[4], a2 = c0 * R0[2] + s0 * R0[5];
-  const S b0 = c0 * R0[3] - s0 * R0[0];
   const S r11 = ct * a0 - st * R0[6];
   const S r12 = ct * a1 - st * R0[7];
   const S r13 = ct * a2 - st * R0[8];
-  const S r21 = b0;
+  const S r21 = c0 * R0[3] - s0 * R0[0];
   const S r31 = st * a0 + ct * R0[6];
 
   const bool regular = M::abs(r11 - S(1)) > P.eps;  // :272
-  S a3 = S(0), a5 = S(0);
-  if (regular) {
-    a3 = M::atan2(r21, -r31);  // :273
-    a5 = M::atan2(r12, r13);   // :274
-  }
-  const bool use13 = M::abs(r13) > P.eps;  // :279
+  const bool use13 = M::abs(r13) > P.eps;           // :279
+  const S a3 = M::atan2_fast(r21, -r31);                 // :273
+  const S a5 = M::atan2_fast(r12, r13);                  // :274
+  const S q4p = M::atan2_fast(M::sqrt(r12 * r12 + r13 * r13), r11);  // :280 with w = 0
 #pragma unroll
   for (int i = 0; i < NW; ++i) {
     S q3 = S(0), q4 = S(0), q5 = S(0);
@@ -310,9 +351,9 @@ __device__ __forceinline__ void fanuc_ik_mk(const FanucP<S>& P, const S (&R0)[9]
       q3 = M::sub(a3, wpi);  // :276
       q5 = M::sub(a5, wpi);  // :277
       if (use13)
-        q4 = M::atan2(r13 / M::cos(q5), r11);  // :280
+        q4 = (wl[i] == 0) ? q4p : -q4p;          // :280: r13 / cos(q5) = +-hypot(r12, r13)
       else
-        q4 = M::atan2(r12 / M::sin(q5), r11);  // :282
+        q4 = M::atan2(r12 / M::sin(q5), r11);    // :282 (rare; NaN quirk preserved)
     }
     const S qs[6] = {q0, q1, q2, q3, q4, q5};
     bool out = false;
@@ -322,11 +363,9 @@ __device__ __forceinline__ void fanuc_ik_mk(const FanucP<S>& P, const S (&R0)[9]
       qu[j] = M::mul(M::sub(qs[j], P.off[j]), P.dir[j]);   // :290
       out = out || (qu[j] < P.lo[j]) || (qu[j] > P.hi[j]);  // :292-297 (NaN passes)
     }
-    if (!out) {
-      valid[i] = true;
+    valid[i] = reach && !out;
 #pragma unroll
-      for (int j = 0; j < 6; ++j) qout[i][j] = qu[j];
-    }
+    for (int j = 0; j < 6; ++j) qout[i][j] = valid[i] ? qu[j] : S(0);
   }
 }
 
@@ -340,7 +379,7 @@ __device__ __forceinline__ void load_T12(const S* __restrict__ T, int64_t i, int
 // Branch index b = 4*[m==-1] + 2*[k==-1] + w.  Validity bits of the 4 lanes of a pose
 // are gathered with warp shuffles so one lane writes the pose's 8 validity bytes.
 template <typename S, bool SOA>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 4)
 fanuc_ik8_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict__ T, int64_t n, int64_t ld,
                  S* __restrict__ q_out, uint8_t* __restrict__ valid) {
   constexpr int PPW = kWarp / 4;  // poses per warp
@@ -365,7 +404,7 @@ fanuc_ik8_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict__ T, i
     const int wl[2] = {0, 1};
     S qo[2][6];
     bool ok[2];
-    fanuc_ik_mk<S, 2>(P, R0, p0, m, k, wl, qo, ok);
+    fanuc_ik_mk<S, 2, true>(P, R0, p0, m, k, wl, qo, ok);
 
     // validity: 2 bits per lane -> 8 bytes per pose via shuffles
     const unsigned mine = (ok[0] ? 1u : 0u) | (ok[1] ? 2u : 0u);
@@ -426,7 +465,7 @@ fanuc_ik_list_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant_
     const int wl[1] = {BL.mkw[b * 3 + 2]};
     S qo[1][6];
     bool ok[1];
-    fanuc_ik_mk<S, 1>(P, R0, p0, BL.mkw[b * 3 + 0], BL.mkw[b * 3 + 1], wl, qo, ok);
+    fanuc_ik_mk<S, 1, false>(P, R0, p0, BL.mkw[b * 3 + 0], BL.mkw[b * 3 + 1], wl, qo, ok);
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
       if (SOA)
