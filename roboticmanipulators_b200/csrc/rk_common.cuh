@@ -126,7 +126,10 @@ __device__ __forceinline__ double fast_atan2(double y, double x) {
   const bool big = mn > 0x1.a827999fcef32p-2 * mx;
   const double num = big ? mn - mx : mn;
   const double den = big ? mn + mx : mx;
-  if (!(den > 1e-280 && den < 1e280 && mn > 1e-280)) return ::atan2(y, x);
+  // exponent window test on the high words (den >= mn >= 0): both in [2^-900, 2^+900];
+  // zero, denormal, huge, inf and NaN all fail it
+  const unsigned hd = (unsigned)__double2hiint(den), hm = (unsigned)__double2hiint(mn);
+  if (hd - 0x07b00000u > 0x70800000u || hm < 0x07b00000u) return ::atan2(y, x);
   const double r = fast_rcp(den);
   double u = num * r;
   u = fma(fma(-den, u, num), r, u);

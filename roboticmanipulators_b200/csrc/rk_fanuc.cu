@@ -2,6 +2,7 @@
 // One thread owns one pose (K1) or one (pose, elbow/root branch) pair (K2); the screw
 // chain is unrolled in registers.  See include/rk_b200.h for the reference citations.
 #include <cmath>
+#include <cstdlib>
 
 #include "rk_common.cuh"
 
@@ -371,15 +372,19 @@ __device__ __forceinline__ void fanuc_ik_mk(const FanucP<S>& P, const S (&R0)[9]
 
 template <typename S, bool SOA>
 __device__ __forceinline__ void load_T12(const S* __restrict__ T, int64_t i, int64_t ld, S (&Tin)[12]) {
+  const S* p = SOA ? T + i : T + i * 16;
 #pragma unroll
-  for (int k = 0; k < 12; ++k) Tin[k] = SOA ? T[k * ld + i] : T[i * 16 + k];
+  for (int k = 0; k < 12; ++k) {
+    Tin[k] = __ldcs(p);
+    p += SOA ? ld : 1;
+  }
 }
 
 // Canonical 8 branches: 4 lanes per pose, lane = (pose, (m,k)); each lane emits w = 0, 1.
 // Branch index b = 4*[m==-1] + 2*[k==-1] + w.  Validity bits of the 4 lanes of a pose
 // are gathered with warp shuffles so one lane writes the pose's 8 validity bytes.
-template <typename S, bool SOA>
-__global__ void __launch_bounds__(kBlock, 4)
+template <typename S, bool SOA, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB)
 fanuc_ik8_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict__ T, int64_t n, int64_t ld,
                  S* __restrict__ q_out, uint8_t* __restrict__ valid) {
   constexpr int PPW = kWarp / 4;  // poses per warp
@@ -417,12 +422,15 @@ fanuc_ik8_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict__ T, i
     }
     if (SOA) {
       if (live) {
+        S* qp = q_out + (int64_t)(mk * 12) * ld + i;
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
-          const int b = mk * 2 + w;
 #pragma unroll
-          for (int j = 0; j < 6; ++j) q_out[(int64_t)(b * 6 + j) * ld + i] = qo[w][j];
-          valid[(int64_t)b * ld + i] = ok[w] ? 1 : 0;
+          for (int j = 0; j < 6; ++j) {
+            __stcs(qp, qo[w][j]);
+            qp += ld;
+          }
+          valid[(int64_t)(mk * 2 + w) * ld + i] = ok[w] ? 1 : 0;
         }
       }
     } else {
@@ -525,13 +533,22 @@ static int launch_ik(const RkFanuc* robot, const S* T, int64_t n, int64_t ld, in
             canonical = false;
   }
   if (canonical) {
+    const char* env = getenv("RK_IK_MINB");
+    const int minb = env ? atoi(env) : 4;
+#define RK_LAUNCH_IK8(SOAV, MB)                                                              \
+  {                                                                                         \
+    int grid = persistent_grid(fanuc_ik8_kernel<S, SOAV, MB>, kBlock, 0, n * 4);            \
+    fanuc_ik8_kernel<S, SOAV, MB><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);      \
+  }
     if (soa) {
-      int grid = persistent_grid(fanuc_ik8_kernel<S, true>, kBlock, 0, n * 4);
-      fanuc_ik8_kernel<S, true><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
+      if (minb == 5) RK_LAUNCH_IK8(true, 5)
+      else if (minb == 6) RK_LAUNCH_IK8(true, 6)
+      else if (minb == 3) RK_LAUNCH_IK8(true, 3)
+      else RK_LAUNCH_IK8(true, 4)
     } else {
-      int grid = persistent_grid(fanuc_ik8_kernel<S, false>, kBlock, 0, n * 4);
-      fanuc_ik8_kernel<S, false><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
+      RK_LAUNCH_IK8(false, 4)
     }
+#undef RK_LAUNCH_IK8
     return check_launch();
   }
   BranchList BL;
