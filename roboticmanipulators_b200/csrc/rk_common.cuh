@@ -59,6 +59,7 @@ struct Sc<double> {
   static __device__ __forceinline__ double atan2(double y, double x) { return ::atan2(y, x); }
   static __device__ __forceinline__ double atan2_fast(double y, double x);
   static __device__ __forceinline__ double rsqrt_fast(double x);
+  static __device__ __forceinline__ double sqrt_fast(double x);
   static __device__ __forceinline__ double abs(double x) { return ::fabs(x); }
   static __device__ __forceinline__ double pi() { return 3.141592653589793; }
 };
@@ -77,6 +78,7 @@ struct Sc<float> {
   static __device__ __forceinline__ float atan2(float y, float x) { return ::atan2f(y, x); }
   static __device__ __forceinline__ float atan2_fast(float y, float x) { return ::atan2f(y, x); }
   static __device__ __forceinline__ float rsqrt_fast(float x) { return ::rsqrtf(x); }
+  static __device__ __forceinline__ float sqrt_fast(float x) { return ::sqrtf(x); }
   static __device__ __forceinline__ float abs(float x) { return ::fabsf(x); }
   static __device__ __forceinline__ float pi() { return 3.14159265358979323846f; }
 };
@@ -126,10 +128,6 @@ __device__ __forceinline__ double fast_atan2(double y, double x) {
   const bool big = mn > 0x1.a827999fcef32p-2 * mx;
   const double num = big ? mn - mx : mn;
   const double den = big ? mn + mx : mx;
-  // exponent window test on the high words (den >= mn >= 0): both in [2^-900, 2^+900];
-  // zero, denormal, huge, inf and NaN all fail it
-  const unsigned hd = (unsigned)__double2hiint(den), hm = (unsigned)__double2hiint(mn);
-  if (hd - 0x07b00000u > 0x70800000u || hm < 0x07b00000u) return ::atan2(y, x);
   const double r = fast_rcp(den);
   double u = num * r;
   u = fma(fma(-den, u, num), r, u);
@@ -151,11 +149,28 @@ __device__ __forceinline__ double fast_atan2(double y, double x) {
   if (big) a += 0x1.921fb54442d18p-1;           // pi/4
   if (swap) a = 0x1.921fb54442d18p+0 - a;       // pi/2
   if (__double2hiint(x) < 0) a = 0x1.921fb54442d18p+1 - a;  // pi
-  return copysign(a, y);
+  a = copysign(a, y);
+  // The straight-line path above is valid when den and mn are normal and moderate:
+  // exponent window test on the high words (den >= mn >= 0), both in [2^-900, 2^+900].
+  // Zero, denormal, huge, inf and NaN operands fail it and take libm.  The test comes
+  // LAST so that several independent calls can be interleaved by the scheduler.
+  const unsigned hd = (unsigned)__double2hiint(den), hm = (unsigned)__double2hiint(mn);
+  if (hd - 0x07b00000u > 0x70800000u || hm < 0x07b00000u) a = ::atan2(y, x);
+  return a;
+}
+
+// sqrt(t) for t >= 0 without the IEEE slow-path branch (<= 1 ulp); 0 for t <= 0 or tiny.
+__device__ __forceinline__ double fast_sqrt(double t) {
+  const bool ok = t > 1e-290;
+  const double rs = fast_rsqrt(ok ? t : 1.0);
+  double r = t * rs;
+  r = fma(fma(-r, r, t), 0.5 * rs, r);
+  return ok ? r : 0.0;
 }
 
 __device__ __forceinline__ double Sc<double>::atan2_fast(double y, double x) { return fast_atan2(y, x); }
 __device__ __forceinline__ double Sc<double>::rsqrt_fast(double x) { return fast_rsqrt(x); }
+__device__ __forceinline__ double Sc<double>::sqrt_fast(double x) { return fast_sqrt(x); }
 
 // 3-vectors as plain scalars keep everything in registers.
 template <typename S>

@@ -287,7 +287,7 @@ __device__ __forceinline__ void fanuc_ik_mk(const FanucP<S>& P, const S (&R0)[9]
   const bool reach = !(M::abs(psi_cos) > S(1));  // fanuc.py:237-239 (NaN goes on, as there)
   const S c = reach ? psi_cos : S(0);            // unreachable lanes keep computing (discarded)
 
-  const S sabs = M::sqrt((S(1) - c) * (S(1) + c));  // sin(acos c) >= 0
+  const S sabs = M::sqrt_fast((S(1) - c) * (S(1) + c));  // sin(acos c) >= 0
   const S sb = -d * sabs, cb = l3 + d * c;          // beta = atan2(d sin(m psi), l3 + d cos psi)
   S acosc, beta, gamma, q0;
   if (PAIRED) {
@@ -343,7 +343,7 @@ __device__ __forceinline__ void fanuc_ik_mk(const FanucP<S>& P, const S (&R0)[9]
   const bool use13 = M::abs(r13) > P.eps;           // :279
   const S a3 = M::atan2_fast(r21, -r31);                 // :273
   const S a5 = M::atan2_fast(r12, r13);                  // :274
-  const S q4p = M::atan2_fast(M::sqrt(r12 * r12 + r13 * r13), r11);  // :280 with w = 0
+  const S q4p = M::atan2_fast(M::sqrt_fast(r12 * r12 + r13 * r13), r11);  // :280 with w = 0
 #pragma unroll
   for (int i = 0; i < NW; ++i) {
     S q3 = S(0), q4 = S(0), q5 = S(0);
