@@ -2,7 +2,6 @@
 // One thread owns one pose (K1) or one (pose, elbow/root branch) pair (K2); the screw
 // chain is unrolled in registers.  See include/rk_b200.h for the reference citations.
 #include <cmath>
-#include <cstdlib>
 
 #include "rk_common.cuh"
 
@@ -285,7 +284,8 @@ __device__ __forceinline__ void fanuc_ik_mk(const FanucP<S>& P, const S (&R0)[9]
   const S den = M::mul(M::mul(S(2), d), l3);
   const S psi_cos = M::div(num, den);
   const bool reach = !(M::abs(psi_cos) > S(1));  // fanuc.py:237-239 (NaN goes on, as there)
-  const S c = reach ? psi_cos : S(0);            // unreachable lanes keep computing (discarded)
+  const S c = reach ? psi_cos : S(0.5);          // unreachable lanes keep computing (discarded);
+                                                 // 0.5 keeps their atan2 operands off the libm path
 
   const S sabs = M::sqrt_fast((S(1) - c) * (S(1) + c));  // sin(acos c) >= 0
   const S sb = -d * sabs, cb = l3 + d * c;          // beta = atan2(d sin(m psi), l3 + d cos psi)
@@ -411,14 +411,15 @@ fanuc_ik8_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict__ T, i
     bool ok[2];
     fanuc_ik_mk<S, 2, true>(P, R0, p0, m, k, wl, qo, ok);
 
-    // validity: 2 bits per lane -> 8 bytes per pose via shuffles
-    const unsigned mine = (ok[0] ? 1u : 0u) | (ok[1] ? 2u : 0u);
+    // validity (AOS): 2 bits per lane -> the pose's 8 bytes, gathered with two shuffles
     unsigned long long packed = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      unsigned v = __shfl_sync(0xffffffffu, mine, (lane & ~3) + j);
-      packed |= (unsigned long long)(v & 1u) << (8 * (2 * j));
-      packed |= (unsigned long long)((v >> 1) & 1u) << (8 * (2 * j + 1));
+    if constexpr (!SOA) {
+      const unsigned mine = (ok[0] ? 1u : 0u) | (ok[1] ? 0x100u : 0u);
+      const unsigned other = __shfl_xor_sync(0xffffffffu, mine, 1);
+      const unsigned pair = (mk & 1) ? (other | (mine << 16)) : (mine | (other << 16));
+      const unsigned pair2 = __shfl_xor_sync(0xffffffffu, pair, 2);
+      packed = (mk & 2) ? ((unsigned long long)pair2 | ((unsigned long long)pair << 32))
+                        : ((unsigned long long)pair | ((unsigned long long)pair2 << 32));
     }
     if (SOA) {
       if (live) {
@@ -533,22 +534,15 @@ static int launch_ik(const RkFanuc* robot, const S* T, int64_t n, int64_t ld, in
             canonical = false;
   }
   if (canonical) {
-    const char* env = getenv("RK_IK_MINB");
-    const int minb = env ? atoi(env) : 4;
-#define RK_LAUNCH_IK8(SOAV, MB)                                                              \
-  {                                                                                         \
-    int grid = persistent_grid(fanuc_ik8_kernel<S, SOAV, MB>, kBlock, 0, n * 4);            \
-    fanuc_ik8_kernel<S, SOAV, MB><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);      \
-  }
+    // 128 registers / 4 CTAs per SM measured best (3: 8.1 ms, 4: 7.2 ms, 5: 7.2 ms, 6 spills: 8.1 ms
+    // per 2^25 poses)
     if (soa) {
-      if (minb == 5) RK_LAUNCH_IK8(true, 5)
-      else if (minb == 6) RK_LAUNCH_IK8(true, 6)
-      else if (minb == 3) RK_LAUNCH_IK8(true, 3)
-      else RK_LAUNCH_IK8(true, 4)
+      int grid = persistent_grid(fanuc_ik8_kernel<S, true, 4>, kBlock, 0, n * 4);
+      fanuc_ik8_kernel<S, true, 4><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
     } else {
-      RK_LAUNCH_IK8(false, 4)
+      int grid = persistent_grid(fanuc_ik8_kernel<S, false, 4>, kBlock, 0, n * 4);
+      fanuc_ik8_kernel<S, false, 4><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
     }
-#undef RK_LAUNCH_IK8
     return check_launch();
   }
   BranchList BL;
