@@ -1,0 +1,77 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: contiguous sharding and the
+single all-reduce of the packed calibration normal equations followed by the redundant
+18x18 solve on every rank.  The per-shard partial sums come from the oracle here (the GPU
+kernel that produces them is covered by the -m gpu tests)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_shard_bounds_cover_everything():
+    from roboticmanipulators_b200._shard import shard_bounds
+    for n in (0, 1, 7, 8, 9, 240, 10**9 + 3):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import np_oracle as O
+    from roboticmanipulators_b200._shard import shard_bounds
+    from test_host_logic_cpu import fanuc_calibrator
+    from test_oracle_golden import _calib_model
+    g = np.load(os.path.join(ROOT, "tests", "golden", "calibration.npz"))
+    mc = fanuc_calibrator()
+    mc.get_reduced_model()
+    model = _calib_model(g)
+    lo, hi = shard_bounds(len(g["qs"]), rank, world)
+    H, gv = O.calib_normal_equations(model, g["qs"][lo:hi], g["pts"][lo:hi], np.zeros(18),
+                                     g["T_base"], list(g["T_tools"]))
+    packed = torch.tensor(np.concatenate([H[np.triu_indices(18)], gv, [0.0]]))
+    mc._allreduce(packed, dist.ReduceOp.SUM, None)           # the ONE collective of the path
+    Hs, gs, _ = mc.unpack_normal_equations(packed.numpy(), 18)
+    params = np.linalg.inv(Hs).dot(gs)
+    # the max-type metrics of evaluate() reduce with MAX
+    mx = torch.tensor([float(rank + 1)])
+    mc._allreduce(mx, dist.ReduceOp.MAX, None)
+    q.put((rank, params, float(np.abs(Hs - g["J_sum"]).max() / np.abs(g["J_sum"]).max()), float(mx)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_normal_equation_allreduce():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = np.load(os.path.join(ROOT, "tests", "golden", "calibration.npz"))
+    for rank, params, herr, mx in results:
+        assert herr < 1e-12
+        assert np.max(np.abs(params - g["params"])) < 1e-9     # every rank solves the same system
+        assert mx == 2.0
+    assert np.array_equal(results[0][1], results[1][1])        # bit-identical across ranks
