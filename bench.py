@@ -154,7 +154,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=args._out, flush=True)
 
 
 # --------------------------------------------------------------------------------------
@@ -171,9 +171,16 @@ def main():
     ap.add_argument("--batch", type=int, default=1 << 26, help="poses per GPU per step")
     ap.add_argument("--e2e-batch", type=int, default=1 << 20)
     ap.add_argument("--layout", default="soa", choices=["soa", "aos"])
+    ap.add_argument("--ld-pad", type=int, default=0, help="extra elements between SOA planes")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-sample", type=int, default=500000)
     args = ap.parse_args()
+    # Libraries (NCCL's version banner, torchrun) may write to stdout; the contract is ONE JSON
+    # line there, so everything else is sent to stderr and the line is written to the real fd.
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+    args._out = real_stdout
     if args.impl == "reference":
         return run_reference(args)
 
@@ -269,7 +276,7 @@ def main():
         out["cpu_baseline"] = {
             "value": v, "unit": wl.unit, "cores": procs, "kind": "port",
             "sample": wl.cpu_sample_desc(args, dt)}
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=args._out, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 

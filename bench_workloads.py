@@ -56,10 +56,15 @@ class FanucWorkload:
             g = torch.Generator(device=dev).manual_seed(1 + 1000 * rank + b)
             u = torch.rand((6, n), generator=g, device=dev, dtype=torch.float64)
             u = lim[:, :1] + u * (lim[:, 1:] - lim[:, :1])
+            if self.soa and getattr(args, "ld_pad", 0):
+                up = torch.empty((6, n + args.ld_pad), dtype=torch.float64, device=dev)
+                up[:, :n] = u
+                u = up
             self.q.append(u if self.soa else u.t().contiguous())
             del u
         f64 = torch.float64
-        shape = (lambda c: (c, n)) if self.soa else (lambda c: (n, c))
+        self.ld = n + getattr(args, "ld_pad", 0) if self.soa else n
+        shape = (lambda c: (c, self.ld)) if self.soa else (lambda c: (n, c))
         self.T = torch.empty(shape(16), dtype=f64, device=dev)
         self.J = torch.empty(shape(36), dtype=f64, device=dev) if self.mode != "ik" else None
         self.det = torch.empty(n, dtype=f64, device=dev) if self.mode != "ik" else None
@@ -88,13 +93,13 @@ class FanucWorkload:
     def _k1(self, q, with_j=True):
         st = _lib.stream_ptr()
         _lib.check(self.lib.rk_fanuc_fk_jac_f64(
-            C.byref(self.st), _lib.ptr(q), self.n, self.n, self.flags, _lib.ptr(self.T),
+            C.byref(self.st), _lib.ptr(q), self.n, self.ld, self.flags, _lib.ptr(self.T),
             _lib.ptr(self.J) if with_j else None, _lib.ptr(self.det) if with_j else None, st))
 
     def _k2(self):
         st = _lib.stream_ptr()
         _lib.check(self.lib.rk_fanuc_ik_f64(
-            C.byref(self.st), _lib.ptr(self.T), self.n, self.n, self.flags, None, 8,
+            C.byref(self.st), _lib.ptr(self.T), self.n, self.ld, self.flags, None, 8,
             _lib.ptr(self.qik), _lib.ptr(self.valid), st))
 
     def step(self, s):
@@ -226,7 +231,7 @@ class CalibWorkload:
                 noise = torch.randn((e - s, 3), generator=g, device=dev, dtype=torch.float64) * 0.0439
                 self.pts[s:e, 3 * t:3 * t + 3] = T[:, :3, 3] + noise
         torch.cuda.synchronize()
-        self.events, self.params = [], None
+        self.events, self.params, self.host_ms = [], None, []
         self.alg_bytes = {"calib_normal_eq": 120}
         self.traffic = {}
         self.launches_per_step = 1
@@ -250,13 +255,21 @@ class CalibWorkload:
         if timed:
             ev[1].record()
             self.events.append(ev)
+        t0 = time.perf_counter()
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(out)
-        H, g, _ = self.mc.unpack_normal_equations(out.cpu().numpy(), 18)
+        host = out.cpu().numpy()
+        t1 = time.perf_counter()
+        H, g, _ = self.mc.unpack_normal_equations(host, 18)
         self.params = np.linalg.inv(H).dot(g)
+        if timed:
+            self.host_ms.append((1e3 * (t1 - t0), 1e3 * (time.perf_counter() - t1)))
 
     def kernel_times_ms(self):
+        hm = np.mean(np.array(self.host_ms), axis=0)
+        self.config["step_breakdown_ms"] = {
+            "wait_kernel_allreduce_d2h": float(hm[0]), "unpack_and_18x18_solve": float(hm[1])}
         return {"calib_normal_eq": float(np.mean([e[0].elapsed_time(e[1]) for e in self.events]))}
 
     def e2e(self, args):

@@ -300,6 +300,13 @@ int rk_probe_dfma(int64_t iters, double* sink, int64_t* total_fma, void* stream)
  * polynomial, used by the IK kernels instead of libm); exposed so the accuracy tests can
  * compare it against libm over the whole plane. */
 int rk_probe_atan2(const double* y, const double* x, int64_t n, double* out, void* stream);
+/* Access-pattern ceiling: each thread reads `nin` SOA planes and writes `nout` planes at its
+ * index with 8-byte (vec = 1) or 16-byte (vec = 2) accesses, streaming (cs = 1) or default
+ * stores; used by tools/stream_probe.py to find what K1's 6-in / 53-out pattern can reach. */
+int rk_probe_stream(const double* in, int nin, double* out, int nout, int64_t n, int64_t ld, int vec,
+                    int cs, int blocks_per_sm, void* stream);
+/* s[i], c[i] = the library's internal FP64 sincos(x[i]) (Cody-Waite + polynomials). */
+int rk_probe_sincos(const double* x, int64_t n, double* s, double* c, void* stream);
 
 #ifdef __cplusplus
 }

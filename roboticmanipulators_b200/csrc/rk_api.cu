@@ -21,6 +21,41 @@ __global__ void atan2_probe_kernel(const double* y, const double* x, int64_t n, 
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     out[i] = fast_atan2(y[i], x[i]);
 }
+__global__ void sincos_probe_kernel(const double* x, int64_t n, double* s, double* c) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    fast_sincos(x[i], s + i, c + i);
+}
+// Access-pattern ceiling probe: every thread reads NIN planes and writes NOUT planes at its
+// index (VEC = 1: 8 B per lane, VEC = 2: 16 B per lane), no arithmetic to speak of.
+template <int VEC, bool CS>
+__global__ void __launch_bounds__(128, 4)
+stream_probe_kernel(const double* __restrict__ in, int nin, double* __restrict__ out, int nout,
+                    int64_t n, int64_t ld) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * VEC;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; i < n; i += stride) {
+    double a0 = 0.0, a1 = 0.0;
+    for (int k = 0; k < nin; ++k) {
+      if (VEC == 2) {
+        const double2 v = *reinterpret_cast<const double2*>(in + k * ld + i);
+        a0 += v.x, a1 += v.y;
+      } else {
+        a0 += in[k * ld + i];
+      }
+    }
+#pragma unroll 8
+    for (int k = 0; k < nout; ++k) {
+      if (VEC == 2) {
+        double2 v = make_double2(a0 + k, a1 + k);
+        if (CS) __stcs(reinterpret_cast<double2*>(out + k * ld + i), v);
+        else *reinterpret_cast<double2*>(out + k * ld + i) = v;
+      } else {
+        if (CS) __stcs(out + k * ld + i, a0 + k);
+        else out[k * ld + i] = a0 + k;
+      }
+    }
+  }
+}
 }  // namespace rk
 
 extern "C" {
@@ -48,6 +83,26 @@ int rk_probe_dfma(int64_t iters, double* sink, int64_t* total_fma, void* stream)
   const int blocks = sms * 8, threads = 256;
   rk::dfma_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink);
   if (total_fma) *total_fma = (int64_t)blocks * threads * iters * 8;
+  return rk::check_launch();
+}
+
+int rk_probe_stream(const double* in, int nin, double* out, int nout, int64_t n, int64_t ld, int vec,
+                    int cs, int blocks_per_sm, void* stream) {
+  if (n <= 0 || !in || !out) return RK_ERR_INVALID_ARG;
+  const int grid = 148 * (blocks_per_sm > 0 ? blocks_per_sm : 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec == 2 && cs) rk::stream_probe_kernel<2, true><<<grid, 128, 0, st>>>(in, nin, out, nout, n, ld);
+  else if (vec == 2) rk::stream_probe_kernel<2, false><<<grid, 128, 0, st>>>(in, nin, out, nout, n, ld);
+  else if (cs) rk::stream_probe_kernel<1, true><<<grid, 128, 0, st>>>(in, nin, out, nout, n, ld);
+  else rk::stream_probe_kernel<1, false><<<grid, 128, 0, st>>>(in, nin, out, nout, n, ld);
+  return rk::check_launch();
+}
+
+int rk_probe_sincos(const double* x, int64_t n, double* s, double* c, void* stream) {
+  if (n < 0) return RK_ERR_INVALID_ARG;
+  if (n == 0) return RK_OK;
+  if (!x || !s || !c) return RK_ERR_INVALID_ARG;
+  rk::sincos_probe_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(x, n, s, c);
   return rk::check_launch();
 }
 

@@ -68,9 +68,9 @@ __device__ __forceinline__ void arm_finish(const ArmP& P, double (&R)[9], V3<dou
 __device__ __forceinline__ void rrr_fk_jac_pose(const ArmP& P, const double (&q)[3], double (&T)[16],
                                                 double (&J)[18]) {
   double s0, c0, s1, c1, s2, c2;
-  sincos(q[0], &s0, &c0);
-  sincos(q[1], &s1, &c1);
-  sincos(q[2], &s2, &c2);
+  fast_sincos(q[0], &s0, &c0);
+  fast_sincos(q[1], &s1, &c1);
+  fast_sincos(q[2], &s2, &c2);
   const double c12 = c1 * c2 - s1 * s2, s12 = s1 * c2 + c1 * s2;
   const double l0 = P.l[0], l1 = P.l[1], l2 = P.l[2];
   const V3<double> y1 = {-s0, c0, 0.0};
@@ -89,8 +89,8 @@ __device__ __forceinline__ void rrr_fk_jac_pose(const ArmP& P, const double (&q)
 __device__ __forceinline__ void rr_fk_jac_pose(const ArmP& P, const double (&q)[2], double (&T)[16],
                                                double (&J)[12]) {
   double s0, c0, s1, c1;
-  sincos(q[0], &s0, &c0);
-  sincos(q[1], &s1, &c1);
+  fast_sincos(q[0], &s0, &c0);
+  fast_sincos(q[1], &s1, &c1);
   const double c01 = c0 * c1 - s0 * s1, s01 = s0 * c1 + c0 * s1;
   const double l0 = P.l[0], l1 = P.l[1];
   V3<double> On = {l0 * c0 + l1 * c01, l0 * s0 + l1 * s01, 0.0};
@@ -134,7 +134,7 @@ __device__ __forceinline__ bool rrr_ik_branch(const ArmP& P, const double (&p0)[
   if (fabs(cc) > 1.0) return false;                                            // :171
   const double q2 = fm * acos(cc);                                             // :175
   double s2, c2;
-  sincos(q2, &s2, &c2);
+  fast_sincos(q2, &s2, &c2);
   const double beta = atan2(l2 * (fm * s2), l1 + l2 * c2);                     // :177-178
   const double q1 = M::sub(atan2(zp, xp), M::mul(fm, beta));                   // :179
   const double A = l1 * cos(q1) + l2 * cos(M::add(q1, q2));                    // :181
@@ -162,7 +162,7 @@ __device__ __forceinline__ bool rr_ik_branch(const ArmP& P, const double (&p0)[3
   if (fabs(cc) > 1.0) return false;                                            // :172
   const double q1 = fm * acos(cc);                                             // :176
   double s1, c1;
-  sincos(q1, &s1, &c1);
+  fast_sincos(q1, &s1, &c1);
   const double beta = atan2(l1 * (fm * s1), l0 + l1 * c1);                     // :177-178
   const double q0 = M::sub(atan2(y, x), M::mul(fm, beta));                     // :179
   const double qs[2] = {q0, q1};

@@ -134,7 +134,7 @@ __device__ __forceinline__ void load_joints(const CalibP& P, const double* __res
       const double raw = live ? q[i * P.nj + j] : 0.0;
       const double v = __dadd_rn(__dmul_rn(raw, P.jdir[j]), P.joff[j]);  // model_calibration.py:557
       if (P.jkind[j] == 1)
-        sincos(v, &s[j], &c[j]);
+        fast_sincos(v, &s[j], &c[j]);
       else
         s[j] = v;
     }

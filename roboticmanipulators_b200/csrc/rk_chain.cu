@@ -57,7 +57,7 @@ __device__ __forceinline__ void frame_apply(Frame& F, int op, double v) {
     }
   } else {
     double s, c;
-    sincos(v, &s, &c);
+    fast_sincos(v, &s, &c);
     if (kind == 3) s = -s;  // transpose
     switch (axis) {
       case 0: frame_rotate<0>(F, s, c); break;

@@ -52,7 +52,7 @@ struct Sc<double> {
   static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
   static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
   static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
-  static __device__ __forceinline__ void sincos(double x, double* s, double* c) { ::sincos(x, s, c); }
+  static __device__ __forceinline__ void sincos(double x, double* s, double* c);
   static __device__ __forceinline__ double sin(double x) { return ::sin(x); }
   static __device__ __forceinline__ double cos(double x) { return ::cos(x); }
   static __device__ __forceinline__ double acos(double x) { return ::acos(x); }
@@ -159,6 +159,46 @@ __device__ __forceinline__ double fast_atan2(double y, double x) {
   return a;
 }
 
+// sin and cos together, <= ~1.5 ulp for |x| <= 1e5 (libm beyond that and for NaN/inf).
+// Cody-Waite reduction by pi/2 in three FMA steps, degree-11/12 polynomials in r^2 whose
+// coefficients sit in constant memory, quadrant fix-up with selects.  No branch until the
+// final range test, so the six joint sincos of a pose interleave instead of serialising
+// behind libm's Payne-Hanek branch (K1 went from 873 to ~480 issue slots per pose).
+__constant__ double kSinPoly[6] = {-0x1.5555555555555p-3, 0x1.1111111110b23p-7,  -0x1.a01a019e623afp-13,
+                                   0x1.71de376b9c575p-19, -0x1.ae5fdeb852566p-26, 0x1.5dfb4dfaf15abp-33};
+__constant__ double kCosPoly[6] = {0x1.5555555555555p-5,  -0x1.6c16c16c1691fp-10, 0x1.a01a019f3df42p-16,
+                                   -0x1.27e4fa025e03dp-22, 0x1.1eeb52bea9072p-29, -0x1.906dd38cb66a1p-37};
+
+__device__ __forceinline__ void fast_sincos(double x, double* sp, double* cp) {
+  const double kf = rint(x * 0x1.45f306dc9c883p-1);  // x * 2/pi
+  const int q = (int)kf;
+  double r = fma(-kf, 0x1.921fb54442d18p+0, x);
+  r = fma(-kf, 0x1.1a62633145c07p-54, r);
+  r = fma(-kf, -0x1.f1976b7ed8fbcp-110, r);
+  const double z = r * r;
+  double ps = kSinPoly[5];
+  ps = fma(ps, z, kSinPoly[4]);
+  ps = fma(ps, z, kSinPoly[3]);
+  ps = fma(ps, z, kSinPoly[2]);
+  ps = fma(ps, z, kSinPoly[1]);
+  ps = fma(ps, z, kSinPoly[0]);
+  double pc = kCosPoly[5];
+  pc = fma(pc, z, kCosPoly[4]);
+  pc = fma(pc, z, kCosPoly[3]);
+  pc = fma(pc, z, kCosPoly[2]);
+  pc = fma(pc, z, kCosPoly[1]);
+  pc = fma(pc, z, kCosPoly[0]);
+  const double sn = fma(r * z, ps, r);
+  const double cs = fma(z * z, pc, fma(-0.5, z, 1.0));
+  double s = (q & 1) ? cs : sn;
+  double c = (q & 1) ? sn : cs;
+  if (q & 2) s = -s;
+  if ((q + 1) & 2) c = -c;
+  if (!(fabs(x) <= 1.0e5)) ::sincos(x, &s, &c);
+  *sp = s;
+  *cp = c;
+}
+
 // sqrt(t) for t >= 0 without the IEEE slow-path branch (<= 1 ulp); 0 for t <= 0 or tiny.
 __device__ __forceinline__ double fast_sqrt(double t) {
   const bool ok = t > 1e-290;
@@ -170,7 +210,57 @@ __device__ __forceinline__ double fast_sqrt(double t) {
 
 __device__ __forceinline__ double Sc<double>::atan2_fast(double y, double x) { return fast_atan2(y, x); }
 __device__ __forceinline__ double Sc<double>::rsqrt_fast(double x) { return fast_rsqrt(x); }
+__device__ __forceinline__ void Sc<double>::sincos(double x, double* s, double* c) { fast_sincos(x, s, c); }
 __device__ __forceinline__ double Sc<double>::sqrt_fast(double x) { return fast_sqrt(x); }
+
+// ---------------------------------------------------------------------------------
+// TMA bulk copies (1-D cp.async.bulk) + mbarrier: the SOA planes of a tile move between HBM
+// and shared memory without occupying the LSU or registers, asynchronously to the math.
+// Addresses and sizes must be multiples of 16 bytes.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "RK_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra RK_DONE_%=;\n"
+      "bra RK_WAIT_%=;\n"
+      "RK_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 
 // 3-vectors as plain scalars keep everything in registers.
 template <typename S>

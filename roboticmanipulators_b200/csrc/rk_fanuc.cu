@@ -55,9 +55,10 @@ static FanucP<S> make_params(const RkFanuc* r, int flags) {
 // lower triangular, det J = det[u_k x (O3 - O_k)]_{k<3} * det[u3 u4 u5]
 //        = rho3 * l3 * (l5 s2 - l4 c2) * (-s4).
 // -----------------------------------------------------------------------------------
-template <typename S>
-__device__ __forceinline__ void fanuc_fk_jac_pose(const FanucP<S>& P, const S (&q)[6], S (&T)[16],
-                                                  S (&J)[36], S& det) {
+// Results leave through `out` (out.T(k, v), out.J(k, v), out.det(v)) as soon as they exist, so
+// the SOA kernel can turn each into a store immediately and keep register pressure low.
+template <typename S, typename Out>
+__device__ __forceinline__ void fanuc_fk_jac_emit(const FanucP<S>& P, const S (&q)[6], Out& out) {
   using M = Sc<S>;
   S c[6], s[6];
 #pragma unroll
@@ -103,34 +104,45 @@ __device__ __forceinline__ void fanuc_fk_jac_pose(const FanucP<S>& P, const S (&
     for (int i = 0; i < 9; ++i) R[i] = Rn[i];
   }
 
-  // Jacobian columns in the base-local frame
+  S dt = -s[4] * rho3 * l3 * (l5 * s[2] - l4 * c[2]);
+  if (P.user_jac) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) dt *= P.dir[k];
+  }
+  out.det(dt);
+
+  // Jacobian column k = [u x (O_n - O_k); u], rotated into the world and emitted at once so
+  // that only the frame vectors stay live
+  const bool hb = P.has_base != 0;
+  const S* Tb = P.Tb;
+  const S Rb[9] = {Tb[0], Tb[1], Tb[2], Tb[4], Tb[5], Tb[6], Tb[8], Tb[9], Tb[10]};
+  auto emit_col = [&](int k, const V3<S>& u, const V3<S>& Ok) {
+    V3<S> lin = cross(u, sub(On, Ok));
+    V3<S> ang = u;
+    if (hb) {
+      lin = rot(Rb, lin);
+      ang = rot(Rb, ang);
+    }
+    if (P.user_jac) {
+      const S dk = P.dir[k];
+      lin = {lin.x * dk, lin.y * dk, lin.z * dk};
+      ang = {ang.x * dk, ang.y * dk, ang.z * dk};
+    }
+    out.J(0 * 6 + k, lin.x), out.J(1 * 6 + k, lin.y), out.J(2 * 6 + k, lin.z);
+    out.J(3 * 6 + k, ang.x), out.J(4 * 6 + k, ang.y), out.J(5 * 6 + k, ang.z);
+  };
+  const V3<S> zax = {S(0), S(0), S(1)};
+  const V3<S> O0 = {S(0), S(0), l0};
   const V3<S> O1 = {l2 * c[0], l2 * s[0], h1};
   const V3<S> O2 = {rho2 * c[0], rho2 * s[0], h2};
-  V3<S> jv[6], jw[6];
-  jw[0] = {S(0), S(0), S(1)};
-  jv[0] = {-On.y, On.x, S(0)};
-  jw[1] = y1;
-  jv[1] = cross(y1, sub(On, O1));
-  jw[2] = y1;
-  jv[2] = cross(y1, sub(On, O2));
-  const V3<S> rw = sub(On, O3);
-  jw[3] = x3;
-  jv[3] = cross(x3, rw);
-  jw[4] = y4;
-  jv[4] = cross(y4, rw);
-  jw[5] = x5;
-  jv[5] = cross(x5, rw);
+  emit_col(0, zax, O0);
+  emit_col(1, y1, O1);
+  emit_col(2, y1, O2);
+  emit_col(3, x3, O3);
+  emit_col(4, y4, O3);
+  emit_col(5, x5, O3);
 
-  S dt = -s[4] * rho3 * l3 * (l5 * s[2] - l4 * c[2]);
-
-  if (P.has_base) {
-    const S* Tb = P.Tb;
-    const S Rb[9] = {Tb[0], Tb[1], Tb[2], Tb[4], Tb[5], Tb[6], Tb[8], Tb[9], Tb[10]};
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      jv[k] = rot(Rb, jv[k]);
-      jw[k] = rot(Rb, jw[k]);
-    }
+  if (hb) {
     V3<S> p = rot(Rb, On);
     On = {p.x + Tb[3], p.y + Tb[7], p.z + Tb[11]};
     S Rn[9];
@@ -142,30 +154,46 @@ __device__ __forceinline__ void fanuc_fk_jac_pose(const FanucP<S>& P, const S (&
 #pragma unroll
     for (int i = 0; i < 9; ++i) R[i] = Rn[i];
   }
-  if (P.user_jac) {
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const S dk = P.dir[k];
-      jv[k] = {jv[k].x * dk, jv[k].y * dk, jv[k].z * dk};
-      jw[k] = {jw[k].x * dk, jw[k].y * dk, jw[k].z * dk};
-      dt *= dk;
-    }
-  }
-  T[0] = R[0], T[1] = R[1], T[2] = R[2], T[3] = On.x;
-  T[4] = R[3], T[5] = R[4], T[6] = R[5], T[7] = On.y;
-  T[8] = R[6], T[9] = R[7], T[10] = R[8], T[11] = On.z;
-  T[12] = S(0), T[13] = S(0), T[14] = S(0), T[15] = S(1);
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    J[0 * 6 + k] = jv[k].x;
-    J[1 * 6 + k] = jv[k].y;
-    J[2 * 6 + k] = jv[k].z;
-    J[3 * 6 + k] = jw[k].x;
-    J[4 * 6 + k] = jw[k].y;
-    J[5 * 6 + k] = jw[k].z;
-  }
-  det = dt;
+  out.T(0, R[0]), out.T(1, R[1]), out.T(2, R[2]), out.T(3, On.x);
+  out.T(4, R[3]), out.T(5, R[4]), out.T(6, R[5]), out.T(7, On.y);
+  out.T(8, R[6]), out.T(9, R[7]), out.T(10, R[8]), out.T(11, On.z);
+  out.T(12, S(0)), out.T(13, S(0)), out.T(14, S(0)), out.T(15, S(1));
 }
+
+template <typename S>
+struct ArraySink {
+  S (&Tv)[16];
+  S (&Jv)[36];
+  S& dv;
+  __device__ __forceinline__ void T(int k, S v) { Tv[k] = v; }
+  __device__ __forceinline__ void J(int k, S v) { Jv[k] = v; }
+  __device__ __forceinline__ void det(S v) { dv = v; }
+};
+
+template <typename S>
+__device__ __forceinline__ void fanuc_fk_jac_pose(const FanucP<S>& P, const S (&q)[6], S (&T)[16],
+                                                  S (&J)[36], S& det) {
+  ArraySink<S> sink{T, J, det};
+  fanuc_fk_jac_emit(P, q, sink);
+}
+
+// Streams every component straight to its SOA plane.
+template <typename S>
+struct PlaneSink {
+  S* Tp;
+  S* Jp;
+  S* dp;
+  int64_t ld;
+  __device__ __forceinline__ void T(int k, S v) {
+    if (Tp) __stcs(Tp + k * ld, v);
+  }
+  __device__ __forceinline__ void J(int k, S v) {
+    if (Jp) __stcs(Jp + k * ld, v);
+  }
+  __device__ __forceinline__ void det(S v) {
+    if (dp) __stcs(dp, v);
+  }
+};
 
 // SOA: component planes, every warp access is one contiguous 256-byte (f64) segment.
 template <typename S>
@@ -173,21 +201,23 @@ __global__ void __launch_bounds__(kBlock, 4)
 fanuc_fk_jac_soa_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict__ q, int64_t n,
                         int64_t ld, S* __restrict__ T, S* __restrict__ J, S* __restrict__ det) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  // software pipeline: the next trip's joint vector is in flight while this trip computes
+  // (ncu: 55 % of warp time was long-scoreboard on these six loads)
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  S qn[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) qn[k] = (i < n) ? __ldcs(q + k * ld + i) : S(0);
+  for (; i < n; i += stride) {
     S qv[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) qv[k] = __ldcs(q + k * ld + i);
-    S Tv[16], Jv[36], dv;
-    fanuc_fk_jac_pose(P, qv, Tv, Jv, dv);
-    if (T) {
+    for (int k = 0; k < 6; ++k) qv[k] = qn[k];
+    const int64_t inext = i + stride;
+    if (inext < n) {
 #pragma unroll
-      for (int k = 0; k < 16; ++k) __stcs(T + k * ld + i, Tv[k]);
+      for (int k = 0; k < 6; ++k) qn[k] = __ldcs(q + k * ld + inext);
     }
-    if (J) {
-#pragma unroll
-      for (int k = 0; k < 36; ++k) __stcs(J + k * ld + i, Jv[k]);
-    }
-    if (det) __stcs(det + i, dv);
+    PlaneSink<S> sink{T ? T + i : nullptr, J ? J + i : nullptr, det ? det + i : nullptr, ld};
+    fanuc_fk_jac_emit(P, qv, sink);
   }
 }
 
@@ -450,6 +480,88 @@ fanuc_ik8_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict__ T, i
   }
 }
 
+// SOA fast path: the same lane mapping as fanuc_ik8_kernel, but a CTA walks tiles of 64
+// poses whose 12 input planes arrive by TMA bulk loads (double buffered, issued one tile
+// ahead) and whose 48 result planes + 8 validity planes leave by TMA bulk stores, so neither
+// the DRAM latency of the loads nor the 392 B/pose of stores sits on the math's critical path
+// (with LSU loads/stores the kernel took compute + store time: 10.2 + 4.1 ms per 2^26 poses).
+template <typename S>
+struct Ik8Tile {
+  static constexpr int kPoses = 64;
+  S in[2][12][kPoses];
+  S out[48][kPoses];
+  uint8_t ok[8][kPoses];
+  uint64_t bar[2];
+};
+
+template <typename S>
+__global__ void __launch_bounds__(kBlock, 4)
+fanuc_ik8_tma_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict__ T, int64_t ntiles,
+                     int64_t ld, S* __restrict__ q_out, uint8_t* __restrict__ valid) {
+  using Tile = Ik8Tile<S>;
+  constexpr int TP = Tile::kPoses;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Tile& sm = *reinterpret_cast<Tile*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int mk = lane & 3, pl = lane >> 2;
+  const int m = (mk & 2) ? -1 : 1, k = (mk & 1) ? -1 : 1;
+  if (tid == 0) {
+    mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue_loads = [&](int64_t tile, int buf) {  // one thread
+    mbar_expect_tx(&sm.bar[buf], 12 * TP * sizeof(S));
+#pragma unroll
+    for (int c = 0; c < 12; ++c)
+      bulk_load(&sm.in[buf][c][0], T + (int64_t)c * ld + tile * TP, TP * sizeof(S), &sm.bar[buf]);
+  };
+  int64_t tile = blockIdx.x;
+  if (tid == 0 && tile < ntiles) issue_loads(tile, 0);
+  int it = 0;
+  for (; tile < ntiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int64_t next = tile + gridDim.x;
+    if (tid == 0 && next < ntiles) issue_loads(next, buf ^ 1);
+    mbar_wait(&sm.bar[buf], (it >> 1) & 1);
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      const int p = pass * 32 + warp * 8 + pl;  // pose within the tile
+      S Tin[12];
+#pragma unroll
+      for (int c = 0; c < 12; ++c) Tin[c] = sm.in[buf][c][p];
+      S R0[9], p0[3];
+      fanuc_ik_t0(P, Tin, R0, p0);
+      const int wl[2] = {0, 1};
+      S qo[2][6];
+      bool ok[2];
+      fanuc_ik_mk<S, 2, true>(P, R0, p0, m, k, wl, qo, ok);
+      if (pass == 0) {
+        // the previous tile's bulk stores must have finished reading sm.out
+        if (tid < 56) bulk_wait_read0();
+        __syncthreads();
+      }
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) sm.out[(mk * 2 + w) * 6 + j][p] = qo[w][j];
+        sm.ok[mk * 2 + w][p] = ok[w] ? 1 : 0;
+      }
+    }
+    fence_async_smem();
+    __syncthreads();  // also: everyone is done reading sm.in[buf]
+    if (tid < 48) {
+      bulk_store(q_out + (int64_t)tid * ld + tile * TP, &sm.out[tid][0], TP * sizeof(S));
+      bulk_commit();
+    } else if (tid < 56) {
+      bulk_store(valid + (int64_t)(tid - 48) * ld + tile * TP, &sm.ok[tid - 48][0], TP);
+      bulk_commit();
+    }
+  }
+  if (tid < 56) bulk_wait_all();
+}
+
 // Arbitrary branch list: one thread per (pose, branch).
 struct BranchList {
   int8_t mkw[3 * 16];
@@ -537,8 +649,31 @@ static int launch_ik(const RkFanuc* robot, const S* T, int64_t n, int64_t ld, in
     // 128 registers / 4 CTAs per SM measured best (3: 8.1 ms, 4: 7.2 ms, 5: 7.2 ms, 6 spills: 8.1 ms
     // per 2^25 poses)
     if (soa) {
-      int grid = persistent_grid(fanuc_ik8_kernel<S, true, 4>, kBlock, 0, n * 4);
-      fanuc_ik8_kernel<S, true, 4><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
+      // full 64-pose tiles go through the TMA kernel when every plane start is 16-byte aligned
+      constexpr int TP = Ik8Tile<S>::kPoses;
+      int64_t done = 0;
+      const bool aligned = (ld % 16 == 0) && ((uintptr_t)T % 16 == 0) && ((uintptr_t)q_out % 16 == 0) &&
+                           ((uintptr_t)valid % 16 == 0);
+      if (aligned && n >= TP) {
+        const int64_t ntiles = n / TP;
+        const size_t smem = sizeof(Ik8Tile<S>);
+        static thread_local bool attr_done = false;
+        if (!attr_done) {
+          cudaFuncSetAttribute(fanuc_ik8_tma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          attr_done = true;
+        }
+        int grid = persistent_grid(fanuc_ik8_tma_kernel<S>, kBlock, smem, ntiles * kBlock);
+        fanuc_ik8_tma_kernel<S><<<grid, kBlock, smem, st>>>(P, T, ntiles, ld, q_out, valid);
+        int rc = check_launch();
+        if (rc != RK_OK) return rc;
+        done = ntiles * TP;
+      }
+      if (done < n) {
+        const int64_t rest = n - done;
+        int grid = persistent_grid(fanuc_ik8_kernel<S, true, 4>, kBlock, 0, rest * 4);
+        fanuc_ik8_kernel<S, true, 4><<<grid, kBlock, 0, st>>>(P, T + done, rest, ld, q_out + done,
+                                                              valid + done);
+      }
     } else {
       int grid = persistent_grid(fanuc_ik8_kernel<S, false, 4>, kBlock, 0, n * 4);
       fanuc_ik8_kernel<S, false, 4><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);

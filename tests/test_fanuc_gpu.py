@@ -269,3 +269,26 @@ def test_internal_atan2_accuracy():
     assert np.array_equal(np.signbit(got[ok]), np.signbit(ref[ok]))
     err = np.abs(got[ok] - ref[ok]) / np.maximum(np.abs(ref[ok]), 1e-300)
     assert err.max() < 5e-16, err.max()                      # <= ~2 ulp
+
+
+def test_internal_sincos_accuracy():
+    """The kernels' own FP64 sincos vs libm: joint-angle range, large arguments, specials."""
+    from roboticmanipulators_b200 import _lib
+    rng = np.random.default_rng(1)
+    n = 1 << 22
+    x = np.concatenate([rng.uniform(-8, 8, n // 2), rng.uniform(-1e5, 1e5, n // 4),
+                        rng.normal(size=n // 4) * 10.0 ** rng.integers(-12, 9, size=n // 4)])
+    x[:12] = [0.0, -0.0, np.pi / 2, -np.pi / 2, np.pi, 1e5, -1e5, 1.0000001e5, 1e22, np.inf, -np.inf, np.nan]
+    xt = torch.tensor(x, device="cuda")
+    s, c = torch.empty_like(xt), torch.empty_like(xt)
+    _lib.check(_lib.load().rk_probe_sincos(_lib.ptr(xt), n, _lib.ptr(s), _lib.ptr(c), _lib.stream_ptr()))
+    s, c = s.cpu().numpy(), c.cpu().numpy()
+    with np.errstate(invalid="ignore"):
+        rs, rc = np.sin(x), np.cos(x)
+    assert np.array_equal(np.isnan(s), np.isnan(rs)) and np.array_equal(np.isnan(c), np.isnan(rc))
+    ok = ~np.isnan(rs)
+    assert np.max(np.abs(s[ok] - rs[ok])) < 2.3e-16 and np.max(np.abs(c[ok] - rc[ok])) < 2.3e-16
+    big = ok & (np.abs(rs) > 1e-3)
+    assert np.max(np.abs(s[big] - rs[big]) / np.abs(rs[big])) < 4.5e-16
+    big = ok & (np.abs(rc) > 1e-3)
+    assert np.max(np.abs(c[big] - rc[big]) / np.abs(rc[big])) < 4.5e-16
