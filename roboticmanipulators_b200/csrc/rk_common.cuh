@@ -1,5 +1,6 @@
 // Shared device helpers for librk_b200 (sm_100a).  No torch, no third-party headers.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -261,6 +262,66 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+
+// 2-D tiled tensor maps: one TMA instruction moves a whole [rows][cols] box between the SOA
+// planes in HBM and a dense shared-memory tile; out-of-range columns are zero-filled on load and
+// clipped on store, so ragged tails need no special code.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int x, int y, const void* smem_src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map),
+               "r"(x), "r"(y), "r"(smem_u32(smem_src))
+               : "memory");
+}
+
+// Host: encode a [rows][cols] tensor with row pitch `pitch_bytes` and box [box_rows][box_cols].
+// Returns false when the driver entry point is unavailable or the layout violates TMA's
+// alignment rules (16-byte base and pitch) -- callers then use the LSU kernels.
+inline bool make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base,
+                         uint64_t cols, uint64_t rows, uint64_t pitch_bytes, uint32_t box_cols,
+                         uint32_t box_rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeFn)p;
+    cudaGetLastError();
+  }
+  if (!fn) return false;
+  if (((uintptr_t)base & 15) || (pitch_bytes & 15) || ((uint64_t)box_cols * elem_bytes & 15)) return false;
+  if (cols == 0 || cols > 0x7fffffffull || rows == 0) return false;
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstride[1] = {pitch_bytes};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename S>
+struct TmapType;
+template <>
+struct TmapType<double> {
+  static constexpr CUtensorMapDataType value = CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+};
+template <>
+struct TmapType<float> {
+  static constexpr CUtensorMapDataType value = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+};
 
 // 3-vectors as plain scalars keep everything in registers.
 template <typename S>

@@ -480,11 +480,13 @@ fanuc_ik8_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict__ T, i
   }
 }
 
-// SOA fast path: the same lane mapping as fanuc_ik8_kernel, but a CTA walks tiles of 64
-// poses whose 12 input planes arrive by TMA bulk loads (double buffered, issued one tile
-// ahead) and whose 48 result planes + 8 validity planes leave by TMA bulk stores, so neither
-// the DRAM latency of the loads nor the 392 B/pose of stores sits on the math's critical path
-// (with LSU loads/stores the kernel took compute + store time: 10.2 + 4.1 ms per 2^26 poses).
+// SOA fast path: the same lane mapping as fanuc_ik8_kernel, but a CTA walks tiles of 64 poses.
+// ONE 2-D TMA load brings the tile's 12 input planes ([12][64] box of the [16][ld] pose array),
+// double buffered and issued one tile ahead; results are staged in shared memory and leave as
+// ONE TMA store of the [48][64] box of q_out plus one of the [8][64] validity box.  Neither the
+// DRAM latency of the loads nor the 392 B/pose of stores occupies the LSU or sits on the math's
+// critical path (with LSU accesses the kernel took compute + store time: 10.2 + 4.1 ms per 2^26
+// poses).  The tensor maps clip the ragged last tile (zero fill on load, no write out of range).
 template <typename S>
 struct Ik8Tile {
   static constexpr int kPoses = 64;
@@ -496,8 +498,9 @@ struct Ik8Tile {
 
 template <typename S>
 __global__ void __launch_bounds__(kBlock, 4)
-fanuc_ik8_tma_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict__ T, int64_t ntiles,
-                     int64_t ld, S* __restrict__ q_out, uint8_t* __restrict__ valid) {
+fanuc_ik8_tma_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant__ CUtensorMap tmT,
+                     const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmV,
+                     int64_t ntiles) {
   using Tile = Ik8Tile<S>;
   constexpr int TP = Tile::kPoses;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -511,19 +514,17 @@ fanuc_ik8_tma_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict__ 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  auto issue_loads = [&](int64_t tile, int buf) {  // one thread
+  auto issue_load = [&](int64_t tile, int buf) {  // one thread
     mbar_expect_tx(&sm.bar[buf], 12 * TP * sizeof(S));
-#pragma unroll
-    for (int c = 0; c < 12; ++c)
-      bulk_load(&sm.in[buf][c][0], T + (int64_t)c * ld + tile * TP, TP * sizeof(S), &sm.bar[buf]);
+    tma_load_2d(&sm.in[buf][0][0], &tmT, (int)(tile * TP), 0, &sm.bar[buf]);
   };
   int64_t tile = blockIdx.x;
-  if (tid == 0 && tile < ntiles) issue_loads(tile, 0);
+  if (tid == 0 && tile < ntiles) issue_load(tile, 0);
   int it = 0;
   for (; tile < ntiles; tile += gridDim.x, ++it) {
     const int buf = it & 1;
     const int64_t next = tile + gridDim.x;
-    if (tid == 0 && next < ntiles) issue_loads(next, buf ^ 1);
+    if (tid == 0 && next < ntiles) issue_load(next, buf ^ 1);
     mbar_wait(&sm.bar[buf], (it >> 1) & 1);
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
@@ -538,8 +539,8 @@ fanuc_ik8_tma_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict__ 
       bool ok[2];
       fanuc_ik_mk<S, 2, true>(P, R0, p0, m, k, wl, qo, ok);
       if (pass == 0) {
-        // the previous tile's bulk stores must have finished reading sm.out
-        if (tid < 56) bulk_wait_read0();
+        // the previous tile's TMA stores must have finished reading sm.out / sm.ok
+        if (tid == 0) bulk_wait_read0();
         __syncthreads();
       }
 #pragma unroll
@@ -551,15 +552,13 @@ fanuc_ik8_tma_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict__ 
     }
     fence_async_smem();
     __syncthreads();  // also: everyone is done reading sm.in[buf]
-    if (tid < 48) {
-      bulk_store(q_out + (int64_t)tid * ld + tile * TP, &sm.out[tid][0], TP * sizeof(S));
-      bulk_commit();
-    } else if (tid < 56) {
-      bulk_store(valid + (int64_t)(tid - 48) * ld + tile * TP, &sm.ok[tid - 48][0], TP);
+    if (tid == 0) {
+      tma_store_2d(&tmQ, (int)(tile * TP), 0, &sm.out[0][0]);
+      tma_store_2d(&tmV, (int)(tile * TP), 0, &sm.ok[0][0]);
       bulk_commit();
     }
   }
-  if (tid < 56) bulk_wait_all();
+  if (tid == 0) bulk_wait_all();
 }
 
 // Arbitrary branch list: one thread per (pose, branch).
@@ -649,13 +648,15 @@ static int launch_ik(const RkFanuc* robot, const S* T, int64_t n, int64_t ld, in
     // 128 registers / 4 CTAs per SM measured best (3: 8.1 ms, 4: 7.2 ms, 5: 7.2 ms, 6 spills: 8.1 ms
     // per 2^25 poses)
     if (soa) {
-      // full 64-pose tiles go through the TMA kernel when every plane start is 16-byte aligned
+      // TMA path when the three arrays satisfy the tensor-map alignment rules, LSU kernel otherwise
       constexpr int TP = Ik8Tile<S>::kPoses;
-      int64_t done = 0;
-      const bool aligned = (ld % 16 == 0) && ((uintptr_t)T % 16 == 0) && ((uintptr_t)q_out % 16 == 0) &&
-                           ((uintptr_t)valid % 16 == 0);
-      if (aligned && n >= TP) {
-        const int64_t ntiles = n / TP;
+      CUtensorMap tmT, tmQ, tmV;
+      const bool tma_ok =
+          make_tmap_2d(&tmT, TmapType<S>::value, sizeof(S), T, n, 12, ld * sizeof(S), TP, 12) &&
+          make_tmap_2d(&tmQ, TmapType<S>::value, sizeof(S), q_out, n, 48, ld * sizeof(S), TP, 48) &&
+          make_tmap_2d(&tmV, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, valid, n, 8, ld, TP, 8);
+      if (tma_ok) {
+        const int64_t ntiles = (n + TP - 1) / TP;
         const size_t smem = sizeof(Ik8Tile<S>);
         static thread_local bool attr_done = false;
         if (!attr_done) {
@@ -663,16 +664,10 @@ static int launch_ik(const RkFanuc* robot, const S* T, int64_t n, int64_t ld, in
           attr_done = true;
         }
         int grid = persistent_grid(fanuc_ik8_tma_kernel<S>, kBlock, smem, ntiles * kBlock);
-        fanuc_ik8_tma_kernel<S><<<grid, kBlock, smem, st>>>(P, T, ntiles, ld, q_out, valid);
-        int rc = check_launch();
-        if (rc != RK_OK) return rc;
-        done = ntiles * TP;
-      }
-      if (done < n) {
-        const int64_t rest = n - done;
-        int grid = persistent_grid(fanuc_ik8_kernel<S, true, 4>, kBlock, 0, rest * 4);
-        fanuc_ik8_kernel<S, true, 4><<<grid, kBlock, 0, st>>>(P, T + done, rest, ld, q_out + done,
-                                                              valid + done);
+        fanuc_ik8_tma_kernel<S><<<grid, kBlock, smem, st>>>(P, tmT, tmQ, tmV, ntiles);
+      } else {
+        int grid = persistent_grid(fanuc_ik8_kernel<S, true, 4>, kBlock, 0, n * 4);
+        fanuc_ik8_kernel<S, true, 4><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
       }
     } else {
       int grid = persistent_grid(fanuc_ik8_kernel<S, false, 4>, kBlock, 0, n * 4);
