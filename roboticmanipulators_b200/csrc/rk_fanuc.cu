@@ -221,6 +221,83 @@ fanuc_fk_jac_soa_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict
   }
 }
 
+// SOA fast path of K1: a CTA walks 128-pose tiles.  The tile's six joint planes arrive by one
+// 2-D TMA load (double buffered, one tile ahead); every result is written to a dense
+// shared-memory tile the moment it exists and the tile leaves as three TMA stores
+// (T [16][128], J [36][128], det [1][128]).  The store path then runs at the memory system's pace
+// instead of through 53 LSU store instructions per thread (ncu: lg_throttle + long_scoreboard).
+template <typename S>
+struct FkTile {
+  static constexpr int kPoses = kBlock;
+  S q[2][6][kPoses];
+  S T[16][kPoses];
+  S J[36][kPoses];
+  S det[kPoses];
+  uint64_t bar[2];
+};
+
+// Emits into the shared tile; the first emission of a trip (det) first makes sure the previous
+// trip's TMA stores have finished reading the tile.
+template <typename S>
+struct TileSink {
+  FkTile<S>& sm;
+  int tid;
+  __device__ __forceinline__ void det(S v) {
+    if (tid == 0) bulk_wait_read0();
+    __syncthreads();
+    sm.det[tid] = v;
+  }
+  __device__ __forceinline__ void T(int k, S v) { sm.T[k][tid] = v; }
+  __device__ __forceinline__ void J(int k, S v) { sm.J[k][tid] = v; }
+};
+
+template <typename S>
+__global__ void __launch_bounds__(kBlock, 3)
+fanuc_fk_jac_tma_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant__ CUtensorMap tmq,
+                        const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUtensorMap tmJ,
+                        const __grid_constant__ CUtensorMap tmD, int64_t ntiles, int wantT, int wantJ,
+                        int wantD) {
+  using Tile = FkTile<S>;
+  constexpr int TP = Tile::kPoses;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Tile& sm = *reinterpret_cast<Tile*>(smem_raw);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue_load = [&](int64_t tile, int buf) {
+    mbar_expect_tx(&sm.bar[buf], 6 * TP * sizeof(S));
+    tma_load_2d(&sm.q[buf][0][0], &tmq, (int)(tile * TP), 0, &sm.bar[buf]);
+  };
+  int64_t tile = blockIdx.x;
+  if (tid == 0 && tile < ntiles) issue_load(tile, 0);
+  TileSink<S> sink{sm, tid};
+  int it = 0;
+  for (; tile < ntiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int64_t next = tile + gridDim.x;
+    if (tid == 0 && next < ntiles) issue_load(next, buf ^ 1);
+    mbar_wait(&sm.bar[buf], (it >> 1) & 1);
+    S qv[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) qv[k] = sm.q[buf][k][tid];
+    fanuc_fk_jac_emit(P, qv, sink);
+    fence_async_smem();
+    __syncthreads();  // tile complete; also everyone is done with sm.q[buf]
+    if (tid == 0) {
+      const int x = (int)(tile * TP);
+      if (wantT) tma_store_2d(&tmT, x, 0, &sm.T[0][0]);
+      if (wantJ) tma_store_2d(&tmJ, x, 0, &sm.J[0][0]);
+      if (wantD) tma_store_2d(&tmD, x, 0, &sm.det[0]);
+      bulk_commit();
+    }
+  }
+  if (tid == 0) bulk_wait_all();
+}
+
 // AOS: the reference's shapes ([n][6] -> [n][4][4], [n][6][6]); each warp stages its 32
 // poses through a private shared-memory tile so that global traffic is whole lines.
 template <typename S>
@@ -614,8 +691,30 @@ static int launch_fk_jac(const RkFanuc* robot, const S* q, int64_t n, int64_t ld
   FanucP<S> P = make_params<S>(robot, flags);
   cudaStream_t st = (cudaStream_t)stream;
   if (soa) {
-    int grid = persistent_grid(fanuc_fk_jac_soa_kernel<S>, kBlock, 0, n);
-    fanuc_fk_jac_soa_kernel<S><<<grid, kBlock, 0, st>>>(P, q, n, ld, T, J, det);
+    constexpr int TP = FkTile<S>::kPoses;
+    CUtensorMap tmq, tmT, tmJ, tmD;
+    const uint64_t pitch = (uint64_t)ld * sizeof(S);
+    // a missing output gets a (never used) alias of q so the kernel signature stays fixed
+    const bool tma_ok =
+        make_tmap_2d(&tmq, TmapType<S>::value, sizeof(S), q, n, 6, pitch, TP, 6) &&
+        make_tmap_2d(&tmT, TmapType<S>::value, sizeof(S), T ? T : (S*)q, n, T ? 16 : 6, pitch, TP, T ? 16 : 6) &&
+        make_tmap_2d(&tmJ, TmapType<S>::value, sizeof(S), J ? J : (S*)q, n, J ? 36 : 6, pitch, TP, J ? 36 : 6) &&
+        make_tmap_2d(&tmD, TmapType<S>::value, sizeof(S), det ? det : (S*)q, n, 1, pitch, TP, 1);
+    if (tma_ok) {
+      const int64_t ntiles = (n + TP - 1) / TP;
+      const size_t smem = sizeof(FkTile<S>);
+      static thread_local bool attr_done = false;
+      if (!attr_done) {
+        cudaFuncSetAttribute(fanuc_fk_jac_tma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_done = true;
+      }
+      int grid = persistent_grid(fanuc_fk_jac_tma_kernel<S>, kBlock, smem, ntiles * kBlock);
+      fanuc_fk_jac_tma_kernel<S><<<grid, kBlock, smem, st>>>(P, tmq, tmT, tmJ, tmD, ntiles, T != nullptr,
+                                                             J != nullptr, det != nullptr);
+    } else {
+      int grid = persistent_grid(fanuc_fk_jac_soa_kernel<S>, kBlock, 0, n);
+      fanuc_fk_jac_soa_kernel<S><<<grid, kBlock, 0, st>>>(P, q, n, ld, T, J, det);
+    }
   } else {
     int grid = persistent_grid(fanuc_fk_jac_aos_kernel<S>, kBlock, 0, n);
     fanuc_fk_jac_aos_kernel<S><<<grid, kBlock, 0, st>>>(P, q, n, T, J, det);
