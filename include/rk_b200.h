@@ -187,6 +187,15 @@ int rk_trap_sample_f64(const double* q_init, const double* v_cur, const double* 
                        const double* t1, const double* tau, int64_t nprof, int nsteps, double* q,
                        double* dq, double* ddq, double* t, int32_t* len, void* stream);
 
+/* PolynomialGenerator.generate_coefficients + polynomial_from_coefs / dpolynomial_from_coefs
+ * (utils/polynomial_generator.py:16-96; TrajectoryGenerator.generate_joint_poly_trajectory,
+ * utils/trajectory_generator.py:27-69) for nprof quintic profiles.
+ *   b0, bf in : [nprof][3] = (position, velocity, acceleration) at t0[i] and tf[i]
+ *   coef  out : [nprof][6] coefficients in powers of t; may be NULL
+ *   q,dq,ddq out: [nprof][nsteps] samples at np.linspace(t0, tf, nsteps); any may be NULL */
+int rk_poly5_f64(const double* b0, const double* bf, const double* t0, const double* tf, int64_t nprof,
+                 int nsteps, double* coef, double* q, double* dq, double* ddq, void* stream);
+
 /* TrajectoryGenerator.generate_p2p_trajectory / _generate_equalized_profiles
  * (trajectory_generator.py:71-92,118-159) over ntraj trajectories of nj joints:
  * per-joint generate_coefficients (trapezoidal_generator.py:36-79), equalisation

@@ -504,6 +504,30 @@ def lin_rrr_batch(p_0, p_f, n, dx_max, ddx_max, control_freq=0):
 
 
 # ---------------------------------------------------------------------------
+# next: quintic polynomial profiles (utils/polynomial_generator.py)
+# ---------------------------------------------------------------------------
+def poly_coefficients(q_init, q_final, t_f, t_0=0.0):
+    """generate_coefficients (polynomial_generator.py:16-36): inv(A).dot([q0,dq0,ddq0,qf,dqf,ddqf])."""
+    def sub(t):                                                   # :38-52
+        return np.array([[1, t, t**2, t**3, t**4, t**5],
+                         [0, 1, 2 * t, 3 * t**2, 4 * t**3, 5 * t**4],
+                         [0, 0, 2, 6 * t, 12 * t**2, 20 * t**3]])
+    A = np.vstack((sub(t_0), sub(t_f)))
+    return np.linalg.inv(A).dot(np.hstack((np.array(q_init), np.array(q_final))))
+
+
+def poly_sample(coefs, d, from_t, to_t, n):
+    """polynomial_from_coefs / dpolynomial_from_coefs (polynomial_generator.py:54-96)."""
+    ts = np.linspace(from_t, to_t, n)
+    if d >= len(coefs):
+        return np.zeros(n)
+    poly = 0
+    for i, coef in enumerate(coefs[d:], d):
+        poly = poly + coef * math.factorial(d) * math.comb(i, d) * ts**(i - d)
+    return poly
+
+
+# ---------------------------------------------------------------------------
 # A10: calibration (utils/model_calibration.py)
 # ---------------------------------------------------------------------------
 class CalibModel:

@@ -81,6 +81,7 @@ _SIGNATURES = {
                                         _vp, _vp, _vp]),
     "rk_trap_sample_f64": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp,
                                   _vp]),
+    "rk_poly5_f64": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp]),
     "rk_trap_p2p_f64": (_int, [_vp, _vp, _i64, _int, _int, C.c_double, C.c_double, C.c_double,
                                _vp, _vp, _vp, _vp, _vp, _vp]),
     "rk_rrr_p2p_fk_f64": (_int, [C.POINTER(RkArm), _vp, _vp, _i64, _int, C.c_double, C.c_double,

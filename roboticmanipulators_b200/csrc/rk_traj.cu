@@ -265,6 +265,60 @@ trap_sample_kernel(const double* __restrict__ q0, const double* __restrict__ v,
   }
 }
 
+// Quintic boundary-value profiles (utils/polynomial_generator.py:16-96): one warp per profile.
+// The reference inverts the 6x6 constraint matrix; the closed form in the shifted variable
+// tau = t - t0 is the same polynomial: a0 = q0, a1 = v0, a2 = acc0 / 2 and a3..a5 from the end
+// conditions; coefficients in powers of t follow by binomial expansion.
+__global__ void __launch_bounds__(kBlock)
+poly5_kernel(const double* __restrict__ b0, const double* __restrict__ bf, const double* __restrict__ t0a,
+             const double* __restrict__ tfa, int64_t nprof, int nsteps, double* __restrict__ coef,
+             double* __restrict__ q, double* __restrict__ dq, double* __restrict__ ddq) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t pr = (((int64_t)blockIdx.x * blockDim.x) >> 5) + warp; pr < nprof; pr += warps) {
+    const double q0 = b0[pr * 3], v0 = b0[pr * 3 + 1], a0 = b0[pr * 3 + 2];
+    const double qf = bf[pr * 3], vf = bf[pr * 3 + 1], af = bf[pr * 3 + 2];
+    const double t0 = t0a[pr], tf = tfa[pr];
+    const double T = tf - t0, T2 = T * T, T3 = T2 * T, T4 = T3 * T, T5 = T4 * T;
+    const double h = qf - q0;
+    double a[6];
+    a[0] = q0, a[1] = v0, a[2] = 0.5 * a0;
+    a[3] = (20.0 * h - (8.0 * vf + 12.0 * v0) * T - (3.0 * a0 - af) * T2) / (2.0 * T3);
+    a[4] = (-30.0 * h + (14.0 * vf + 16.0 * v0) * T + (3.0 * a0 - 2.0 * af) * T2) / (2.0 * T4);
+    a[5] = (12.0 * h - 6.0 * (vf + v0) * T + (af - a0) * T2) / (2.0 * T5);
+    // c_k = sum_{i>=k} a_i C(i,k) (-t0)^(i-k)
+    const double binom[6][6] = {{1, 0, 0, 0, 0, 0}, {1, 1, 0, 0, 0, 0},  {1, 2, 1, 0, 0, 0},
+                                {1, 3, 3, 1, 0, 0}, {1, 4, 6, 4, 1, 0}, {1, 5, 10, 10, 5, 1}};
+    double c[6];
+    const double mt = -t0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      double acc = 0.0, pw = 1.0;
+#pragma unroll
+      for (int i = k; i < 6; ++i) {
+        acc += a[i] * binom[i][k] * pw;
+        pw *= mt;
+      }
+      c[k] = acc;
+    }
+    if (coef && lane < 6) {
+      double v = c[0];
+#pragma unroll
+      for (int k = 1; k < 6; ++k) v = (lane == k) ? c[k] : v;
+      coef[pr * 6 + lane] = v;
+    }
+    const double step = (nsteps > 1) ? M::div(M::sub(tf, t0), (double)(nsteps - 1)) : 0.0;
+    for (int i = lane; i < nsteps; i += kWarp) {
+      const double t = linspace_at(t0, tf, step, nsteps, i);
+      const double t2 = t * t, t3 = t2 * t, t4 = t3 * t, t5 = t4 * t;
+      const int64_t o = pr * nsteps + i;
+      if (q) q[o] = c[0] + c[1] * t + c[2] * t2 + c[3] * t3 + c[4] * t4 + c[5] * t5;
+      if (dq) dq[o] = c[1] + 2.0 * c[2] * t + 3.0 * c[3] * t2 + 4.0 * c[4] * t3 + 5.0 * c[5] * t4;
+      if (ddq) ddq[o] = 2.0 * c[2] + 6.0 * c[3] * t + 12.0 * c[4] * t2 + 20.0 * c[5] * t3;
+    }
+  }
+}
+
 template <int NJ, int MODE>
 static int launch_traj(const ArmP& P, const double* q0, const double* qf, int64_t ntraj, int nsteps,
                        double vmax, double amax, double freq, double* q, double* dq, double* ddq,
@@ -321,6 +375,17 @@ int rk_trap_sample_f64(const double* q_init, const double* v_cur, const double* 
   int grid = rk::persistent_grid(rk::trap_sample_kernel, rk::kBlock, 0, nprof * rk::kWarp);
   rk::trap_sample_kernel<<<grid, rk::kBlock, 0, (cudaStream_t)stream>>>(
       q_init, v_cur, a_cur, t1, tau, nprof, nsteps, q, dq, ddq, t, len);
+  return rk::check_launch();
+}
+
+int rk_poly5_f64(const double* b0, const double* bf, const double* t0, const double* tf, int64_t nprof,
+                 int nsteps, double* coef, double* q, double* dq, double* ddq, void* stream) {
+  if (nprof < 0 || nsteps < 1) return RK_ERR_INVALID_ARG;
+  if (nprof == 0) return RK_OK;
+  if (!b0 || !bf || !t0 || !tf) return RK_ERR_INVALID_ARG;
+  int grid = rk::persistent_grid(rk::poly5_kernel, rk::kBlock, 0, nprof * rk::kWarp);
+  rk::poly5_kernel<<<grid, rk::kBlock, 0, (cudaStream_t)stream>>>(b0, bf, t0, tf, nprof, nsteps, coef, q,
+                                                                    dq, ddq);
   return rk::check_launch();
 }
 

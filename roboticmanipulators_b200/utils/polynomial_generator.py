@@ -1,5 +1,6 @@
-"""Quintic polynomial profiles: drop-in for utils/polynomial_generator.py (host NumPy, as in
-the reference; listed under "next" in SURVEY.md section 8f, not on the accelerated path)."""
+"""Quintic polynomial profiles: drop-in for utils/polynomial_generator.py.  The scalar methods
+are host NumPy exactly like the reference; `profiles_batch` evaluates N profiles (coefficients +
+position / velocity / acceleration samples) in one CUDA launch (rk_poly5_f64)."""
 from math import comb, factorial
 
 import numpy as np
@@ -28,3 +29,27 @@ class PolynomialGenerator():
             return np.zeros(n)
         return sum(c * factorial(d) * comb(i, d) * ts**(i - d)
                    for i, c in enumerate(coefs[d:], d))
+
+    @staticmethod
+    def profiles_batch(b_init, b_final, t_f, t_0=0.0, n=100):
+        """N quintic profiles at once.  b_init, b_final: CUDA tensors [N, 3] of (q, dq, ddq) at
+        t_0 and t_f (scalars or [N] tensors).  Returns coefs [N,6], q, dq, ddq [N,n]."""
+        import torch
+        from .. import _lib
+        _lib.require_cuda(b_init, "b_init")
+        a = b_init.to(torch.float64).contiguous()
+        b = b_final.to(torch.float64).contiguous()
+        N, dev = a.shape[0], a.device
+
+        def vec(x):
+            if isinstance(x, torch.Tensor):
+                return x.to(device=dev, dtype=torch.float64).contiguous()
+            return torch.full((N,), float(x), dtype=torch.float64, device=dev)
+        t0, tf = vec(t_0), vec(t_f)
+        coef = torch.empty((N, 6), dtype=torch.float64, device=dev)
+        q, dq, ddq = (torch.empty((N, n), dtype=torch.float64, device=dev) for _ in range(3))
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().rk_poly5_f64(
+                _lib.ptr(a), _lib.ptr(b), _lib.ptr(t0), _lib.ptr(tf), N, int(n), _lib.ptr(coef),
+                _lib.ptr(q), _lib.ptr(dq), _lib.ptr(ddq), _lib.stream_ptr(dev)))
+        return coef, q, dq, ddq

@@ -89,6 +89,15 @@ class TrajectoryGenerator():
                 _lib.stream_ptr(dev)))
         return x, dx, t, qj, dqj, valid.bool(), length
 
+    def generate_joint_poly_trajectory_batch(self, qs_0, qs_f, t_f, t_0=0.0, n=100):
+        """Quintic joint trajectories for N x J boundary conditions: qs_0, qs_f CUDA tensors
+        [N, J, 3] -> q, dq, ddq [N, n, J] (generate_joint_poly_trajectory, :27-69, batched)."""
+        N, J = qs_0.shape[0], qs_0.shape[1]
+        _, q, dq, ddq = self._pg.profiles_batch(qs_0.reshape(N * J, 3), qs_f.reshape(N * J, 3),
+                                                t_f, t_0, n)
+        shape = lambda x: x.reshape(N, J, n).permute(0, 2, 1)  # noqa: E731
+        return shape(q), shape(dq), shape(ddq)
+
     @staticmethod
     def get_dq_from_dx_batch(qs, dxs, robot):
         """dq = J_v(q)^-1 dx for [N,3] CUDA tensors through the RRR Jacobian kernel."""

@@ -522,9 +522,41 @@ def gen_calibration(out_dir, rows):
     np.savez_compressed(os.path.join(out_dir, "reduced_models.npz"), **red)
 
 
+def gen_poly(out_dir):
+    """utils/polynomial_generator.py + TrajectoryGenerator.generate_joint_poly_trajectory."""
+    from utils.polynomial_generator import PolynomialGenerator
+    from utils.trajectory_generator import TrajectoryGenerator
+    rng = np.random.default_rng(6)
+    pg = PolynomialGenerator()
+    res = {}
+    cases = [([0, 0, 0], [1, 0, 0], 1.0, 0.0)]        # tests/test_polynomial_generator.py
+    for _ in range(30):
+        cases.append((list(rng.uniform(-2, 2, 3)), list(rng.uniform(-2, 2, 3)),
+                      float(rng.uniform(0.5, 4.0)), float(rng.choice([0.0, 0.0, 0.3, -0.5]))))
+    coefs, q, dq, ddq = [], [], [], []
+    n = 64
+    for q0, qf, tf, t0 in cases:
+        c = pg.generate_coefficients(q0, qf, t0 + tf, t0)
+        coefs.append(c)
+        q.append(pg.polynomial_from_coefs(c, t0, t0 + tf, n))
+        dq.append(pg.dpolynomial_from_coefs(1, c, t0, t0 + tf, n))
+        ddq.append(pg.dpolynomial_from_coefs(2, c, t0, t0 + tf, n))
+    res["q0"] = np.array([c[0] for c in cases])
+    res["qf"] = np.array([c[1] for c in cases])
+    res["tf"] = np.array([c[2] + c[3] for c in cases])
+    res["t0"] = np.array([c[3] for c in cases])
+    res["coefs"], res["q"], res["dq"], res["ddq"] = map(np.array, (coefs, q, dq, ddq))
+    tg = TrajectoryGenerator(1, 20, 1, 10)
+    q_0 = [[0.5, 0, 0], [-0.6, 0, 0], [0, 0, 0]]       # rrr_robot_planning.py:22-25
+    q_f = [[1.57, 0, 0], [0.5, 0, 0], [-2.0, 0, 0]]
+    res["planning_qs"] = tg.generate_joint_poly_trajectory(q_0, q_f, 2, t_0=0, n=50, plot=False)
+    np.savez_compressed(os.path.join(out_dir, "polynomial.npz"), **res)
+    print("poly done", flush=True, file=sys.__stdout__)
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="fanuc,jac,chain,rrr,traj,calib")
+    ap.add_argument("--only", default="fanuc,jac,chain,rrr,traj,calib,poly")
     ap.add_argument("--jobs", type=int, default=os.cpu_count())
     ap.add_argument("--n-rand", type=int, default=56)
     ap.add_argument("--calib-rows", type=int, default=240)
@@ -534,6 +566,8 @@ def main():
     dst = prepare_reference()
     import multiprocessing as mp
     pool = mp.Pool(args.jobs, initializer=_init_worker, initargs=(dst,))
+    if "poly" in only:
+        gen_poly(args.out)
     if "chain" in only:
         gen_generic_chain(args.out)
     if "traj" in only:

@@ -164,3 +164,16 @@ def test_polynomial_generator():
     coefs = pg.generate_coefficients([0, 0, 0], [1, 0, 0], 1.0)
     assert np.allclose(coefs, [0, 0, 0, 10, -15, 6])
     assert np.allclose(pg.dpolynomial_from_coefs(0, coefs, 0, 1, 11), pg.polynomial_from_coefs(coefs, 0, 1, 11))
+
+
+def test_calibration_mat_roundtrip(golden, tmp_path):
+    from roboticmanipulators_b200.utils.calibration_data import load_calibration_mat, save_calibration_mat
+    g = golden("calibration.npz")
+    path = str(tmp_path / "calibration_dataset.mat")
+    save_calibration_mat(path, g["qs"], g["pts"])
+    qs, pts = load_calibration_mat(path, device=None)
+    assert qs.shape == (240, 6) and pts.shape == (240, 9)
+    assert np.array_equal(qs, g["qs"])
+    assert np.max(np.abs(pts - g["pts"])) < 1e-9          # metres <-> millimetres round trip
+    qt, pt = load_calibration_mat(path, device="cpu")
+    assert qt.dtype == __import__("torch").float64 and tuple(pt.shape) == (240, 9)

@@ -241,3 +241,14 @@ def test_calibration_real_dataset(golden):
     assert np.allclose([ev2[k] for k in keys], g["eval_after_params"], rtol=1e-11)
     assert abs(ev2["distance_rms"] - 0.531528594785394) < 1e-9      # docs/GeometricCalibration.md:51
     assert abs(ev2["max_dist"] - 1.32318162735269) < 1e-9
+
+
+def test_polynomial_profiles(golden):
+    g = golden("polynomial.npz")
+    assert np.allclose(O.poly_coefficients([0, 0, 0], [1, 0, 0], 1.0), [0, 0, 0, 10, -15, 6])
+    for i in range(len(g["tf"])):
+        c = O.poly_coefficients(g["q0"][i], g["qf"][i], g["tf"][i], g["t0"][i])
+        assert np.array_equal(c, g["coefs"][i])
+        assert np.array_equal(O.poly_sample(c, 0, g["t0"][i], g["tf"][i], 64), g["q"][i])
+        assert np.array_equal(O.poly_sample(c, 1, g["t0"][i], g["tf"][i], 64), g["dq"][i])
+        assert np.array_equal(O.poly_sample(c, 2, g["t0"][i], g["tf"][i], 64), g["ddq"][i])

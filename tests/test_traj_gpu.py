@@ -152,3 +152,22 @@ def test_lin_trajectory_ik_and_joint_velocities(golden):
     assert np.max(np.abs(q.cpu().numpy() - rq)) < 1e-9
     good = rvalid & np.isfinite(rdq).all(-1) & (np.abs(rdq).max(-1) < 1e3)
     assert np.max(np.abs(dq.cpu().numpy()[good] - rdq[good])) < 1e-7
+
+
+def test_quintic_profiles(golden):
+    from roboticmanipulators_b200.utils.polynomial_generator import PolynomialGenerator
+    from roboticmanipulators_b200.utils.trajectory_generator import TrajectoryGenerator
+    g = golden("polynomial.npz")
+    coef, q, dq, ddq = PolynomialGenerator.profiles_batch(dev(g["q0"]), dev(g["qf"]), dev(g["tf"]), dev(g["t0"]), 64)
+    scale = lambda a: np.maximum(1.0, np.abs(a).max(axis=-1, keepdims=True))  # noqa: E731
+    assert np.max(np.abs(coef.cpu().numpy() - g["coefs"]) / scale(g["coefs"])) < 1e-11
+    assert np.max(np.abs(q.cpu().numpy() - g["q"]) / scale(g["q"])) < 1e-11
+    assert np.max(np.abs(dq.cpu().numpy() - g["dq"]) / scale(g["dq"])) < 1e-11
+    assert np.max(np.abs(ddq.cpu().numpy() - g["ddq"]) / scale(g["ddq"])) < 1e-11
+    assert np.allclose(coef[0].cpu().numpy(), [0, 0, 0, 10, -15, 6], atol=1e-12)   # reference test
+    tg = TrajectoryGenerator(1, 20, 1, 10)
+    q_0 = np.array([[[0.5, 0, 0], [-0.6, 0, 0], [0, 0, 0]]])
+    q_f = np.array([[[1.57, 0, 0], [0.5, 0, 0], [-2.0, 0, 0]]])
+    qb, _, _ = tg.generate_joint_poly_trajectory_batch(dev(q_0), dev(q_f), 2.0, 0.0, 50)
+    assert np.max(np.abs(qb[0].cpu().numpy() - g["planning_qs"])) < 1e-12
+    assert np.max(np.abs(tg.generate_joint_poly_trajectory(q_0[0], q_f[0], 2, n=50, plot=False) - g["planning_qs"])) < 1e-12
