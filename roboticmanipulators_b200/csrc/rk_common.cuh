@@ -127,8 +127,10 @@ __device__ __forceinline__ double fast_atan2(double y, double x) {
   const bool swap = ay > ax;
   const double mx = swap ? ay : ax, mn = swap ? ax : ay;
   const bool big = mn > 0x1.a827999fcef32p-2 * mx;
-  const double num = big ? mn - mx : mn;
-  const double den = big ? mn + mx : mx;
+  // bigf is 1.0 or 0.0: one select on the high word, then the octant shift is plain FMAs
+  const double bigf = __hiloint2double(big ? 0x3ff00000 : 0, 0);
+  const double num = fma(-bigf, mx, mn);  // big ? mn - mx : mn
+  const double den = fma(bigf, mn, mx);   // big ? mn + mx : mx
   const double r = fast_rcp(den);
   double u = num * r;
   u = fma(fma(-den, u, num), r, u);
@@ -147,7 +149,7 @@ __device__ __forceinline__ double fast_atan2(double y, double x) {
   po = fma(po, s2, kAtanPoly[1]);
   const double p = fma(po, s, pe);
   double a = fma(u * s, p, u);
-  if (big) a += 0x1.921fb54442d18p-1;           // pi/4
+  a = fma(bigf, 0x1.921fb54442d18p-1, a);       // + pi/4 in the upper octant
   if (swap) a = 0x1.921fb54442d18p+0 - a;       // pi/2
   if (__double2hiint(x) < 0) a = 0x1.921fb54442d18p+1 - a;  // pi
   a = copysign(a, y);
