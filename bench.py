@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1 << 26, help="poses per GPU per step")
     ap.add_argument("--e2e-batch", type=int, default=1 << 20)
     ap.add_argument("--layout", default="soa", choices=["soa", "aos"])
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="FK/IK arithmetic type")
     ap.add_argument("--ld-pad", type=int, default=0, help="extra elements between SOA planes")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-sample", type=int, default=500000)
@@ -251,7 +252,7 @@ def main():
         "value": value, "unit": wl.unit, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3) if args.warmup else 0,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "vs_baseline": None, "dtype": getattr(wl, "sfx", "f64"), "data": "synthetic",
         "config": wl.config, "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": wl.traffic.get(dom),

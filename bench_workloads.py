@@ -11,6 +11,28 @@ from roboticmanipulators_b200 import _lib
 from roboticmanipulators_b200.robots.fanuc import Fanuc165F
 
 
+def ncu_traffic_per_unit():
+    """DRAM bytes per unit of each kernel from the committed `ncu --set full` summaries
+    (profiles/*_ncu_full_summary.json, written by tools/ncu_summary.py)."""
+    import glob
+    import json
+    import os
+    out = {}
+    root = os.path.dirname(os.path.abspath(__file__))
+    for path in sorted(glob.glob(os.path.join(root, "profiles", "*_ncu_full_summary.json"))):
+        try:
+            for rec in json.load(open(path)):
+                if "traffic_bytes_per_unit" not in rec:
+                    continue
+                for key, pat in (("fanuc_fk_jac", "fanuc_fk_jac"), ("fanuc_ik8", "fanuc_ik8"),
+                                 ("calib_normal_eq", "calib_accumulate"), ("rrr_p2p_fk", "traj_kernel")):
+                    if pat in rec["kernel"]:
+                        out[key] = rec["traffic_bytes_per_unit"]
+        except (OSError, ValueError):
+            pass
+    return out
+
+
 def fp64_probe():
     """Measured FP64 FMA peak (dependent-free DFMA loop on all SMs)."""
     lib = _lib.load()
@@ -47,6 +69,8 @@ class FanucWorkload:
         self.lib = _lib.load()
         self.soa = args.layout == "soa"
         self.flags = _lib.RK_SOA if self.soa else _lib.RK_AOS
+        self.f32 = getattr(args, "dtype", "f64") == "f32"
+        self.sfx = "f32" if self.f32 else "f64"
         dev = torch.device("cuda")
         # distinct input batches (so 15 steps really are 1e9 different poses), capped at 48 GB
         nbuf = max(1, min(args.steps, int(48e9 // (48 * n))))
@@ -60,9 +84,11 @@ class FanucWorkload:
                 up = torch.empty((6, n + args.ld_pad), dtype=torch.float64, device=dev)
                 up[:, :n] = u
                 u = up
+            if self.f32:
+                u = u.float()
             self.q.append(u if self.soa else u.t().contiguous())
             del u
-        f64 = torch.float64
+        f64 = torch.float32 if self.f32 else torch.float64
         self.ld = n + getattr(args, "ld_pad", 0) if self.soa else n
         shape = (lambda c: (c, self.ld)) if self.soa else (lambda c: (n, c))
         self.T = torch.empty(shape(16), dtype=f64, device=dev)
@@ -75,15 +101,16 @@ class FanucWorkload:
             self._k1(self.q[0], with_j=False)
             torch.cuda.synchronize()
         self.events = []
-        self.alg_bytes = {"fanuc_fk_jac": 472, "fanuc_ik8": 520}
-        self.traffic = {}
+        self.alg_bytes = {"fanuc_fk_jac": 236, "fanuc_ik8": 264} if self.f32 else \
+            {"fanuc_fk_jac": 472, "fanuc_ik8": 520}
+        self.traffic = {} if self.f32 else {k: v * n for k, v in ncu_traffic_per_unit().items()}
         self.launches_per_step = {"fk_jac_ik": 2, "fk_jac": 1, "ik": 1}[self.mode]
         self.config = {
             "workload": {"fk_jac_ik": "fanuc165f_fk_jac_det_then_ik8",
                          "fk_jac": "fanuc165f_fk_jac_det", "ik": "fanuc165f_ik8"}[self.mode],
             "baseline_config": "configs[1] (+configs[2] IK on the same poses), chunked: "
                                f"{args.steps} steps x {n} poses per GPU",
-            "batch_per_gpu_per_step": n, "layout": args.layout,
+            "batch_per_gpu_per_step": n, "layout": args.layout, "dtype": self.sfx,
             "distinct_input_batches": nbuf,
             "l2": "inputs larger than L2 (each step streams >= 3.2 GB of fresh q and "
                   "overwrites >= 28 GB of outputs)",
@@ -92,13 +119,13 @@ class FanucWorkload:
 
     def _k1(self, q, with_j=True):
         st = _lib.stream_ptr()
-        _lib.check(self.lib.rk_fanuc_fk_jac_f64(
+        _lib.check(getattr(self.lib, "rk_fanuc_fk_jac_" + self.sfx)(
             C.byref(self.st), _lib.ptr(q), self.n, self.ld, self.flags, _lib.ptr(self.T),
             _lib.ptr(self.J) if with_j else None, _lib.ptr(self.det) if with_j else None, st))
 
     def _k2(self):
         st = _lib.stream_ptr()
-        _lib.check(self.lib.rk_fanuc_ik_f64(
+        _lib.check(getattr(self.lib, "rk_fanuc_ik_" + self.sfx)(
             C.byref(self.st), _lib.ptr(self.T), self.n, self.ld, self.flags, None, 8,
             _lib.ptr(self.qik), _lib.ptr(self.valid), st))
 
@@ -233,7 +260,7 @@ class CalibWorkload:
         torch.cuda.synchronize()
         self.events, self.params, self.host_ms = [], None, []
         self.alg_bytes = {"calib_normal_eq": 120}
-        self.traffic = {}
+        self.traffic = {k: v * m for k, v in ncu_traffic_per_unit().items()}
         self.launches_per_step = 1
         self.config = {
             "workload": "fanuc_calibration_normal_equations",

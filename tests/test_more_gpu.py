@@ -1,0 +1,143 @@
+"""GPU parity, second helping: option flags, custom robot constants, constant tokens in the
+generic chain, non-default streams, tool counts other than 3."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(x):
+    return torch.tensor(np.asarray(x, dtype=np.float64), device="cuda")
+
+
+def test_jacobian_user_angle_convention():
+    from roboticmanipulators_b200.robots import Fanuc165F
+    robot, c = Fanuc165F(), O.FanucConst()
+    rng = np.random.default_rng(0)
+    q = rng.uniform(c.lim[:, 0], c.lim[:, 1], size=(2000, 6))
+    _, Jm, dm = robot.forward_kinematics_batch(dev(q), jacobian=True, measure=True)
+    _, Ju, du = robot.forward_kinematics_batch(dev(q), jacobian=True, measure=True, user_angles=True)
+    dirs = torch.tensor(c.directions, device="cuda")
+    assert torch.equal(Ju, Jm * dirs)                       # column i scaled by directions[i]
+    assert torch.allclose(du, dm * float(np.prod(c.directions)), rtol=0, atol=0)
+    # finite-difference check of d p / d q_user on a few poses
+    h = 1e-6
+    for i in range(3):
+        for j in range(6):
+            qp, qm = q[i].copy(), q[i].copy()
+            qp[j] += h
+            qm[j] -= h
+            fd = (O.fanuc_fk(qp)[:3, 3] - O.fanuc_fk(qm)[:3, 3]) / (2 * h)
+            assert np.max(np.abs(fd - Ju[i, :3, j].cpu().numpy())) < 1e-4
+
+
+def test_custom_lengths_offsets_directions():
+    from roboticmanipulators_b200.robots import Fanuc165F
+    ls = (300.0, 350.0, 280.0, 900.0, 200.0, 1100.0, 180.0)
+    off = np.array([0.1, -1.2, 1.4, 0.0, 0.2, -0.3])
+    dirs = np.array([1, -1, 1, -1, 1, 1])
+    robot = Fanuc165F(lengths=ls, offsets=off, directions=dirs)
+    c = O.FanucConst(lengths=ls, offsets=off, directions=dirs)
+    assert abs(float(robot.d) - c.d) == 0 and abs(float(robot.dq) - c.dq) == 0
+    rng = np.random.default_rng(1)
+    q = rng.uniform(-1.0, 1.0, size=(3000, 6))
+    for layout in ("aos", "soa"):
+        T, J, det = robot.forward_kinematics_batch(dev(q), jacobian=True, measure=True, layout=layout)
+        T_ref, J_ref = O.fanuc_fk(q, c), O.fanuc_jacobian(q, c)
+        assert np.max(np.abs(T.cpu().numpy() - T_ref) / np.maximum(1, np.abs(T_ref))) < 1e-12
+        assert np.max(np.abs(J.cpu().numpy() - J_ref)) / np.abs(J_ref).max() < 1e-12
+        scale = np.prod(np.linalg.norm(J_ref, axis=1), axis=1)
+        assert np.all(np.abs(det.cpu().numpy() - np.linalg.det(J_ref)) <= 1e-12 * scale)
+        qb, vb = robot.inverse_kinematics_batch(T, layout=layout)
+        q_ref, v_ref = O.fanuc_ik_branches(T_ref, O.CANONICAL_8, c)
+        assert np.array_equal(vb.cpu().numpy(), v_ref)
+        d = qb.cpu().numpy() - q_ref
+        d[..., [3, 5]] = (d[..., [3, 5]] + np.pi) % (2 * np.pi) - np.pi
+        assert np.nanmax(np.abs(d)) < 1e-8
+
+
+def test_chain_with_constant_tokens():
+    from roboticmanipulators_b200.utils.robo_math import chain_batch
+    rng = np.random.default_rng(2)
+    tokens = O.tokens_from_sequence(O.FANUC_SEQ)
+    ls = O.FanucConst().ls
+    cst = [ls[0], 0, ls[1], ls[2], 0, ls[3], 0, ls[4], ls[5], 0, 0, 0, ls[6]]
+    src = [-1, 0, -1, -1, 1, -1, 2, -1, -1, 3, 4, 5, -1]         # joint angles come from 6 columns
+    qm = rng.uniform(-3, 3, size=(4000, 6))
+    for layout in ("aos", "soa"):
+        T, J = chain_batch(tokens, dev(qm), active=O.FANUC_IND, src=src, cst=cst, layout=layout)
+        vals = O.fanuc_values(qm, ls)
+        assert np.max(np.abs(T.cpu().numpy() - O.chain(tokens, vals))) / 3000 < 1e-13
+        J_ref = O.jacobian_numerically(O.FANUC_SEQ, O.FANUC_IND, vals)
+        assert np.max(np.abs(J.cpu().numpy() - J_ref)) / np.abs(J_ref).max() < 1e-13
+
+
+def test_non_default_stream_and_reentrancy():
+    from roboticmanipulators_b200.robots import Fanuc165F, RRRRobot
+    robot, c = Fanuc165F(), O.FanucConst()
+    rng = np.random.default_rng(3)
+    q = rng.uniform(c.lim[:, 0], c.lim[:, 1], size=(1 << 16, 6))
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    outs = []
+    qd = dev(q)
+    torch.cuda.synchronize()
+    for s in streams:
+        with torch.cuda.stream(s):
+            T, J, det = robot.forward_kinematics_batch(qd, jacobian=True, measure=True)
+            qb, vb = robot.inverse_kinematics_batch(T)
+            Tr = RRRRobot().forward_kinematics_batch(qd[:, :3].contiguous())
+            outs.append((T, J, det, qb, vb, Tr))
+    torch.cuda.synchronize()
+    T_ref = O.fanuc_fk(q, c)
+    for T, J, det, qb, vb, Tr in outs:
+        assert np.max(np.abs(T.cpu().numpy() - T_ref) / np.maximum(1, np.abs(T_ref))) < 1e-12
+        assert torch.equal(T, outs[0][0]) and torch.equal(qb.nan_to_num(), outs[0][3].nan_to_num())
+        assert torch.equal(vb, outs[0][4])
+
+
+def test_tool_base_other_tool_counts(golden):
+    from test_host_logic_cpu import fanuc_calibrator
+    from test_oracle_golden import _calib_model
+    g = golden("calibration.npz")
+    model = _calib_model(g)
+    for ntools in (1, 2, 4):
+        mc = fanuc_calibrator()
+        mc.get_reduced_model()
+        qs = g["qs"][:100]
+        tools = [O.chain("TxTyTz", v) for v in ([400, -20, 60], [420, 55, -15], [410, -40, -45], [390, 10, 5])][:ntools]
+        pts = np.concatenate([O.calib_pose(model, qs, np.zeros(18), g["T_base"], Tt)[:, :3, 3] for Tt in tools], axis=1)
+        T_base, T_tools = mc.estimate_tool_base(qs, pts[:, :, None])
+        A_sum, Adp = mc._last_tool_base_equations
+        Ao, bo = O.calib_tool_base_equations(model, qs, pts, np.zeros(18))
+        assert np.max(np.abs(A_sum - Ao)) / np.abs(Ao).max() < 1e-13
+        assert np.max(np.abs(Adp - bo)) / np.abs(bo).max() < 1e-12
+        assert len(T_tools) == ntools
+        # the estimate is the oracle's (a small-angle linearisation: it does not reproduce the
+        # generating base exactly, model_calibration.py:296-365)
+        est_o, Tb_o, Tt_o, _, _ = O.calib_estimate_tool_base(model, qs, pts, np.zeros(18))
+        assert np.max(np.abs(mc._base_est - est_o) / np.maximum(1, np.abs(est_o))) < 1e-8
+        assert np.max(np.abs(np.array(T_base, dtype=float) - Tb_o)) < 1e-6
+        ev = mc.evaluate(qs, pts[:, :, None], T_base, T_tools)
+        evo = O.calib_evaluate(model, qs, pts, np.zeros(18), Tb_o, Tt_o)
+        assert abs(ev["distance_rms"] - evo["distance_rms"]) < 1e-6
+
+
+def test_ik_f32_with_base_and_tool(golden):
+    from roboticmanipulators_b200.robots import Fanuc165F
+    g = golden("fanuc_fk_ik.npz")
+    robot = Fanuc165F(T_base=g["rotated_T_base"], T_tool=g["rotated_T_tool"])
+    c = O.FanucConst(g["rotated_T_base"], g["rotated_T_tool"])
+    rng = np.random.default_rng(5)
+    q = rng.uniform(c.lim[:, 0], c.lim[:, 1], size=(4096, 6))
+    T32 = torch.tensor(O.fanuc_fk(q, c), device="cuda", dtype=torch.float32)
+    for layout in ("aos", "soa"):
+        qb, vb = robot.inverse_kinematics_batch(T32, layout=layout)
+        q_ref, v_ref = O.fanuc_ik_branches(T32.cpu().numpy().astype(np.float64), O.CANONICAL_8, c)
+        assert (vb.cpu().numpy() == v_ref).mean() > 0.99
+        both = vb.cpu().numpy() & v_ref
+        d = qb.cpu().numpy().astype(np.float64) - q_ref
+        d[..., [3, 5]] = (d[..., [3, 5]] + np.pi) % (2 * np.pi) - np.pi
+        assert np.nanpercentile(np.abs(d[both]), 99) < 5e-3
