@@ -213,6 +213,9 @@ def main():
         sampler.start()
         time.sleep(0.12)
     torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()      # rank 0 slept while starting the clock sampler: line the ranks up again
+        torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     ev0.record()

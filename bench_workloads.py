@@ -277,12 +277,14 @@ class CalibWorkload:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if timed else None
         if timed:
             ev[0].record()
+        tl0 = time.perf_counter()
         out = self.mc.normal_equations(self.q, self.pts, self.T_base, self.T_tools,
                                        parameters=np.zeros(18), process_group=False)
         if timed:
             ev[1].record()
             self.events.append(ev)
         t0 = time.perf_counter()
+        self.launch_ms = getattr(self, "launch_ms", []) + [1e3 * (t0 - tl0)]
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(out)
@@ -296,6 +298,7 @@ class CalibWorkload:
     def kernel_times_ms(self):
         hm = np.mean(np.array(self.host_ms), axis=0)
         self.config["step_breakdown_ms"] = {
+            "host_compile_and_launch": float(np.mean(self.launch_ms[-len(self.host_ms):])),
             "wait_kernel_allreduce_d2h": float(hm[0]), "unpack_and_18x18_solve": float(hm[1])}
         return {"calib_normal_eq": float(np.mean([e[0].elapsed_time(e[1]) for e in self.events]))}
 
