@@ -59,6 +59,8 @@ struct Sc<double> {
   static __device__ __forceinline__ double acos(double x) { return ::acos(x); }
   static __device__ __forceinline__ double atan2(double y, double x) { return ::atan2(y, x); }
   static __device__ __forceinline__ double atan2_fast(double y, double x);
+  static __device__ __forceinline__ double atan2_core(double y, double x, bool& rare);
+  static __device__ __forceinline__ double rcp_fast(double x);
   static __device__ __forceinline__ double rsqrt_fast(double x);
   static __device__ __forceinline__ double sqrt_fast(double x);
   static __device__ __forceinline__ double abs(double x) { return ::fabs(x); }
@@ -78,6 +80,8 @@ struct Sc<float> {
   static __device__ __forceinline__ float acos(float x) { return ::acosf(x); }
   static __device__ __forceinline__ float atan2(float y, float x) { return ::atan2f(y, x); }
   static __device__ __forceinline__ float atan2_fast(float y, float x) { return ::atan2f(y, x); }
+  static __device__ __forceinline__ float atan2_core(float y, float x, bool&) { return ::atan2f(y, x); }
+  static __device__ __forceinline__ float rcp_fast(float x) { return 1.0f / x; }
   static __device__ __forceinline__ float rsqrt_fast(float x) { return ::rsqrtf(x); }
   static __device__ __forceinline__ float sqrt_fast(float x) { return ::sqrtf(x); }
   static __device__ __forceinline__ float abs(float x) { return ::fabsf(x); }
@@ -118,11 +122,13 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
   return fma(r, e, r);
 }
 
-// atan2(y, x), <= 2 ulp for finite normal operands; zeros, infinities, NaN, denormals and
-// huge values take the libm path.  Octant reduction to |u| <= tan(pi/8) with ONE division:
+// atan2(y, x), <= 2 ulp whenever max(|x|,|y|) is normal and moderate (exact zeros of the smaller
+// operand included); `rare` is raised for everything else (both zero, denormal/huge magnitudes,
+// inf, NaN) and the caller then takes libm.  Octant reduction to |u| <= tan(pi/8) with ONE division:
 //   t = min/max;  t > tan(pi/8):  atan t = pi/4 + atan((min - max)/(min + max)).
 // atan(u) = u + u^3 g(u^2), g = degree-10 interpolant at Chebyshev nodes (error 8e-18).
-__device__ __forceinline__ double fast_atan2(double y, double x) {
+// Straight-line code: no branch, so independent calls interleave in the FP64 pipe.
+__device__ __forceinline__ double fast_atan2_core(double y, double x, bool& rare) {
   const double ax = fabs(x), ay = fabs(y);
   const bool swap = ay > ax;
   const double mx = swap ? ay : ax, mn = swap ? ax : ay;
@@ -131,7 +137,11 @@ __device__ __forceinline__ double fast_atan2(double y, double x) {
   const double bigf = __hiloint2double(big ? 0x3ff00000 : 0, 0);
   const double num = fma(-bigf, mx, mn);  // big ? mn - mx : mn
   const double den = fma(bigf, mn, mx);   // big ? mn + mx : mx
-  const double r = fast_rcp(den);
+  // u = num / den: hardware seed (2^-23), one Newton step (2^-46), then one residual
+  // correction of the quotient itself (<= 0.5 ulp + 2^-92)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+  r = fma(r, fma(-den, r, 1.0), r);
   double u = num * r;
   u = fma(fma(-den, u, num), r, u);
   const double s = u * u, s2 = s * s;
@@ -153,12 +163,16 @@ __device__ __forceinline__ double fast_atan2(double y, double x) {
   if (swap) a = 0x1.921fb54442d18p+0 - a;       // pi/2
   if (__double2hiint(x) < 0) a = 0x1.921fb54442d18p+1 - a;  // pi
   a = copysign(a, y);
-  // The straight-line path above is valid when den and mn are normal and moderate:
-  // exponent window test on the high words (den >= mn >= 0), both in [2^-900, 2^+900].
-  // Zero, denormal, huge, inf and NaN operands fail it and take libm.  The test comes
-  // LAST so that several independent calls can be interleaved by the scheduler.
-  const unsigned hd = (unsigned)__double2hiint(den), hm = (unsigned)__double2hiint(mn);
-  if (hd - 0x07b00000u > 0x70800000u || hm < 0x07b00000u) a = ::atan2(y, x);
+  // valid when den = max (+ min) is in [2^-900, 2^+900]: exponent window on its high word
+  // (den >= 0).  Zero, denormal, huge, inf and NaN fail it.
+  rare = rare || ((unsigned)__double2hiint(den) - 0x07b00000u > 0x70800000u);
+  return a;
+}
+
+__device__ __forceinline__ double fast_atan2(double y, double x) {
+  bool rare = false;
+  double a = fast_atan2_core(y, x, rare);
+  if (rare) a = ::atan2(y, x);
   return a;
 }
 
@@ -212,6 +226,10 @@ __device__ __forceinline__ double fast_sqrt(double t) {
 }
 
 __device__ __forceinline__ double Sc<double>::atan2_fast(double y, double x) { return fast_atan2(y, x); }
+__device__ __forceinline__ double Sc<double>::atan2_core(double y, double x, bool& rare) {
+  return fast_atan2_core(y, x, rare);
+}
+__device__ __forceinline__ double Sc<double>::rcp_fast(double x) { return fast_rcp(x); }
 __device__ __forceinline__ double Sc<double>::rsqrt_fast(double x) { return fast_rsqrt(x); }
 __device__ __forceinline__ void Sc<double>::sincos(double x, double* s, double* c) { fast_sincos(x, s, c); }
 __device__ __forceinline__ double Sc<double>::sqrt_fast(double x) { return fast_sqrt(x); }

@@ -11,6 +11,7 @@ template <typename S>
 struct FanucP {
   S l[7], off[6], dir[6], lo[6], hi[6];
   S d, dq, eps, cdq, sdq;
+  S dd, l3l3, den, rden;  // d*d, l3*l3, 2*d*l3 rounded exactly as fanuc.py:233-234 does; 1/den
   S Tb[12], Tt[12], Tbi[12], Tti[12];
   int has_base, has_tool, user_jac;
 };
@@ -28,6 +29,10 @@ static FanucP<S> make_params(const RkFanuc* r, int flags) {
   p.d = (S)r->d;
   p.dq = (S)r->dq;
   p.eps = (S)r->eps;
+  p.dd = p.d * p.d;
+  p.l3l3 = p.l[3] * p.l[3];
+  p.den = (S(2) * p.d) * p.l[3];
+  p.rden = S(1) / p.den;
   p.cdq = (S)cos(r->dq);
   p.sdq = (S)sin(r->dq);
   for (int i = 0; i < 12; ++i) {
@@ -477,6 +482,104 @@ __device__ __forceinline__ void fanuc_ik_mk(const FanucP<S>& P, const S (&R0)[9]
   }
 }
 
+// All 8 canonical branches of ONE pose in ONE thread (the SOA fast path of K2).  What depends
+// only on the pose (q0, the Rz(-q0) R0 rows) is computed once, what depends only on k (acos,
+// beta, gamma and their unit vectors) twice, the wrist four times; m and k are compile-time
+// signs, so their multiplications disappear.  The code is straight-line: every data-dependent
+// special case of fanuc_ik_mk (arm on the axis :253-255, wrist singular :272, |r13| <= eps
+// :279-282, degenerate lengths, operands outside fast_atan2_core's domain) only raises the
+// returned `rare` flag, and the caller recomputes such a pose with fanuc_ik_mk.  The 19 atan2
+// and 9 sqrt/rsqrt of a pose are independent chains the scheduler interleaves.
+// Branch index b = 4*[m==-1] + 2*[k==-1] + w; emitted through out.q(b, j, v) / out.ok(b, flag).
+template <typename S, typename Out>
+__device__ __forceinline__ bool fanuc_ik8_pose(const FanucP<S>& P, const S (&R0)[9], const S (&p0)[3],
+                                               Out& out) {
+  using M = Sc<S>;
+  bool rare = false;
+  const S l1 = P.l[1], l2 = P.l[2], l3 = P.l[3], d = P.d;
+  const S x = p0[0], y = p0[1], z = p0[2];
+  // fanuc.py:228-230 (operation by operation: these decide reachability)
+  const S rxy = M::sqrt(M::add(M::mul(x, x), M::mul(y, y)));
+  const S zp = M::sub(l1, z);
+  const S zp2 = M::mul(zp, zp);
+  const S q0 = M::atan2_core(y, x, rare);  // :246
+  rare = rare || !(rxy > S(1e-100));
+  const S irxy = M::rcp_fast(rxy);
+  const S c0 = x * irxy, s0 = y * irxy;
+  // rows of Rz(-q0) R0
+  const S a0 = c0 * R0[0] + s0 * R0[3], a1 = c0 * R0[1] + s0 * R0[4], a2 = c0 * R0[2] + s0 * R0[5];
+  const S r21 = c0 * R0[3] - s0 * R0[0];
+  const S u0 = M::mul(M::sub(q0, P.off[0]), P.dir[0]);       // :290
+  const bool out0 = (u0 < P.lo[0]) || (u0 > P.hi[0]);         // :292-297 (NaN passes)
+#pragma unroll
+  for (int ki = 0; ki < 2; ++ki) {
+    const S xp = M::sub(ki ? -rxy : rxy, l2);                 // k * rxy - l2
+    const S rg2 = M::add(M::mul(xp, xp), zp2);
+    // psi_cos = num / den (:231-234).  |RN(num/den)| > 1 <=> |num| > |den| for IEEE doubles, so
+    // the reachability test (:237-239) needs no division; the quotient itself is num * (1/den)
+    // with one residual correction (<= 1 ulp).
+    const S num = M::sub(M::sub(rg2, P.dd), P.l3l3);
+    const bool reach = !(M::abs(num) > M::abs(P.den));
+    S pc = num * P.rden;
+    pc = fma(fma(-pc, P.den, num), P.rden, pc);
+    const S c = reach ? pc : S(0.5);                          // unreachable: computed, discarded
+    const S sabs = M::sqrt_fast((S(1) - c) * (S(1) + c));     // sin(acos c) >= 0
+    const S sb = -d * sabs, cb = l3 + d * c;                  // beta operands for m = +1
+    const S acosc = M::atan2_core(sabs, c, rare);             // :241
+    const S beta = M::atan2_core(sb, cb, rare);               // :242-243 (m = +1; odd in m)
+    const S gamma = M::atan2_core(zp, xp, rare);              // :244
+    rare = rare || !(rg2 > S(1e-200));
+    // |(sb, cb)|^2 = d^2 + l3^2 + 2 d l3 c = x'^2 + z'^2 (cosine rule): one rsqrt serves both
+    const S irg = M::rsqrt_fast(rg2);
+    const S cg = xp * irg, sg = zp * irg, cbn = cb * irg, sbn = sb * irg;
+    const S cc = cg * cbn, ss = sg * sbn, sc = sg * cbn, cs = cg * sbn;
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+      // m = +1: psi = -acos, q1 = gamma - beta;  m = -1: psi = +acos, q1 = gamma + beta
+      const S psi = mi ? acosc : -acosc;
+      const S q1 = mi ? M::add(gamma, beta) : M::sub(gamma, beta);  // :247
+      const S q2 = M::add(psi, P.dq);                                // :248
+      const S c1 = mi ? cc - ss : cc + ss;                           // cos(q1)
+      const S s1 = mi ? sc + cs : sc - cs;
+      const S sps = mi ? sabs : -sabs;                               // sin(psi)
+      const S c1p = c1 * c - s1 * sps;                               // cos(q1 + psi)
+      const S s1p = s1 * c + c1 * sps;
+      const S A = d * c1p + l2 + l3 * c1;                            // :250-251
+      rare = rare || (M::abs(A) < P.eps);                            // :253-255
+      const S ct = c1p * P.cdq - s1p * P.sdq;                        // cos(q1 + q2)
+      const S st = s1p * P.cdq + c1p * P.sdq;
+      // T_rot = Ry(-dq) T_012^-1 T_0 (:262-264): rotation Ry(-(q1+q2)) Rz(-q0) R0
+      const S r11 = ct * a0 - st * R0[6];
+      const S r12 = ct * a1 - st * R0[7];
+      const S r13 = ct * a2 - st * R0[8];
+      const S r31 = st * a0 + ct * R0[6];
+      rare = rare || !(M::abs(r11 - S(1)) > P.eps) || !(M::abs(r13) > P.eps);  // :272, :279
+      const S a3 = M::atan2_core(r21, -r31, rare);                   // :273
+      const S a5 = M::atan2_core(r12, r13, rare);                    // :274
+      const S q4p = M::atan2_core(M::sqrt_fast(r12 * r12 + r13 * r13), r11, rare);  // :280, w = 0
+      const S u1 = M::mul(M::sub(q1, P.off[1]), P.dir[1]);
+      const S u2 = M::mul(M::sub(q2, P.off[2]), P.dir[2]);
+      const bool bad = !reach || out0 || (u1 < P.lo[1]) || (u1 > P.hi[1]) || (u2 < P.lo[2]) ||
+                       (u2 > P.hi[2]);
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        const S q3 = w ? M::sub(a3, M::pi()) : a3;                   // :276
+        const S q5 = w ? M::sub(a5, M::pi()) : a5;                   // :277
+        const S q4 = w ? -q4p : q4p;      // :280: r13 / cos(q5) = +-hypot(r12, r13)
+        const S u3 = M::mul(M::sub(q3, P.off[3]), P.dir[3]);
+        const S u4 = M::mul(M::sub(q4, P.off[4]), P.dir[4]);
+        const S u5 = M::mul(M::sub(q5, P.off[5]), P.dir[5]);
+        const bool ok = !(bad || (u3 < P.lo[3]) || (u3 > P.hi[3]) || (u4 < P.lo[4]) ||
+                          (u4 > P.hi[4]) || (u5 < P.lo[5]) || (u5 > P.hi[5]));
+        const int b = mi * 4 + ki * 2 + w;
+        const S u[6] = {u0, u1, u2, u3, u4, u5};
+        out.branch(b, ok, u);  // the solution, or the all-zero failure sentinel (:239, :300)
+      }
+    }
+  }
+  return rare;
+}
+
 template <typename S, bool SOA>
 __device__ __forceinline__ void load_T12(const S* __restrict__ T, int64_t i, int64_t ld, S (&Tin)[12]) {
   const S* p = SOA ? T + i : T + i * 16;
@@ -638,6 +741,93 @@ fanuc_ik8_tma_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant_
   if (tid == 0) bulk_wait_all();
 }
 
+// SOA fast path, thread-per-pose: one thread computes all 8 branches of its pose with
+// fanuc_ik8_pose (about half the instructions per pose of the 4-lanes-per-pose mapping, which
+// replicates the pose- and k-level work and spends ~200 instructions per lane on uniform-register
+// spills and lane pairing).  Every warp runs its own pipeline over 32-pose tiles: the tile's 12
+// input planes arrive by one 2-D TMA load ([12][32] box, double buffered, issued one tile ahead,
+// per-warp mbarriers -- no CTA barrier anywhere); each result is stored to its SOA plane the
+// moment it exists (a warp store = one contiguous 256-byte run; `st.global.cs`).
+template <typename S>
+struct IkPlaneSink {
+  S* qp;
+  uint8_t* vp;
+  int64_t ld;
+  __device__ __forceinline__ void q(int b, int j, S v) { __stcs(qp + (int64_t)(b * 6 + j) * ld, v); }
+  __device__ __forceinline__ void branch(int b, bool okf, const S (&u)[6]) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) q(b, j, okf ? u[j] : S(0));
+    ok(b, okf);
+  }
+  __device__ __forceinline__ void ok(int b, bool f) { vp[(int64_t)b * ld] = f ? 1 : 0; }
+};
+
+template <typename S>
+struct alignas(128) IkPoseTile {
+  static constexpr int kPoses = kWarp;
+  S in[2][12][kPoses];
+  uint64_t bar[2];
+};
+
+template <typename S>
+__global__ void __launch_bounds__(kBlock, 4)
+fanuc_ik8_pose_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant__ CUtensorMap tmT,
+                      S* __restrict__ q_out, uint8_t* __restrict__ valid, int64_t n, int64_t ld,
+                      int64_t ntiles) {
+  using Tile = IkPoseTile<S>;
+  constexpr int TP = Tile::kPoses;
+  constexpr int WPB = kBlock / kWarp;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Tile& sm = reinterpret_cast<Tile*>(smem_raw)[warp];
+  if (lane == 0) {
+    mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  auto issue_load = [&](int64_t tile, int buf) {  // one lane
+    mbar_expect_tx(&sm.bar[buf], 12 * TP * sizeof(S));
+    tma_load_2d(&sm.in[buf][0][0], &tmT, (int)(tile * TP), 0, &sm.bar[buf]);
+  };
+  const int64_t stride = (int64_t)gridDim.x * WPB;
+  int64_t tile = (int64_t)blockIdx.x * WPB + warp;
+  if (lane == 0 && tile < ntiles) issue_load(tile, 0);
+  int it = 0;
+  for (; tile < ntiles; tile += stride, ++it) {
+    const int buf = it & 1;
+    const int64_t next = tile + stride;
+    // sm.in[buf ^ 1] was consumed by every lane one iteration ago (the __syncwarp below)
+    if (lane == 0 && next < ntiles) issue_load(next, buf ^ 1);
+    mbar_wait(&sm.bar[buf], (it >> 1) & 1);
+    S Tin[12];
+#pragma unroll
+    for (int c = 0; c < 12; ++c) Tin[c] = sm.in[buf][c][lane];
+    __syncwarp();
+    const int64_t i = tile * TP + lane;
+    if (i >= n) continue;  // ragged last tile (the TMA load zero-filled it)
+    S R0[9], p0[3];
+    fanuc_ik_t0(P, Tin, R0, p0);
+    IkPlaneSink<S> sink{q_out + i, valid + i, ld};
+    if (fanuc_ik8_pose(P, R0, p0, sink)) {
+      // measure-zero configurations: the branch-by-branch routine with all its special cases
+#pragma unroll 1
+      for (int mk = 0; mk < 4; ++mk) {
+        const int wl[2] = {0, 1};
+        S qo[2][6];
+        bool ok[2];
+        fanuc_ik_mk<S, 2, false>(P, R0, p0, (mk & 2) ? -1 : 1, (mk & 1) ? -1 : 1, wl, qo, ok);
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+#pragma unroll
+          for (int j = 0; j < 6; ++j) sink.q(mk * 2 + w, j, qo[w][j]);
+          sink.ok(mk * 2 + w, ok[w]);
+        }
+      }
+    }
+  }
+}
+
 // Arbitrary branch list: one thread per (pose, branch).
 struct BranchList {
   int8_t mkw[3 * 16];
@@ -747,23 +937,15 @@ static int launch_ik(const RkFanuc* robot, const S* T, int64_t n, int64_t ld, in
     // 128 registers / 4 CTAs per SM measured best (3: 8.1 ms, 4: 7.2 ms, 5: 7.2 ms, 6 spills: 8.1 ms
     // per 2^25 poses)
     if (soa) {
-      // TMA path when the three arrays satisfy the tensor-map alignment rules, LSU kernel otherwise
-      constexpr int TP = Ik8Tile<S>::kPoses;
-      CUtensorMap tmT, tmQ, tmV;
-      const bool tma_ok =
-          make_tmap_2d(&tmT, TmapType<S>::value, sizeof(S), T, n, 12, ld * sizeof(S), TP, 12) &&
-          make_tmap_2d(&tmQ, TmapType<S>::value, sizeof(S), q_out, n, 48, ld * sizeof(S), TP, 48) &&
-          make_tmap_2d(&tmV, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, valid, n, 8, ld, TP, 8);
-      if (tma_ok) {
+      // thread-per-pose kernel when T satisfies the tensor-map alignment rules (16-byte base and
+      // pitch), 4-lanes-per-pose LSU kernel otherwise
+      constexpr int TP = IkPoseTile<S>::kPoses;
+      CUtensorMap tmT;
+      if (make_tmap_2d(&tmT, TmapType<S>::value, sizeof(S), T, n, 12, ld * sizeof(S), TP, 12)) {
         const int64_t ntiles = (n + TP - 1) / TP;
-        const size_t smem = sizeof(Ik8Tile<S>);
-        static thread_local bool attr_done = false;
-        if (!attr_done) {
-          cudaFuncSetAttribute(fanuc_ik8_tma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          attr_done = true;
-        }
-        int grid = persistent_grid(fanuc_ik8_tma_kernel<S>, kBlock, smem, ntiles * kBlock);
-        fanuc_ik8_tma_kernel<S><<<grid, kBlock, smem, st>>>(P, tmT, tmQ, tmV, ntiles);
+        const size_t smem = sizeof(IkPoseTile<S>) * (kBlock / kWarp);
+        int grid = persistent_grid(fanuc_ik8_pose_kernel<S>, kBlock, smem, ntiles * kWarp);
+        fanuc_ik8_pose_kernel<S><<<grid, kBlock, smem, st>>>(P, tmT, q_out, valid, n, ld, ntiles);
       } else {
         int grid = persistent_grid(fanuc_ik8_kernel<S, true, 4>, kBlock, 0, n * 4);
         fanuc_ik8_kernel<S, true, 4><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
