@@ -64,6 +64,14 @@ struct Sc<double> {
   static __device__ __forceinline__ double rsqrt_fast(double x);
   static __device__ __forceinline__ double sqrt_fast(double x);
   static __device__ __forceinline__ double abs(double x) { return ::fabs(x); }
+  // neg ? -x : x by an integer XOR on the sign bit (keeps the FP64 pipe free; neg is 0 or 1)
+  static __device__ __forceinline__ double flip(double x, int neg) {
+    return __hiloint2double(__double2hiint(x) ^ (neg << 31), __double2loint(x));
+  }
+  // x with its sign bit XORed by mask (0 or 0x80000000): multiplication by +-1 without the FP64 pipe
+  static __device__ __forceinline__ double flipm(double x, unsigned mask) {
+    return __hiloint2double(__double2hiint(x) ^ (int)mask, __double2loint(x));
+  }
   static __device__ __forceinline__ double pi() { return 3.141592653589793; }
 };
 
@@ -85,6 +93,12 @@ struct Sc<float> {
   static __device__ __forceinline__ float rsqrt_fast(float x) { return ::rsqrtf(x); }
   static __device__ __forceinline__ float sqrt_fast(float x) { return ::sqrtf(x); }
   static __device__ __forceinline__ float abs(float x) { return ::fabsf(x); }
+  static __device__ __forceinline__ float flip(float x, int neg) {
+    return __int_as_float(__float_as_int(x) ^ (neg << 31));
+  }
+  static __device__ __forceinline__ float flipm(float x, unsigned mask) {
+    return __int_as_float(__float_as_int(x) ^ (int)mask);
+  }
   static __device__ __forceinline__ float pi() { return 3.14159265358979323846f; }
 };
 
@@ -129,12 +143,15 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
 // atan(u) = u + u^3 g(u^2), g = degree-10 interpolant at Chebyshev nodes (error 8e-18).
 // Straight-line code: no branch, so independent calls interleave in the FP64 pipe.
 __device__ __forceinline__ double fast_atan2_core(double y, double x, bool& rare) {
-  const double ax = fabs(x), ay = fabs(y);
+  // |x|, |y| by integer masks and the octant flag from the sign of mn - tan(pi/8) mx: the FP64
+  // pipe sees one compare and one FMA here
+  const double ax = __hiloint2double(__double2hiint(x) & 0x7fffffff, __double2loint(x));
+  const double ay = __hiloint2double(__double2hiint(y) & 0x7fffffff, __double2loint(y));
   const bool swap = ay > ax;
   const double mx = swap ? ay : ax, mn = swap ? ax : ay;
-  const bool big = mn > 0x1.a827999fcef32p-2 * mx;
-  // bigf is 1.0 or 0.0: one select on the high word, then the octant shift is plain FMAs
-  const double bigf = __hiloint2double(big ? 0x3ff00000 : 0, 0);
+  const double t8 = fma(-0x1.a827999fcef32p-2, mx, mn);
+  // bigf is 1.0 (upper octant) or 0.0: the octant shift is then plain FMAs
+  const double bigf = __hiloint2double(~(__double2hiint(t8) >> 31) & 0x3ff00000, 0);
   const double num = fma(-bigf, mx, mn);  // big ? mn - mx : mn
   const double den = fma(bigf, mn, mx);   // big ? mn + mx : mx
   // u = num / den: hardware seed (2^-23), one Newton step (2^-46), then one residual
@@ -217,11 +234,16 @@ __device__ __forceinline__ void fast_sincos(double x, double* sp, double* cp) {
 }
 
 // sqrt(t) for t >= 0 without the IEEE slow-path branch (<= 1 ulp); 0 for t <= 0 or tiny.
+// Hardware seed (2^-23), one Newton step on 1/sqrt (2^-45), then the residual correction of the
+// root itself, which squares the error again.
 __device__ __forceinline__ double fast_sqrt(double t) {
   const bool ok = t > 1e-290;
-  const double rs = fast_rsqrt(ok ? t : 1.0);
-  double r = t * rs;
-  r = fma(fma(-r, r, t), 0.5 * rs, r);
+  const double x = ok ? t : 1.0;
+  double rs;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(rs) : "d"(x));
+  rs = fma(rs, fma(-0.5 * x * rs, rs, 0.5), rs);
+  double r = x * rs;
+  r = fma(fma(-r, r, x), 0.5 * rs, r);
   return ok ? r : 0.0;
 }
 
@@ -300,6 +322,18 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int x, int 
                : "memory");
 }
 
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                             const void* smem_src) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(map),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(smem_src))
+               : "memory");
+}
+
+// Warp index as a value the compiler knows to be warp-uniform (broadcast from lane 0): tile
+// indices, shared-memory tile addresses and TMA coordinates derived from it then live in uniform
+// registers instead of being re-uniformised by a loop before every TMA instruction.
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // Host: encode a [rows][cols] tensor with row pitch `pitch_bytes` and box [box_rows][box_cols].
 // Returns false when the driver entry point is unavailable or the layout violates TMA's
 // alignment rules (16-byte base and pitch) -- callers then use the LSU kernels.
@@ -329,6 +363,41 @@ inline bool make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_byte
   const cuuint32_t estr[2] = {1, 1};
   return fn(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Host: general tiled tensor map of `rank` dimensions (dim 0 innermost, contiguous); strides[i] is
+// the byte stride of dimension i+1.  Same failure conventions as make_tmap_2d.
+inline bool make_tmap_nd(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, int rank,
+                         const uint64_t* dims, const uint64_t* strides, const uint32_t* box) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeFn)p;
+    cudaGetLastError();
+  }
+  if (!fn || rank < 1 || rank > 5) return false;
+  if (((uintptr_t)base & 15) || ((uint64_t)box[0] * elem_bytes & 15)) return false;
+  cuuint64_t gdim[5], gstride[4];
+  cuuint32_t bx[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    if (dims[i] == 0 || dims[i] > 0x7fffffffull || box[i] == 0 || box[i] > 256) return false;
+    gdim[i] = dims[i], bx[i] = box[i], estr[i] = 1;
+    if (i + 1 < rank) {
+      if (strides[i] & 15) return false;
+      gstride[i] = strides[i];
+    }
+  }
+  return fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstride, bx, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 

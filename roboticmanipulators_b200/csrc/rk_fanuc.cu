@@ -2,6 +2,7 @@
 // One thread owns one pose (K1) or one (pose, elbow/root branch) pair (K2); the screw
 // chain is unrolled in registers.  See include/rk_b200.h for the reference citations.
 #include <cmath>
+#include <cstdlib>
 
 #include "rk_common.cuh"
 
@@ -14,7 +15,23 @@ struct FanucP {
   S dd, l3l3, den, rden;  // d*d, l3*l3, 2*d*l3 rounded exactly as fanuc.py:233-234 does; 1/den
   S Tb[12], Tt[12], Tbi[12], Tti[12];
   int has_base, has_tool, user_jac;
+  unsigned smask[6];  // sign-bit mask of dir[j] (used when every direction is +-1)
+  int std_limits;     // see fanuc_std_limits()
 };
+
+// The stock Fanuc165F constants (fanuc.py:79-86, :101-111) have a structure the IK limit test can
+// use: every direction is +-1, joints 0, 3, 4, 5 have no offset, and every joint but 1 has limits
+// symmetric about zero.  Then (q - off) * dir is a sign flip and lo <= u <= hi is one |.| compare,
+// bit-identical to the reference's two compares.  Any other constants take the general code.
+static bool fanuc_std_limits(const RkFanuc* r) {
+  for (int i = 0; i < 6; ++i)
+    if (r->directions[i] != 1.0 && r->directions[i] != -1.0) return false;
+  for (int i : {0, 3, 4, 5})
+    if (r->offsets[i] != 0.0) return false;
+  for (int i : {0, 2, 3, 4, 5})
+    if (r->lim_lo[i] != -r->lim_hi[i]) return false;
+  return true;
+}
 
 template <typename S>
 static FanucP<S> make_params(const RkFanuc* r, int flags) {
@@ -44,6 +61,8 @@ static FanucP<S> make_params(const RkFanuc* r, int flags) {
   p.has_base = r->has_base;
   p.has_tool = r->has_tool;
   p.user_jac = (flags & RK_JAC_USER_ANGLES) ? 1 : 0;
+  for (int i = 0; i < 6; ++i) p.smask[i] = r->directions[i] < 0 ? 0x80000000u : 0u;
+  p.std_limits = fanuc_std_limits(r) ? 1 : 0;
   return p;
 }
 
@@ -491,7 +510,7 @@ __device__ __forceinline__ void fanuc_ik_mk(const FanucP<S>& P, const S (&R0)[9]
 // returned `rare` flag, and the caller recomputes such a pose with fanuc_ik_mk.  The 19 atan2
 // and 9 sqrt/rsqrt of a pose are independent chains the scheduler interleaves.
 // Branch index b = 4*[m==-1] + 2*[k==-1] + w; emitted through out.q(b, j, v) / out.ok(b, flag).
-template <typename S, typename Out>
+template <typename S, int UK, int UM, bool STD, typename Out>
 __device__ __forceinline__ bool fanuc_ik8_pose(const FanucP<S>& P, const S (&R0)[9], const S (&p0)[3],
                                                Out& out) {
   using M = Sc<S>;
@@ -509,11 +528,23 @@ __device__ __forceinline__ bool fanuc_ik8_pose(const FanucP<S>& P, const S (&R0)
   // rows of Rz(-q0) R0
   const S a0 = c0 * R0[0] + s0 * R0[3], a1 = c0 * R0[1] + s0 * R0[4], a2 = c0 * R0[2] + s0 * R0[5];
   const S r21 = c0 * R0[3] - s0 * R0[0];
-  const S u0 = M::mul(M::sub(q0, P.off[0]), P.dir[0]);       // :290
-  const bool out0 = (u0 < P.lo[0]) || (u0 > P.hi[0]);         // :292-297 (NaN passes)
-#pragma unroll
+  // user angle u = (q - off) * dir (:290) and its limit test (:292-297; NaN passes).  STD: the
+  // constants satisfy fanuc_std_limits(), so u is a sign flip and symmetric limits need one compare.
+  S u0;
+  bool out0;
+  if (STD) {
+    u0 = M::flipm(q0, P.smask[0]);
+    out0 = M::abs(q0) > P.hi[0];
+  } else {
+    u0 = M::mul(M::sub(q0, P.off[0]), P.dir[0]);
+    out0 = (u0 < P.lo[0]) || (u0 > P.hi[0]);
+  }
+  // The k and m loops are unrolled or rolled by template choice (code size vs instruction-level
+  // parallelism: fully unrolled the pose is 32 KB of straight-line code, the size of the L1.5
+  // instruction cache); ki/mi = 1 means k/m = -1, applied as sign-bit flips.
+#pragma unroll UK
   for (int ki = 0; ki < 2; ++ki) {
-    const S xp = M::sub(ki ? -rxy : rxy, l2);                 // k * rxy - l2
+    const S xp = M::sub(M::flip(rxy, ki), l2);                // k * rxy - l2
     const S rg2 = M::add(M::mul(xp, xp), zp2);
     // psi_cos = num / den (:231-234).  |RN(num/den)| > 1 <=> |num| > |den| for IEEE doubles, so
     // the reachability test (:237-239) needs no division; the quotient itself is num * (1/den)
@@ -533,15 +564,14 @@ __device__ __forceinline__ bool fanuc_ik8_pose(const FanucP<S>& P, const S (&R0)
     const S irg = M::rsqrt_fast(rg2);
     const S cg = xp * irg, sg = zp * irg, cbn = cb * irg, sbn = sb * irg;
     const S cc = cg * cbn, ss = sg * sbn, sc = sg * cbn, cs = cg * sbn;
-#pragma unroll
+#pragma unroll UM
     for (int mi = 0; mi < 2; ++mi) {
       // m = +1: psi = -acos, q1 = gamma - beta;  m = -1: psi = +acos, q1 = gamma + beta
-      const S psi = mi ? acosc : -acosc;
-      const S q1 = mi ? M::add(gamma, beta) : M::sub(gamma, beta);  // :247
-      const S q2 = M::add(psi, P.dq);                                // :248
-      const S c1 = mi ? cc - ss : cc + ss;                           // cos(q1)
-      const S s1 = mi ? sc + cs : sc - cs;
-      const S sps = mi ? sabs : -sabs;                               // sin(psi)
+      const S q1 = M::sub(gamma, M::flip(beta, mi));                 // :247
+      const S q2 = M::sub(P.dq, M::flip(acosc, mi));                 // :248 (psi + dq)
+      const S c1 = cc + M::flip(ss, mi);                             // cos(q1)
+      const S s1 = sc - M::flip(cs, mi);
+      const S sps = M::flip(sabs, 1 - mi);                           // sin(psi)
       const S c1p = c1 * c - s1 * sps;                               // cos(q1 + psi)
       const S s1p = s1 * c + c1 * sps;
       const S A = d * c1p + l2 + l3 * c1;                            // :250-251
@@ -553,29 +583,55 @@ __device__ __forceinline__ bool fanuc_ik8_pose(const FanucP<S>& P, const S (&R0)
       const S r12 = ct * a1 - st * R0[7];
       const S r13 = ct * a2 - st * R0[8];
       const S r31 = st * a0 + ct * R0[6];
-      rare = rare || !(M::abs(r11 - S(1)) > P.eps) || !(M::abs(r13) > P.eps);  // :272, :279
-      const S a3 = M::atan2_core(r21, -r31, rare);                   // :273
-      const S a5 = M::atan2_core(r12, r13, rare);                    // :274
-      const S q4p = M::atan2_core(M::sqrt_fast(r12 * r12 + r13 * r13), r11, rare);  // :280, w = 0
-      const S u1 = M::mul(M::sub(q1, P.off[1]), P.dir[1]);
-      const S u2 = M::mul(M::sub(q2, P.off[2]), P.dir[2]);
-      const bool bad = !reach || out0 || (u1 < P.lo[1]) || (u1 > P.hi[1]) || (u2 < P.lo[2]) ||
-                       (u2 > P.hi[2]);
+      const bool regular = M::abs(r11 - S(1)) > P.eps;               // :272
+      rare = rare || (regular && !(M::abs(r13) > P.eps));            // :279 -> :282
+      S a3 = M::atan2_core(r21, -r31, rare);                         // :273
+      S a5 = M::atan2_core(r12, r13, rare);                          // :274
+      S q4p = M::atan2_core(M::sqrt_fast(r12 * r12 + r13 * r13), r11, rare);  // :280, w = 0
+      // wrist singular (|q4| < ~4.5e-3: 0.15 % of uniformly sampled poses): q3 = q4 = q5 = 0 for
+      // every w (:266-268); pi is added back so that the w = 1 subtraction below returns 0
+      S wpi = M::pi();
+      if (__any_sync(0xffffffffu, !regular)) {
+        if (!regular) a3 = S(0), a5 = S(0), q4p = S(0), wpi = S(0);
+      }
+      S u1, u2;
+      bool bad = !reach || out0;
+      if (STD) {
+        const S t2 = M::sub(q2, P.off[2]);
+        u1 = M::flipm(M::sub(q1, P.off[1]), P.smask[1]);
+        u2 = M::flipm(t2, P.smask[2]);
+        bad = bad || (u1 < P.lo[1]) || (u1 > P.hi[1]) || (M::abs(t2) > P.hi[2]) ||
+              (M::abs(q4p) > P.hi[4]);  // |q4| is the same for w = 0 and 1
+      } else {
+        u1 = M::mul(M::sub(q1, P.off[1]), P.dir[1]);
+        u2 = M::mul(M::sub(q2, P.off[2]), P.dir[2]);
+        bad = bad || (u1 < P.lo[1]) || (u1 > P.hi[1]) || (u2 < P.lo[2]) || (u2 > P.hi[2]);
+      }
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
-        const S q3 = w ? M::sub(a3, M::pi()) : a3;                   // :276
-        const S q5 = w ? M::sub(a5, M::pi()) : a5;                   // :277
+        const S q3 = w ? M::sub(a3, wpi) : a3;                       // :276
+        const S q5 = w ? M::sub(a5, wpi) : a5;                       // :277
         const S q4 = w ? -q4p : q4p;      // :280: r13 / cos(q5) = +-hypot(r12, r13)
-        const S u3 = M::mul(M::sub(q3, P.off[3]), P.dir[3]);
-        const S u4 = M::mul(M::sub(q4, P.off[4]), P.dir[4]);
-        const S u5 = M::mul(M::sub(q5, P.off[5]), P.dir[5]);
-        const bool ok = !(bad || (u3 < P.lo[3]) || (u3 > P.hi[3]) || (u4 < P.lo[4]) ||
-                          (u4 > P.hi[4]) || (u5 < P.lo[5]) || (u5 > P.hi[5]));
-        const int b = mi * 4 + ki * 2 + w;
+        S u3, u4, u5;
+        bool ok;
+        if (STD) {
+          u3 = M::flipm(q3, P.smask[3]), u4 = M::flipm(q4, P.smask[4]), u5 = M::flipm(q5, P.smask[5]);
+          ok = !(bad || (M::abs(q3) > P.hi[3]) || (M::abs(q5) > P.hi[5]));
+        } else {
+          u3 = M::mul(M::sub(q3, P.off[3]), P.dir[3]);
+          u4 = M::mul(M::sub(q4, P.off[4]), P.dir[4]);
+          u5 = M::mul(M::sub(q5, P.off[5]), P.dir[5]);
+          ok = !(bad || (u3 < P.lo[3]) || (u3 > P.hi[3]) || (u4 < P.lo[4]) || (u4 > P.hi[4]) ||
+                 (u5 < P.lo[5]) || (u5 > P.hi[5]));
+        }
         const S u[6] = {u0, u1, u2, u3, u4, u5};
-        out.branch(b, ok, u);  // the solution, or the all-zero failure sentinel (:239, :300)
+        if (w == 0) out.begin_mk();
+        if (w == 0 && mi == 0) out.begin_k();
+        out.branch(mi * 4 + ki * 2 + w, ok, u);  // solution or the all-zero sentinel (:239, :300)
       }
+      out.end_mk(mi * 4 + ki * 2);
     }
+    out.end_k(ki);
   }
   return rare;
 }
@@ -753,13 +809,21 @@ struct IkPlaneSink {
   S* qp;
   uint8_t* vp;
   int64_t ld;
-  __device__ __forceinline__ void q(int b, int j, S v) { __stcs(qp + (int64_t)(b * 6 + j) * ld, v); }
+  __device__ __forceinline__ void q(int b, int j, S v) {
+    if (qp) __stcs(qp + (int64_t)(b * 6 + j) * ld, v);
+  }
   __device__ __forceinline__ void branch(int b, bool okf, const S (&u)[6]) {
 #pragma unroll
     for (int j = 0; j < 6; ++j) q(b, j, okf ? u[j] : S(0));
     ok(b, okf);
   }
-  __device__ __forceinline__ void ok(int b, bool f) { vp[(int64_t)b * ld] = f ? 1 : 0; }
+  __device__ __forceinline__ void ok(int b, bool f) {
+    if (qp) vp[(int64_t)b * ld] = f ? 1 : 0;
+  }
+  __device__ __forceinline__ void begin_mk() {}
+  __device__ __forceinline__ void end_mk(int) {}
+  __device__ __forceinline__ void begin_k() {}
+  __device__ __forceinline__ void end_k(int) {}
 };
 
 template <typename S>
@@ -769,7 +833,7 @@ struct alignas(128) IkPoseTile {
   uint64_t bar[2];
 };
 
-template <typename S>
+template <typename S, bool STD>
 __global__ void __launch_bounds__(kBlock, 4)
 fanuc_ik8_pose_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant__ CUtensorMap tmT,
                       S* __restrict__ q_out, uint8_t* __restrict__ valid, int64_t n, int64_t ld,
@@ -778,7 +842,7 @@ fanuc_ik8_pose_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant
   constexpr int TP = Tile::kPoses;
   constexpr int WPB = kBlock / kWarp;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = uniform_warp_idx();
   Tile& sm = reinterpret_cast<Tile*>(smem_raw)[warp];
   if (lane == 0) {
     mbar_init(&sm.bar[0], 1);
@@ -804,12 +868,13 @@ fanuc_ik8_pose_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant
 #pragma unroll
     for (int c = 0; c < 12; ++c) Tin[c] = sm.in[buf][c][lane];
     __syncwarp();
+    // every lane runs (fanuc_ik8_pose votes across the warp); lanes past the end of a ragged last
+    // tile compute on the zeros the TMA load filled in and store nothing
     const int64_t i = tile * TP + lane;
-    if (i >= n) continue;  // ragged last tile (the TMA load zero-filled it)
     S R0[9], p0[3];
     fanuc_ik_t0(P, Tin, R0, p0);
-    IkPlaneSink<S> sink{q_out + i, valid + i, ld};
-    if (fanuc_ik8_pose(P, R0, p0, sink)) {
+    IkPlaneSink<S> sink{q_out && i < n ? q_out + i : nullptr, valid + i, ld};
+    if (fanuc_ik8_pose<S, 1, 1, STD>(P, R0, p0, sink)) {
       // measure-zero configurations: the branch-by-branch routine with all its special cases
 #pragma unroll 1
       for (int mk = 0; mk < 4; ++mk) {
@@ -826,6 +891,126 @@ fanuc_ik8_pose_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant
       }
     }
   }
+}
+
+// The same pipeline with TMA on both sides: the two solutions of one (m, k) pair (12 planes x 32
+// poses) are staged in a warp-private shared-memory tile and leave as ONE 2-D TMA store, double
+// buffered so the store of pair i drains while pair i+1 computes; the 8 validity bytes of the
+// tile leave as one [8][32] store per tile.  Per value the thread then issues one STS with an
+// immediate offset instead of 64-bit address arithmetic + STG, and the LSU/L1 path carries no
+// global traffic at all.
+template <typename S>
+struct alignas(128) IkPoseTileIO {
+  static constexpr int kPoses = kWarp;
+  S in[2][12][kPoses];
+  S out[2][12][kPoses];  // [m][w * 6 + j][pose] of the current k
+  uint8_t ok[8][kPoses];
+  uint64_t bar[2];
+};
+
+// q_out is addressed as a 4-D tensor (pose, row within a pair = w*6+j, k, m): the four solutions
+// that share k are the box (32, 12, 1, 2).
+template <typename S>
+struct IkTileSink {
+  IkPoseTileIO<S>& sm;
+  const CUtensorMap* tmQ;
+  int lane, x;
+  __device__ __forceinline__ void begin_mk() {}
+  __device__ __forceinline__ void begin_k() {
+    // the previous store (issued one k ago) was the last reader of sm.out
+    if (lane == 0) bulk_wait_read0();
+    __syncwarp();
+  }
+  __device__ __forceinline__ void branch(int b, bool okf, const S (&u)[6]) {
+    const int w = b & 1, mi = b >> 2;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) sm.out[mi][w * 6 + j][lane] = okf ? u[j] : S(0);
+    sm.ok[b][lane] = okf ? 1 : 0;
+  }
+  __device__ __forceinline__ void end_mk(int) {}
+  __device__ __forceinline__ void end_k(int ki) {
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_4d(tmQ, x, 0, ki, 0, &sm.out[0][0][0]);
+      bulk_commit();
+    }
+  }
+};
+
+template <typename S, bool STD>
+__global__ void __launch_bounds__(kBlock, 4)
+fanuc_ik8_pose_tma_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant__ CUtensorMap tmT,
+                          const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmV,
+                          S* __restrict__ q_out, uint8_t* __restrict__ valid, int64_t n, int64_t ld,
+                          int64_t ntiles) {
+  using Tile = IkPoseTileIO<S>;
+  constexpr int TP = Tile::kPoses;
+  constexpr int WPB = kBlock / kWarp;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = uniform_warp_idx();
+  Tile& sm = reinterpret_cast<Tile*>(smem_raw)[warp];
+  if (lane == 0) {
+    mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  auto issue_load = [&](int64_t tile, int buf) {  // one lane
+    mbar_expect_tx(&sm.bar[buf], 12 * TP * sizeof(S));
+    tma_load_2d(&sm.in[buf][0][0], &tmT, (int)(tile * TP), 0, &sm.bar[buf]);
+  };
+  const int64_t stride = (int64_t)gridDim.x * WPB;
+  int64_t tile = (int64_t)blockIdx.x * WPB + warp;
+  if (lane == 0 && tile < ntiles) issue_load(tile, 0);
+  int it = 0;
+  for (; tile < ntiles; tile += stride, ++it) {
+    const int buf = it & 1;
+    const int64_t next = tile + stride;
+    // sm.in[buf ^ 1] was consumed by every lane one iteration ago (the __syncwarp below)
+    if (lane == 0 && next < ntiles) issue_load(next, buf ^ 1);
+    mbar_wait(&sm.bar[buf], (it >> 1) & 1);
+    S Tin[12];
+#pragma unroll
+    for (int c = 0; c < 12; ++c) Tin[c] = sm.in[buf][c][lane];
+    if (lane == 0) bulk_wait_read0();  // the previous tile's validity store has read sm.ok
+    __syncwarp();
+    // every lane runs (the TMA load zero-filled a ragged last tile and the stores clip it)
+    S R0[9], p0[3];
+    fanuc_ik_t0(P, Tin, R0, p0);
+    IkTileSink<S> sink{sm, &tmQ, lane, (int)(tile * TP)};
+    const bool rare = fanuc_ik8_pose<S, 1, 1, STD>(P, R0, p0, sink);
+    // validity bytes of the whole tile (end_mk's fence + __syncwarp covered sm.ok)
+    if (lane == 0) {
+      tma_store_2d(&tmV, (int)(tile * TP), 0, &sm.ok[0][0]);
+      bulk_commit();
+    }
+    if (__any_sync(0xffffffffu, rare)) {
+      // measure-zero configurations: redo the pose with the branch-by-branch routine and all its
+      // special cases, writing straight to global memory once the tile's TMA stores have landed
+      if (lane == 0) bulk_wait_all();
+      __syncwarp();
+      const int64_t i = tile * TP + lane;
+      if (rare && i < n) {
+        IkPlaneSink<S> direct{q_out + i, valid + i, ld};
+#pragma unroll 1
+        for (int mk = 0; mk < 4; ++mk) {
+          const int wl[2] = {0, 1};
+          S qo[2][6];
+          bool ok[2];
+          fanuc_ik_mk<S, 2, false>(P, R0, p0, (mk & 2) ? -1 : 1, (mk & 1) ? -1 : 1, wl, qo, ok);
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) direct.q(mk * 2 + w, j, qo[w][j]);
+            direct.ok(mk * 2 + w, ok[w]);
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  if (lane == 0) bulk_wait_all();
 }
 
 // Arbitrary branch list: one thread per (pose, branch).
@@ -937,15 +1122,38 @@ static int launch_ik(const RkFanuc* robot, const S* T, int64_t n, int64_t ld, in
     // 128 registers / 4 CTAs per SM measured best (3: 8.1 ms, 4: 7.2 ms, 5: 7.2 ms, 6 spills: 8.1 ms
     // per 2^25 poses)
     if (soa) {
-      // thread-per-pose kernel when T satisfies the tensor-map alignment rules (16-byte base and
-      // pitch), 4-lanes-per-pose LSU kernel otherwise
+      // thread-per-pose kernels when T satisfies the tensor-map alignment rules (16-byte base and
+      // pitch): TMA on both sides if q_out and valid do too, else TMA loads + LSU stores;
+      // 4-lanes-per-pose LSU kernel otherwise
       constexpr int TP = IkPoseTile<S>::kPoses;
-      CUtensorMap tmT;
+      CUtensorMap tmT, tmQ, tmV;
+      auto make_q4d = [&](CUtensorMap* m) {  // (pose, w*6+j, k, m) view of q_out[48][ld]
+        const uint64_t pitch = (uint64_t)ld * sizeof(S);
+        const uint64_t dims[4] = {(uint64_t)n, 12, 2, 2}, strides[3] = {pitch, 12 * pitch, 24 * pitch};
+        const uint32_t box[4] = {TP, 12, 1, 2};
+        return make_tmap_nd(m, TmapType<S>::value, sizeof(S), q_out, 4, dims, strides, box);
+      };
+      static const int variant = getenv("RK_IK_VARIANT") ? atoi(getenv("RK_IK_VARIANT")) : 0;
+      const bool std_lim = P.std_limits && variant != 1;
       if (make_tmap_2d(&tmT, TmapType<S>::value, sizeof(S), T, n, 12, ld * sizeof(S), TP, 12)) {
         const int64_t ntiles = (n + TP - 1) / TP;
-        const size_t smem = sizeof(IkPoseTile<S>) * (kBlock / kWarp);
-        int grid = persistent_grid(fanuc_ik8_pose_kernel<S>, kBlock, smem, ntiles * kWarp);
-        fanuc_ik8_pose_kernel<S><<<grid, kBlock, smem, st>>>(P, tmT, q_out, valid, n, ld, ntiles);
+        if (variant < 2 && make_q4d(&tmQ) &&
+            make_tmap_2d(&tmV, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, valid, n, 8, ld, TP, 8)) {
+          const size_t smem = sizeof(IkPoseTileIO<S>) * (kBlock / kWarp);
+          auto kern = std_lim ? fanuc_ik8_pose_tma_kernel<S, true> : fanuc_ik8_pose_tma_kernel<S, false>;
+          static thread_local bool attr_done[2] = {false, false};
+          if (!attr_done[std_lim]) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_done[std_lim] = true;
+          }
+          int grid = persistent_grid(kern, kBlock, smem, ntiles * kWarp);
+          kern<<<grid, kBlock, smem, st>>>(P, tmT, tmQ, tmV, q_out, valid, n, ld, ntiles);
+        } else {
+          const size_t smem = sizeof(IkPoseTile<S>) * (kBlock / kWarp);
+          auto kern = std_lim ? fanuc_ik8_pose_kernel<S, true> : fanuc_ik8_pose_kernel<S, false>;
+          int grid = persistent_grid(kern, kBlock, smem, ntiles * kWarp);
+          kern<<<grid, kBlock, smem, st>>>(P, tmT, variant == 3 ? nullptr : q_out, valid, n, ld, ntiles);
+        }
       } else {
         int grid = persistent_grid(fanuc_ik8_kernel<S, true, 4>, kBlock, 0, n * 4);
         fanuc_ik8_kernel<S, true, 4><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
