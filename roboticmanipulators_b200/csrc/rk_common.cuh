@@ -322,13 +322,6 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int x, int 
                : "memory");
 }
 
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3,
-                                             const void* smem_src) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(map),
-               "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(smem_src))
-               : "memory");
-}
-
 // Warp index as a value the compiler knows to be warp-uniform (broadcast from lane 0): tile
 // indices, shared-memory tile addresses and TMA coordinates derived from it then live in uniform
 // registers instead of being re-uniformised by a loop before every TMA instruction.
@@ -363,41 +356,6 @@ inline bool make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_byte
   const cuuint32_t estr[2] = {1, 1};
   return fn(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-// Host: general tiled tensor map of `rank` dimensions (dim 0 innermost, contiguous); strides[i] is
-// the byte stride of dimension i+1.  Same failure conventions as make_tmap_2d.
-inline bool make_tmap_nd(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, int rank,
-                         const uint64_t* dims, const uint64_t* strides, const uint32_t* box) {
-  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static EncodeFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeFn)p;
-    cudaGetLastError();
-  }
-  if (!fn || rank < 1 || rank > 5) return false;
-  if (((uintptr_t)base & 15) || ((uint64_t)box[0] * elem_bytes & 15)) return false;
-  cuuint64_t gdim[5], gstride[4];
-  cuuint32_t bx[5], estr[5];
-  for (int i = 0; i < rank; ++i) {
-    if (dims[i] == 0 || dims[i] > 0x7fffffffull || box[i] == 0 || box[i] > 256) return false;
-    gdim[i] = dims[i], bx[i] = box[i], estr[i] = 1;
-    if (i + 1 < rank) {
-      if (strides[i] & 15) return false;
-      gstride[i] = strides[i];
-    }
-  }
-  return fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstride, bx, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 

@@ -2,7 +2,6 @@
 // One thread owns one pose (K1) or one (pose, elbow/root branch) pair (K2); the screw
 // chain is unrolled in registers.  See include/rk_b200.h for the reference citations.
 #include <cmath>
-#include <cstdlib>
 
 #include "rk_common.cuh"
 
@@ -503,14 +502,15 @@ __device__ __forceinline__ void fanuc_ik_mk(const FanucP<S>& P, const S (&R0)[9]
 
 // All 8 canonical branches of ONE pose in ONE thread (the SOA fast path of K2).  What depends
 // only on the pose (q0, the Rz(-q0) R0 rows) is computed once, what depends only on k (acos,
-// beta, gamma and their unit vectors) twice, the wrist four times; m and k are compile-time
-// signs, so their multiplications disappear.  The code is straight-line: every data-dependent
-// special case of fanuc_ik_mk (arm on the axis :253-255, wrist singular :272, |r13| <= eps
-// :279-282, degenerate lengths, operands outside fast_atan2_core's domain) only raises the
-// returned `rare` flag, and the caller recomputes such a pose with fanuc_ik_mk.  The 19 atan2
-// and 9 sqrt/rsqrt of a pose are independent chains the scheduler interleaves.
-// Branch index b = 4*[m==-1] + 2*[k==-1] + w; emitted through out.q(b, j, v) / out.ok(b, flag).
-template <typename S, int UK, int UM, bool STD, typename Out>
+// beta, gamma and their unit vectors) twice, the wrist four times -- the 4-lanes-per-pose mapping
+// of fanuc_ik8_kernel replicates the first two.  m and k act as sign-bit flips.  The code has no
+// data-dependent branch: the wrist-singular case (:272, 0.15 % of uniformly sampled poses) is a
+// warp-voted select, and the measure-zero special cases of fanuc_ik_mk (arm on the axis :253-255,
+// |r13| <= eps :279-282, degenerate lengths, operands outside fast_atan2_core's domain) only
+// raise the returned `rare` flag; the caller then recomputes that pose with fanuc_ik_mk.
+// Must be called by all 32 lanes of a warp.
+// Branch index b = 4*[m==-1] + 2*[k==-1] + w; emitted through out.branch(b, ok, u[6]).
+template <typename S, bool STD, typename Out>
 __device__ __forceinline__ bool fanuc_ik8_pose(const FanucP<S>& P, const S (&R0)[9], const S (&p0)[3],
                                                Out& out) {
   using M = Sc<S>;
@@ -539,10 +539,10 @@ __device__ __forceinline__ bool fanuc_ik8_pose(const FanucP<S>& P, const S (&R0)
     u0 = M::mul(M::sub(q0, P.off[0]), P.dir[0]);
     out0 = (u0 < P.lo[0]) || (u0 > P.hi[0]);
   }
-  // The k and m loops are unrolled or rolled by template choice (code size vs instruction-level
-  // parallelism: fully unrolled the pose is 32 KB of straight-line code, the size of the L1.5
-  // instruction cache); ki/mi = 1 means k/m = -1, applied as sign-bit flips.
-#pragma unroll UK
+  // The k and m loops stay rolled (ki/mi = 1 means k/m = -1, applied as sign-bit flips): fully
+  // unrolled the pose is 32 KB of straight-line code, the size of the L1.5 instruction cache, and
+  // measured 7 % slower; each iteration still holds three independent atan2 chains.
+#pragma unroll 1
   for (int ki = 0; ki < 2; ++ki) {
     const S xp = M::sub(M::flip(rxy, ki), l2);                // k * rxy - l2
     const S rg2 = M::add(M::mul(xp, xp), zp2);
@@ -564,7 +564,7 @@ __device__ __forceinline__ bool fanuc_ik8_pose(const FanucP<S>& P, const S (&R0)
     const S irg = M::rsqrt_fast(rg2);
     const S cg = xp * irg, sg = zp * irg, cbn = cb * irg, sbn = sb * irg;
     const S cc = cg * cbn, ss = sg * sbn, sc = sg * cbn, cs = cg * sbn;
-#pragma unroll UM
+#pragma unroll 1
     for (int mi = 0; mi < 2; ++mi) {
       // m = +1: psi = -acos, q1 = gamma - beta;  m = -1: psi = +acos, q1 = gamma + beta
       const S q1 = M::sub(gamma, M::flip(beta, mi));                 // :247
@@ -625,13 +625,9 @@ __device__ __forceinline__ bool fanuc_ik8_pose(const FanucP<S>& P, const S (&R0)
                  (u5 < P.lo[5]) || (u5 > P.hi[5]));
         }
         const S u[6] = {u0, u1, u2, u3, u4, u5};
-        if (w == 0) out.begin_mk();
-        if (w == 0 && mi == 0) out.begin_k();
         out.branch(mi * 4 + ki * 2 + w, ok, u);  // solution or the all-zero sentinel (:239, :300)
       }
-      out.end_mk(mi * 4 + ki * 2);
     }
-    out.end_k(ki);
   }
   return rare;
 }
@@ -716,87 +712,6 @@ fanuc_ik8_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict__ T, i
   }
 }
 
-// SOA fast path: the same lane mapping as fanuc_ik8_kernel, but a CTA walks tiles of 64 poses.
-// ONE 2-D TMA load brings the tile's 12 input planes ([12][64] box of the [16][ld] pose array),
-// double buffered and issued one tile ahead; results are staged in shared memory and leave as
-// ONE TMA store of the [48][64] box of q_out plus one of the [8][64] validity box.  Neither the
-// DRAM latency of the loads nor the 392 B/pose of stores occupies the LSU or sits on the math's
-// critical path (with LSU accesses the kernel took compute + store time: 10.2 + 4.1 ms per 2^26
-// poses).  The tensor maps clip the ragged last tile (zero fill on load, no write out of range).
-template <typename S>
-struct Ik8Tile {
-  static constexpr int kPoses = 64;
-  S in[2][12][kPoses];
-  S out[48][kPoses];
-  uint8_t ok[8][kPoses];
-  uint64_t bar[2];
-};
-
-template <typename S>
-__global__ void __launch_bounds__(kBlock, 4)
-fanuc_ik8_tma_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant__ CUtensorMap tmT,
-                     const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmV,
-                     int64_t ntiles) {
-  using Tile = Ik8Tile<S>;
-  constexpr int TP = Tile::kPoses;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  Tile& sm = *reinterpret_cast<Tile*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int mk = lane & 3, pl = lane >> 2;
-  const int m = (mk & 2) ? -1 : 1, k = (mk & 1) ? -1 : 1;
-  if (tid == 0) {
-    mbar_init(&sm.bar[0], 1);
-    mbar_init(&sm.bar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  auto issue_load = [&](int64_t tile, int buf) {  // one thread
-    mbar_expect_tx(&sm.bar[buf], 12 * TP * sizeof(S));
-    tma_load_2d(&sm.in[buf][0][0], &tmT, (int)(tile * TP), 0, &sm.bar[buf]);
-  };
-  int64_t tile = blockIdx.x;
-  if (tid == 0 && tile < ntiles) issue_load(tile, 0);
-  int it = 0;
-  for (; tile < ntiles; tile += gridDim.x, ++it) {
-    const int buf = it & 1;
-    const int64_t next = tile + gridDim.x;
-    if (tid == 0 && next < ntiles) issue_load(next, buf ^ 1);
-    mbar_wait(&sm.bar[buf], (it >> 1) & 1);
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-      const int p = pass * 32 + warp * 8 + pl;  // pose within the tile
-      S Tin[12];
-#pragma unroll
-      for (int c = 0; c < 12; ++c) Tin[c] = sm.in[buf][c][p];
-      S R0[9], p0[3];
-      fanuc_ik_t0(P, Tin, R0, p0);
-      const int wl[2] = {0, 1};
-      S qo[2][6];
-      bool ok[2];
-      fanuc_ik_mk<S, 2, true>(P, R0, p0, m, k, wl, qo, ok);
-      if (pass == 0) {
-        // the previous tile's TMA stores must have finished reading sm.out / sm.ok
-        if (tid == 0) bulk_wait_read0();
-        __syncthreads();
-      }
-#pragma unroll
-      for (int w = 0; w < 2; ++w) {
-#pragma unroll
-        for (int j = 0; j < 6; ++j) sm.out[(mk * 2 + w) * 6 + j][p] = qo[w][j];
-        sm.ok[mk * 2 + w][p] = ok[w] ? 1 : 0;
-      }
-    }
-    fence_async_smem();
-    __syncthreads();  // also: everyone is done reading sm.in[buf]
-    if (tid == 0) {
-      tma_store_2d(&tmQ, (int)(tile * TP), 0, &sm.out[0][0]);
-      tma_store_2d(&tmV, (int)(tile * TP), 0, &sm.ok[0][0]);
-      bulk_commit();
-    }
-  }
-  if (tid == 0) bulk_wait_all();
-}
-
 // SOA fast path, thread-per-pose: one thread computes all 8 branches of its pose with
 // fanuc_ik8_pose (about half the instructions per pose of the 4-lanes-per-pose mapping, which
 // replicates the pose- and k-level work and spends ~200 instructions per lane on uniform-register
@@ -820,10 +735,6 @@ struct IkPlaneSink {
   __device__ __forceinline__ void ok(int b, bool f) {
     if (qp) vp[(int64_t)b * ld] = f ? 1 : 0;
   }
-  __device__ __forceinline__ void begin_mk() {}
-  __device__ __forceinline__ void end_mk(int) {}
-  __device__ __forceinline__ void begin_k() {}
-  __device__ __forceinline__ void end_k(int) {}
 };
 
 template <typename S>
@@ -873,8 +784,8 @@ fanuc_ik8_pose_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant
     const int64_t i = tile * TP + lane;
     S R0[9], p0[3];
     fanuc_ik_t0(P, Tin, R0, p0);
-    IkPlaneSink<S> sink{q_out && i < n ? q_out + i : nullptr, valid + i, ld};
-    if (fanuc_ik8_pose<S, 1, 1, STD>(P, R0, p0, sink)) {
+    IkPlaneSink<S> sink{i < n ? q_out + i : nullptr, valid + i, ld};
+    if (fanuc_ik8_pose<S, STD>(P, R0, p0, sink)) {
       // measure-zero configurations: the branch-by-branch routine with all its special cases
 #pragma unroll 1
       for (int mk = 0; mk < 4; ++mk) {
@@ -891,126 +802,6 @@ fanuc_ik8_pose_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant
       }
     }
   }
-}
-
-// The same pipeline with TMA on both sides: the two solutions of one (m, k) pair (12 planes x 32
-// poses) are staged in a warp-private shared-memory tile and leave as ONE 2-D TMA store, double
-// buffered so the store of pair i drains while pair i+1 computes; the 8 validity bytes of the
-// tile leave as one [8][32] store per tile.  Per value the thread then issues one STS with an
-// immediate offset instead of 64-bit address arithmetic + STG, and the LSU/L1 path carries no
-// global traffic at all.
-template <typename S>
-struct alignas(128) IkPoseTileIO {
-  static constexpr int kPoses = kWarp;
-  S in[2][12][kPoses];
-  S out[2][12][kPoses];  // [m][w * 6 + j][pose] of the current k
-  uint8_t ok[8][kPoses];
-  uint64_t bar[2];
-};
-
-// q_out is addressed as a 4-D tensor (pose, row within a pair = w*6+j, k, m): the four solutions
-// that share k are the box (32, 12, 1, 2).
-template <typename S>
-struct IkTileSink {
-  IkPoseTileIO<S>& sm;
-  const CUtensorMap* tmQ;
-  int lane, x;
-  __device__ __forceinline__ void begin_mk() {}
-  __device__ __forceinline__ void begin_k() {
-    // the previous store (issued one k ago) was the last reader of sm.out
-    if (lane == 0) bulk_wait_read0();
-    __syncwarp();
-  }
-  __device__ __forceinline__ void branch(int b, bool okf, const S (&u)[6]) {
-    const int w = b & 1, mi = b >> 2;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) sm.out[mi][w * 6 + j][lane] = okf ? u[j] : S(0);
-    sm.ok[b][lane] = okf ? 1 : 0;
-  }
-  __device__ __forceinline__ void end_mk(int) {}
-  __device__ __forceinline__ void end_k(int ki) {
-    fence_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      tma_store_4d(tmQ, x, 0, ki, 0, &sm.out[0][0][0]);
-      bulk_commit();
-    }
-  }
-};
-
-template <typename S, bool STD>
-__global__ void __launch_bounds__(kBlock, 4)
-fanuc_ik8_pose_tma_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant__ CUtensorMap tmT,
-                          const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmV,
-                          S* __restrict__ q_out, uint8_t* __restrict__ valid, int64_t n, int64_t ld,
-                          int64_t ntiles) {
-  using Tile = IkPoseTileIO<S>;
-  constexpr int TP = Tile::kPoses;
-  constexpr int WPB = kBlock / kWarp;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, warp = uniform_warp_idx();
-  Tile& sm = reinterpret_cast<Tile*>(smem_raw)[warp];
-  if (lane == 0) {
-    mbar_init(&sm.bar[0], 1);
-    mbar_init(&sm.bar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-  auto issue_load = [&](int64_t tile, int buf) {  // one lane
-    mbar_expect_tx(&sm.bar[buf], 12 * TP * sizeof(S));
-    tma_load_2d(&sm.in[buf][0][0], &tmT, (int)(tile * TP), 0, &sm.bar[buf]);
-  };
-  const int64_t stride = (int64_t)gridDim.x * WPB;
-  int64_t tile = (int64_t)blockIdx.x * WPB + warp;
-  if (lane == 0 && tile < ntiles) issue_load(tile, 0);
-  int it = 0;
-  for (; tile < ntiles; tile += stride, ++it) {
-    const int buf = it & 1;
-    const int64_t next = tile + stride;
-    // sm.in[buf ^ 1] was consumed by every lane one iteration ago (the __syncwarp below)
-    if (lane == 0 && next < ntiles) issue_load(next, buf ^ 1);
-    mbar_wait(&sm.bar[buf], (it >> 1) & 1);
-    S Tin[12];
-#pragma unroll
-    for (int c = 0; c < 12; ++c) Tin[c] = sm.in[buf][c][lane];
-    if (lane == 0) bulk_wait_read0();  // the previous tile's validity store has read sm.ok
-    __syncwarp();
-    // every lane runs (the TMA load zero-filled a ragged last tile and the stores clip it)
-    S R0[9], p0[3];
-    fanuc_ik_t0(P, Tin, R0, p0);
-    IkTileSink<S> sink{sm, &tmQ, lane, (int)(tile * TP)};
-    const bool rare = fanuc_ik8_pose<S, 1, 1, STD>(P, R0, p0, sink);
-    // validity bytes of the whole tile (end_mk's fence + __syncwarp covered sm.ok)
-    if (lane == 0) {
-      tma_store_2d(&tmV, (int)(tile * TP), 0, &sm.ok[0][0]);
-      bulk_commit();
-    }
-    if (__any_sync(0xffffffffu, rare)) {
-      // measure-zero configurations: redo the pose with the branch-by-branch routine and all its
-      // special cases, writing straight to global memory once the tile's TMA stores have landed
-      if (lane == 0) bulk_wait_all();
-      __syncwarp();
-      const int64_t i = tile * TP + lane;
-      if (rare && i < n) {
-        IkPlaneSink<S> direct{q_out + i, valid + i, ld};
-#pragma unroll 1
-        for (int mk = 0; mk < 4; ++mk) {
-          const int wl[2] = {0, 1};
-          S qo[2][6];
-          bool ok[2];
-          fanuc_ik_mk<S, 2, false>(P, R0, p0, (mk & 2) ? -1 : 1, (mk & 1) ? -1 : 1, wl, qo, ok);
-#pragma unroll
-          for (int w = 0; w < 2; ++w) {
-#pragma unroll
-            for (int j = 0; j < 6; ++j) direct.q(mk * 2 + w, j, qo[w][j]);
-            direct.ok(mk * 2 + w, ok[w]);
-          }
-        }
-      }
-      __syncwarp();
-    }
-  }
-  if (lane == 0) bulk_wait_all();
 }
 
 // Arbitrary branch list: one thread per (pose, branch).
@@ -1122,38 +913,16 @@ static int launch_ik(const RkFanuc* robot, const S* T, int64_t n, int64_t ld, in
     // 128 registers / 4 CTAs per SM measured best (3: 8.1 ms, 4: 7.2 ms, 5: 7.2 ms, 6 spills: 8.1 ms
     // per 2^25 poses)
     if (soa) {
-      // thread-per-pose kernels when T satisfies the tensor-map alignment rules (16-byte base and
-      // pitch): TMA on both sides if q_out and valid do too, else TMA loads + LSU stores;
-      // 4-lanes-per-pose LSU kernel otherwise
+      // thread-per-pose kernel when T satisfies the tensor-map alignment rules (16-byte base and
+      // pitch), 4-lanes-per-pose LSU kernel otherwise
       constexpr int TP = IkPoseTile<S>::kPoses;
-      CUtensorMap tmT, tmQ, tmV;
-      auto make_q4d = [&](CUtensorMap* m) {  // (pose, w*6+j, k, m) view of q_out[48][ld]
-        const uint64_t pitch = (uint64_t)ld * sizeof(S);
-        const uint64_t dims[4] = {(uint64_t)n, 12, 2, 2}, strides[3] = {pitch, 12 * pitch, 24 * pitch};
-        const uint32_t box[4] = {TP, 12, 1, 2};
-        return make_tmap_nd(m, TmapType<S>::value, sizeof(S), q_out, 4, dims, strides, box);
-      };
-      static const int variant = getenv("RK_IK_VARIANT") ? atoi(getenv("RK_IK_VARIANT")) : 0;
-      const bool std_lim = P.std_limits && variant != 1;
+      CUtensorMap tmT;
       if (make_tmap_2d(&tmT, TmapType<S>::value, sizeof(S), T, n, 12, ld * sizeof(S), TP, 12)) {
         const int64_t ntiles = (n + TP - 1) / TP;
-        if (variant < 2 && make_q4d(&tmQ) &&
-            make_tmap_2d(&tmV, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, valid, n, 8, ld, TP, 8)) {
-          const size_t smem = sizeof(IkPoseTileIO<S>) * (kBlock / kWarp);
-          auto kern = std_lim ? fanuc_ik8_pose_tma_kernel<S, true> : fanuc_ik8_pose_tma_kernel<S, false>;
-          static thread_local bool attr_done[2] = {false, false};
-          if (!attr_done[std_lim]) {
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_done[std_lim] = true;
-          }
-          int grid = persistent_grid(kern, kBlock, smem, ntiles * kWarp);
-          kern<<<grid, kBlock, smem, st>>>(P, tmT, tmQ, tmV, q_out, valid, n, ld, ntiles);
-        } else {
-          const size_t smem = sizeof(IkPoseTile<S>) * (kBlock / kWarp);
-          auto kern = std_lim ? fanuc_ik8_pose_kernel<S, true> : fanuc_ik8_pose_kernel<S, false>;
-          int grid = persistent_grid(kern, kBlock, smem, ntiles * kWarp);
-          kern<<<grid, kBlock, smem, st>>>(P, tmT, variant == 3 ? nullptr : q_out, valid, n, ld, ntiles);
-        }
+        const size_t smem = sizeof(IkPoseTile<S>) * (kBlock / kWarp);
+        auto kern = P.std_limits ? fanuc_ik8_pose_kernel<S, true> : fanuc_ik8_pose_kernel<S, false>;
+        int grid = persistent_grid(kern, kBlock, smem, ntiles * kWarp);
+        kern<<<grid, kBlock, smem, st>>>(P, tmT, q_out, valid, n, ld, ntiles);
       } else {
         int grid = persistent_grid(fanuc_ik8_kernel<S, true, 4>, kBlock, 0, n * 4);
         fanuc_ik8_kernel<S, true, 4><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);

@@ -292,3 +292,81 @@ def test_internal_sincos_accuracy():
     assert np.max(np.abs(s[big] - rs[big]) / np.abs(rs[big])) < 4.5e-16
     big = ok & (np.abs(rc) > 1e-3)
     assert np.max(np.abs(c[big] - rc[big]) / np.abs(rc[big])) < 4.5e-16
+
+
+def _special_poses():
+    """Targets that hit every special case of fanuc.py:196-302: wrist singular (:272) exactly and
+    within/around eps, |r13| <= eps (:279-282), wrist centre on the base axis (:253-255), exact
+    zeros in R (axis-aligned tools), unreachable targets, zero and non-finite matrices."""
+    c = O.FanucConst()
+    rng = np.random.default_rng(7)
+    off, dirs = np.asarray(c.offsets, float), np.asarray(c.directions, float)
+
+    def user(qm):                                     # model angles -> user angles
+        return (np.asarray(qm, float) - off) / dirs
+
+    qs = []
+    base = rng.uniform(-0.8, 0.8, size=(40, 6))
+    for i, qm in enumerate(base):
+        a = qm.copy()
+        a[4] = [0.0, 1e-6, -3e-6, 4.4e-3, 4.6e-3, 1e-5, -2e-4, 3.2e-3][i % 8]   # q4' ~ 0: r11 ~ 1
+        qs.append(user(a))
+        b = qm.copy()
+        b[5] = [np.pi / 2, -np.pi / 2, np.pi / 2 + 3e-6, np.pi / 2 - 8e-6][i % 4]   # r13 ~ 0
+        qs.append(user(b))
+        z = qm.copy()                                 # wrist centre on the base axis: rho3 = 0
+        z[1] = rng.uniform(0.6, 1.2)
+        rhs = -(c.ls[2] + c.ls[3] * np.cos(z[1])) / c.d
+        q12 = c.dq + np.arccos(np.clip(rhs, -1, 1)) * (1 if i % 2 else -1)
+        z[2] = q12 - z[1] + [0.0, 1e-9, -2e-9, 3e-7][i % 4]
+        qs.append(user(z))
+    T = O.fanuc_fk(np.array(qs), c)
+    extra = []
+    for ang in (0.0, np.pi / 2, np.pi, -np.pi / 2):   # axis-aligned tools: exact zeros in R
+        for p in ((1500.0, 0.0, 1200.0), (0.0, 1400.0, 900.0), (1200.0, -700.0, 1500.0), (-900.0, 0.0, 800.0)):
+            Tm = np.eye(4)
+            ca, sa = np.round(np.cos(ang)), np.round(np.sin(ang))
+            Tm[:3, :3] = [[ca, -sa, 0], [sa, ca, 0], [0, 0, 1]]
+            Tm[:3, 3] = p
+            extra.append(Tm)
+            Tm2 = Tm.copy()
+            Tm2[:3, :3] = Tm[:3, :3] @ np.array([[0, 0, 1.0], [0, 1, 0], [-1, 0, 0]])
+            extra.append(Tm2)
+    far = np.eye(4)
+    far[:3, 3] = (1e5, -2e5, 3e5)
+    onaxis = np.eye(4)
+    onaxis[:3, 3] = (c.ls[6], 0.0, 2000.0)            # wrist centre exactly on the axis: atan2(0, 0)
+    extra += [far, onaxis, np.zeros((4, 4))]
+    bad = np.eye(4)
+    bad[0, 3] = np.nan
+    inf = np.eye(4)
+    inf[1, 3] = np.inf
+    extra += [bad, inf]
+    return np.concatenate([T, np.array(extra)])
+
+
+@pytest.mark.parametrize("layout", ["aos", "soa"])
+def test_ik8_special_poses(layout):
+    """The thread-per-pose kernel defers measure-zero cases to the branch routine and handles
+    the wrist singularity by a warp vote: both must reproduce the reference's answers."""
+    from roboticmanipulators_b200.robots.fanuc import Fanuc165F
+    c = O.FanucConst()
+    T = _special_poses()
+    reps = -(-4096 // len(T))
+    Tb = np.tile(T, (reps, 1, 1))[:4096]              # even, > several warps: the TMA path in SOA
+    with np.errstate(all="ignore"):
+        q_ref, v_ref = O.fanuc_ik_branches(Tb, O.CANONICAL_8, c)
+    qg, vg = Fanuc165F().inverse_kinematics_batch(torch.tensor(Tb, device="cuda"), layout=layout)
+    qg, vg = qg.cpu().numpy(), vg.cpu().numpy()
+    finite = np.isfinite(Tb).all(axis=(1, 2))
+    assert np.array_equal(vg[finite], v_ref[finite])
+    assert np.array_equal(np.isnan(qg[finite]), np.isnan(q_ref[finite]))
+    assert not np.any(np.nan_to_num(qg[finite][~vg[finite]]))
+    d = qg - q_ref
+    d[..., [3, 5]] = (d[..., [3, 5]] + np.pi) % (2 * np.pi) - np.pi
+    # the targets sit ON the ill-conditioned corners (q3, q5 amplify rounding by 1/|sin q4|, and
+    # the reference itself divides by cos(q5) ~ 1e-5 at the r13 corner)
+    ok = finite[:, None] & v_ref & ~np.isnan(q_ref).any(axis=-1)
+    assert ok.sum() > 1000
+    assert np.max(np.abs(d[..., :3][ok])) < 1e-9
+    assert np.max(np.abs(d[..., 3:][ok])) < 1e-7
