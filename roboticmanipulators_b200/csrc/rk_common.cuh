@@ -88,10 +88,18 @@ struct Sc<float> {
   static __device__ __forceinline__ float acos(float x) { return ::acosf(x); }
   static __device__ __forceinline__ float atan2(float y, float x) { return ::atan2f(y, x); }
   static __device__ __forceinline__ float atan2_fast(float y, float x) { return ::atan2f(y, x); }
-  static __device__ __forceinline__ float atan2_core(float y, float x, bool&) { return ::atan2f(y, x); }
-  static __device__ __forceinline__ float rcp_fast(float x) { return 1.0f / x; }
+  static __device__ __forceinline__ float atan2_core(float y, float x, bool& rare);
+  static __device__ __forceinline__ float rcp_fast(float x) {  // normal finite x, <= 1 ulp
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+  }
   static __device__ __forceinline__ float rsqrt_fast(float x) { return ::rsqrtf(x); }
-  static __device__ __forceinline__ float sqrt_fast(float x) { return ::sqrtf(x); }
+  static __device__ __forceinline__ float sqrt_fast(float x) {  // 0 for x <= 0; no slow path
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(x, 0.0f)));
+    return r;
+  }
   static __device__ __forceinline__ float abs(float x) { return ::fabsf(x); }
   static __device__ __forceinline__ float flip(float x, int neg) {
     return __int_as_float(__float_as_int(x) ^ (neg << 31));
@@ -245,6 +253,37 @@ __device__ __forceinline__ double fast_sqrt(double t) {
   double r = x * rs;
   r = fma(fma(-r, r, x), 0.5 * rs, r);
   return ok ? r : 0.0;
+}
+
+// FP32 twin of fast_atan2_core (same octant reduction; degree-4 interpolant, error 1e-9 before
+// rounding; about 1.5 ulp overall).  `rare` outside a moderate exponent window -> caller uses libm.
+__device__ __forceinline__ float fast_atan2f_core(float y, float x, bool& rare) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const bool swap = ay > ax;
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float bigf = fmaf(-0.41421356237f, mx, mn) >= 0.0f ? 1.0f : 0.0f;
+  const float num = fmaf(-bigf, mx, mn), den = fmaf(bigf, mn, mx);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
+  float u = num * r;
+  u = fmaf(fmaf(-den, u, num), r, u);
+  const float s = u * u;
+  float p = -0.06451927870512009f;
+  p = fmaf(p, s, 0.10743731260299683f);
+  p = fmaf(p, s, -0.14263956248760223f);
+  p = fmaf(p, s, 0.19999539852142334f);
+  p = fmaf(p, s, -0.3333333134651184f);
+  float a = fmaf(u * s, p, u);
+  a = fmaf(bigf, 0.78539816339744831f, a);
+  if (swap) a = 1.57079632679489662f - a;
+  if (__float_as_int(x) < 0) a = 3.14159265358979324f - a;
+  a = copysignf(a, y);
+  // den in [2^-100, 2^+100]: zero, denormal, huge, inf and NaN fail
+  rare = rare || ((unsigned)__float_as_int(den) - 0x0d800000u > 0x64000000u);
+  return a;
+}
+__device__ __forceinline__ float Sc<float>::atan2_core(float y, float x, bool& rare) {
+  return fast_atan2f_core(y, x, rare);
 }
 
 __device__ __forceinline__ double Sc<double>::atan2_fast(double y, double x) { return fast_atan2(y, x); }

@@ -745,7 +745,7 @@ struct alignas(128) IkPoseTile {
 };
 
 template <typename S, bool STD>
-__global__ void __launch_bounds__(kBlock, 4)
+__global__ void __launch_bounds__(kBlock, sizeof(S) == 4 ? 6 : 4)
 fanuc_ik8_pose_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant__ CUtensorMap tmT,
                       S* __restrict__ q_out, uint8_t* __restrict__ valid, int64_t n, int64_t ld,
                       int64_t ntiles) {
