@@ -19,6 +19,7 @@ constexpr int kW = 20;         // logical row width: <= 19 columns + residual, 5
 constexpr int kRS = 22;        // slab row stride (doubles): 16-byte aligned, 2-way banked at worst
 constexpr int kMaxTiles = 15;  // upper-triangular 4x4 tiles of a 5x5 block grid
 constexpr int kTileElems = kMaxTiles * 16;
+constexpr int kPartStride = kTileElems + 8;  // per-CTA partial: tiles, then r^T r (6-row kernel)
 constexpr int kMaxGrid = 1024;
 
 struct CalibP {
@@ -221,79 +222,86 @@ __device__ __forceinline__ void fill_rows(const CalibP& P, const double (&s)[RK_
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kMeas, 3)
-calib_accumulate_kernel(const __grid_constant__ CalibP P, const double* __restrict__ q,
-                        const double* __restrict__ pts, int64_t m, int ncols,
-                        double* __restrict__ partial, unsigned int* __restrict__ counter,
-                        double* __restrict__ out) {
-  extern __shared__ __align__(16) double slab[];  // [kMeas*3][kRS]
-  __shared__ int s_last;
-  const int tid = threadIdx.x;
-  const int nblk = (ncols + 3) / 4;
-  const int ntiles = nblk * (nblk + 1) / 2;
-  const int ksplit = kMeas / ntiles;
-  const bool worker = tid < ntiles * ksplit;
-  const int tile = tid % ntiles, ks = tid / ntiles;
-  int bi = 0, bj = 0;
-  {
+// ---- phase 2 and the epilogue, shared by both accumulation kernels -------------------------
+// Thread (tile, k-slice): tile = 4x4 block (bi, bj), bi <= bj, of [J|r]^T [J|r].
+struct GramThread {
+  int ntiles, ksplit, tile, ks, bi, bj;
+  bool worker;
+  double acc[4][4];
+  __device__ __forceinline__ void init(int tid, int ncols) {
+    const int nblk = (ncols + 3) / 4;
+    ntiles = nblk * (nblk + 1) / 2;
+    ksplit = kMeas / ntiles;
+    worker = tid < ntiles * ksplit;
+    tile = tid % ntiles, ks = tid / ntiles;
+    bi = 0;
     int rem = tile;
     while (rem >= nblk - bi) {
       rem -= nblk - bi;
       ++bi;
     }
     bj = bi + rem;
-  }
-  double acc[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-
-  for (int64_t base = (int64_t)blockIdx.x * kMeas; base < m; base += (int64_t)gridDim.x * kMeas) {
-    const int64_t i = base + tid;
-    const bool live = i < m;
-    double sj[RK_CALIB_MAX_JOINTS], cj[RK_CALIB_MAX_JOINTS];
-    load_joints(P, q, i, live, sj, cj);
-    Fr Fend;
-    chain_end(P, sj, cj, Fend);
-    for (int t = 0; t < P.nt; ++t) {
-      __syncthreads();  // previous phase 2 is done with the slab
-      fill_rows<MODE>(P, sj, cj, Fend, pts, i, live, t, ncols, slab + tid * 3 * kRS);
-      __syncthreads();
-      if (worker) {
-        const double* ra = slab + bi * 4;
-        const double* rb = slab + bj * 4;
-#pragma unroll 4
-        for (int sl = ks; sl < kMeas * 3; sl += ksplit) {
-          const double2 a01 = *reinterpret_cast<const double2*>(ra + sl * kRS);
-          const double2 a23 = *reinterpret_cast<const double2*>(ra + sl * kRS + 2);
-          const double2 b01 = *reinterpret_cast<const double2*>(rb + sl * kRS);
-          const double2 b23 = *reinterpret_cast<const double2*>(rb + sl * kRS + 2);
-          const double av[4] = {a01.x, a01.y, a23.x, a23.y};
-          const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
-        }
-      }
-    }
-  }
-
-  // k-slices -> CTA partial (reuse the slab)
-  __syncthreads();
-  if (worker) {
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) slab[(ks * ntiles + tile) * 16 + a * 4 + b] = acc[a][b];
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+  }
+  // accumulate the kMeas*3 slab rows (two LDS.128 pairs feed 16 register FMAs per row)
+  __device__ __forceinline__ void accumulate(const double* __restrict__ slab) {
+    if (!worker) return;
+    const double* ra = slab + bi * 4;
+    const double* rb = slab + bj * 4;
+#pragma unroll 4
+    for (int sl = ks; sl < kMeas * 3; sl += ksplit) {
+      const double2 a01 = *reinterpret_cast<const double2*>(ra + sl * kRS);
+      const double2 a23 = *reinterpret_cast<const double2*>(ra + sl * kRS + 2);
+      const double2 b01 = *reinterpret_cast<const double2*>(rb + sl * kRS);
+      const double2 b23 = *reinterpret_cast<const double2*>(rb + sl * kRS + 2);
+      const double av[4] = {a01.x, a01.y, a23.x, a23.y};
+      const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+    }
+  }
+};
+
+// k-slices -> CTA partial -> workspace; the last CTA to finish adds the partials in index order
+// (deterministic) and scatters the packed result.  `rr` (>= 0 entries) is an optional separately
+// accumulated r^T r per thread (6-row kernel), reduced the same way; pass use_rr = false otherwise.
+template <int MODE>
+__device__ __forceinline__ void gram_epilogue(GramThread& G, double* __restrict__ slab, int ncols,
+                                              double* __restrict__ partial,
+                                              unsigned int* __restrict__ counter,
+                                              double* __restrict__ out, bool use_rr, double rr) {
+  __shared__ int s_last;
+  __shared__ double s_rr[kMeas / kWarp];
+  const int tid = threadIdx.x;
+  const int nblk = (ncols + 3) / 4;
+  const int ntiles = G.ntiles, ksplit = G.ksplit;
+  __syncthreads();
+  if (G.worker) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) slab[(G.ks * ntiles + G.tile) * 16 + a * 4 + b] = G.acc[a][b];
+  }
+  if (use_rr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rr += __shfl_xor_sync(0xffffffffu, rr, o);
+    if ((tid & 31) == 0) s_rr[tid >> 5] = rr;
   }
   __syncthreads();
   for (int e = tid; e < ntiles * 16; e += kMeas) {
     double sum = 0.0;
     for (int k = 0; k < ksplit; ++k) sum += slab[k * ntiles * 16 + e];
-    partial[(int64_t)blockIdx.x * kTileElems + e] = sum;
+    partial[(int64_t)blockIdx.x * kPartStride + e] = sum;
+  }
+  if (use_rr && tid == 0) {
+    double sum = 0.0;
+    for (int w = 0; w < kMeas / kWarp; ++w) sum += s_rr[w];
+    partial[(int64_t)blockIdx.x * kPartStride + kTileElems] = sum;
   }
   __threadfence();
   __syncthreads();
@@ -304,8 +312,13 @@ calib_accumulate_kernel(const __grid_constant__ CalibP P, const double* __restri
   // last CTA: deterministic sum over CTAs, then scatter into the caller's format
   for (int e = tid; e < ntiles * 16; e += kMeas) {
     double sum = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) sum += __ldcg(partial + (int64_t)b * kTileElems + e);
+    for (unsigned b = 0; b < gridDim.x; ++b) sum += __ldcg(partial + (int64_t)b * kPartStride + e);
     slab[e] = sum;
+  }
+  if (use_rr && tid == 0) {
+    double sum = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) sum += __ldcg(partial + (int64_t)b * kPartStride + kTileElems);
+    slab[kTileElems] = sum;
   }
   __syncthreads();
   for (int e = tid; e < ntiles * 16; e += kMeas) {
@@ -326,7 +339,7 @@ calib_accumulate_kernel(const __grid_constant__ CalibP P, const double* __restri
       } else if (gi < np) {
         out[np * (np + 1) / 2 + gi] = v;                               // g
       } else {
-        out[np * (np + 1) / 2 + np] = v;                               // r^T r
+        out[np * (np + 1) / 2 + np] = use_rr ? slab[kTileElems] : v;   // r^T r
       }
     } else {
       const int dim = ncols - 1;
@@ -339,6 +352,332 @@ calib_accumulate_kernel(const __grid_constant__ CalibP P, const double* __restri
     }
   }
   if (tid == 0) *counter = 0;  // workspace is reusable without a memset
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kMeas, 3)
+calib_accumulate_kernel(const __grid_constant__ CalibP P, const double* __restrict__ q,
+                        const double* __restrict__ pts, int64_t m, int ncols,
+                        double* __restrict__ partial, unsigned int* __restrict__ counter,
+                        double* __restrict__ out) {
+  extern __shared__ __align__(16) double slab[];  // [kMeas*3][kRS]
+  const int tid = threadIdx.x;
+  GramThread G;
+  G.init(tid, ncols);
+  for (int64_t base = (int64_t)blockIdx.x * kMeas; base < m; base += (int64_t)gridDim.x * kMeas) {
+    const int64_t i = base + tid;
+    const bool live = i < m;
+    double sj[RK_CALIB_MAX_JOINTS], cj[RK_CALIB_MAX_JOINTS];
+    load_joints(P, q, i, live, sj, cj);
+    Fr Fend;
+    chain_end(P, sj, cj, Fend);
+    for (int t = 0; t < P.nt; ++t) {
+      __syncthreads();  // previous phase 2 is done with the slab
+      fill_rows<MODE>(P, sj, cj, Fend, pts, i, live, t, ncols, slab + tid * 3 * kRS);
+      __syncthreads();
+      G.accumulate(slab);
+    }
+  }
+  gram_epilogue<MODE>(G, slab, ncols, partial, counter, out, false, 0.0);
+}
+
+// -------------------------------------------------------------------------------------------
+// K5 fast path (normal equations): 6 rows per measurement instead of 3 per (measurement, tool).
+//
+// (1) H and g are invariant under a rotation of each measurement's rows, so the Jacobian is
+//     written in the END-EFFECTOR frame.  With S_j = X_j Rot_{j+1} X_{j+1} ... = (Q_j, s_j) the
+//     constant-plus-joint suffix after joint j, a parameter with axis a and origin o in joint j's
+//     frame has the column  a' x (b' + tool_t),  a' = Q_j^T a,  b' = Q_j^T (s_j - o)  (rotation
+//     parameter) or a' (translation parameter).  Only suffixes appear, so ONE backward walk
+//     over the chain serves every parameter and every tool (the forward formulation walked the
+//     chain once per tool), and the walk ends with the whole chain, which the residual needs.
+// (2) The 3*nt rows of all tools are  M [c; a'],  c = a' x b',  M = [I | -[tool_t]x] stacked: a
+//     CONSTANT (3 nt) x 6 matrix.  With M = Q R (Householder, host) the Gram matrix of the
+//     3 nt rows equals that of the 6 rows  y = R [c; a'],  and  J^T r = Y^T (Q^T rho)  with rho
+//     the stacked end-frame residuals.  Phase 2 therefore accumulates 6 rows per measurement
+//     (2/3 of the DFMAs for three tools); r^T r is summed separately.
+// A CTA pass covers kMeas/2 measurements; warps 0,1 and warps 2,3 split the parameters of a
+// measurement by joint (`split`, chosen by the host to balance the two roles): role B walks the
+// whole chain and owns joints < split, the residual and the padding; role A walks joints >= split.
+// -------------------------------------------------------------------------------------------
+struct CalibN {
+  double R[6][6];                         // upper triangular (trapezoidal for one tool)
+  double Qt[6][3 * RK_CALIB_MAX_TOOLS];   // first 6 rows of Q^T
+  int split;
+  int seg_trans[RK_CALIB_MAX_JOINTS];     // X_j is a pure translation (true at the nominal model)
+};
+
+// Householder QR of the (3 nt) x 6 matrix M = [I | -[tool_t]x]; rows of R / Q^T beyond
+// min(3 nt, 6) are zero.
+static void make_calibn(const CalibP& P, CalibN& N) {
+  const int mrows = 3 * P.nt;
+  double A[3 * RK_CALIB_MAX_TOOLS][6], Qm[3 * RK_CALIB_MAX_TOOLS][3 * RK_CALIB_MAX_TOOLS];
+  for (int t = 0; t < P.nt; ++t) {
+    const double* w = P.tool[t];
+    const double K[3][3] = {{0.0, w[2], -w[1]}, {-w[2], 0.0, w[0]}, {w[1], -w[0], 0.0}};  // -[w]x
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        A[3 * t + r][c] = (r == c) ? 1.0 : 0.0;
+        A[3 * t + r][3 + c] = K[r][c];
+      }
+  }
+  for (int i = 0; i < mrows; ++i)
+    for (int j = 0; j < mrows; ++j) Qm[i][j] = (i == j) ? 1.0 : 0.0;  // accumulates Q^T
+  const int steps = mrows < 6 ? mrows : 6;
+  for (int k = 0; k < steps; ++k) {
+    double norm = 0.0;
+    for (int i = k; i < mrows; ++i) norm += A[i][k] * A[i][k];
+    norm = sqrt(norm);
+    if (norm == 0.0) continue;
+    double v[3 * RK_CALIB_MAX_TOOLS];
+    const double alpha = A[k][k] > 0.0 ? -norm : norm;
+    double vn = 0.0;
+    for (int i = k; i < mrows; ++i) {
+      v[i] = A[i][k] - (i == k ? alpha : 0.0);
+      vn += v[i] * v[i];
+    }
+    if (vn == 0.0) continue;
+    for (int c = 0; c < 6; ++c) {
+      double d = 0.0;
+      for (int i = k; i < mrows; ++i) d += v[i] * A[i][c];
+      d *= 2.0 / vn;
+      for (int i = k; i < mrows; ++i) A[i][c] -= d * v[i];
+    }
+    for (int c = 0; c < mrows; ++c) {
+      double d = 0.0;
+      for (int i = k; i < mrows; ++i) d += v[i] * Qm[i][c];
+      d *= 2.0 / vn;
+      for (int i = k; i < mrows; ++i) Qm[i][c] -= d * v[i];
+    }
+  }
+  for (int i = 0; i < 6; ++i) {
+    for (int c = 0; c < 6; ++c) N.R[i][c] = (i < mrows && c >= i) ? A[i][c] : 0.0;
+    for (int c = 0; c < 3 * RK_CALIB_MAX_TOOLS; ++c) N.Qt[i][c] = (i < mrows && c < mrows) ? Qm[i][c] : 0.0;
+  }
+  // role balance (FP64 operation estimates: sincos 45, walk step 55, rotation / translation
+  // parameter 48 / 15, residual 36 + 18 per tool)
+  int best = 0;
+  double best_cost = 1e300;
+  for (int sp = 0; sp <= P.nj; ++sp) {
+    double ca = 0.0, cb = 45.0 * P.nj + 55.0 * P.nj + 54.0 * P.nt;
+    for (int j = 0; j < P.nj; ++j) {
+      double pc = 0.0;
+      for (int p = P.pstart[j]; p < P.pstart[j + 1]; ++p) pc += P.pkind[p] == 1 ? 48.0 : 15.0;
+      if (j >= sp) ca += pc + (j > sp ? 100.0 : 0.0);
+      else cb += pc;
+    }
+    const double cost = ca > cb ? ca : cb;
+    if (cost < best_cost) best_cost = cost, best = sp;
+  }
+  N.split = best;
+  for (int j = 0; j < RK_CALIB_MAX_JOINTS; ++j) {
+    bool ident = true;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) ident = ident && P.seg[j][r * 4 + c] == ((r == c) ? 1.0 : 0.0);
+    N.seg_trans[j] = ident ? 1 : 0;
+  }
+}
+
+// Suffix transform S = (Q, s), 3x4 row-major in registers.
+struct Sfx {
+  double Q[9], s[3];
+};
+
+// S <- Rot_axis(theta) * S  (revolute) or Trans_axis(d) * S (prismatic: d passed in `sn`)
+template <int A>
+__device__ __forceinline__ void sfx_rot(Sfx& S, double sn, double cs) {
+  constexpr int I = (A + 1) % 3, Jc = (A + 2) % 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const double a = S.Q[I * 3 + c], b = S.Q[Jc * 3 + c];
+    S.Q[I * 3 + c] = cs * a - sn * b;
+    S.Q[Jc * 3 + c] = sn * a + cs * b;
+  }
+  const double a = S.s[I], b = S.s[Jc];
+  S.s[I] = cs * a - sn * b;
+  S.s[Jc] = sn * a + cs * b;
+}
+__device__ __forceinline__ void sfx_joint(Sfx& S, int axis, int kind, double sn, double cs) {
+  if (kind == 1) {
+    switch (axis) {
+      case 0: sfx_rot<0>(S, sn, cs); break;
+      case 1: sfx_rot<1>(S, sn, cs); break;
+      default: sfx_rot<2>(S, sn, cs); break;
+    }
+  } else {  // (static indices keep S in registers)
+    S.s[0] += axis == 0 ? sn : 0.0;
+    S.s[1] += axis == 1 ? sn : 0.0;
+    S.s[2] += axis == 2 ? sn : 0.0;
+  }
+}
+// S <- X * S for a constant 3x4 X
+__device__ __forceinline__ void sfx_premul(Sfx& S, const double* X) {
+  double Qn[9], sn[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      Qn[i * 3 + c] = X[i * 4] * S.Q[c] + X[i * 4 + 1] * S.Q[3 + c] + X[i * 4 + 2] * S.Q[6 + c];
+    sn[i] = X[i * 4] * S.s[0] + X[i * 4 + 1] * S.s[1] + X[i * 4 + 2] * S.s[2] + X[i * 4 + 3];
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) S.Q[i] = Qn[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) S.s[i] = sn[i];
+}
+
+// Phase 1 of the 6-row kernel for one (measurement, role): writes this role's columns of the six
+// slab rows (rows + r * 64 * kRS, r < 6); returns this measurement's r^T r (role B) or 0.
+__device__ __forceinline__ double fill_rows6(const CalibP& P, const CalibN& N, bool role_a,
+                                             const double (&qv)[RK_CALIB_MAX_JOINTS],
+                                             const double (&pv)[3 * RK_CALIB_MAX_TOOLS], bool live,
+                                             int ncols, double* __restrict__ rows) {
+  constexpr int kRowStep = (kMeas / 2) * kRS;  // row r of measurement slot ms is slab row r*64 + ms
+  const int wpad = ((ncols + 3) / 4) * 4;
+  const int split = N.split;
+  // columns owned by this role: A [pstart[split], np), B [0, pstart[split]) and [np, wpad)
+  if (!live) {
+    const int c0 = role_a ? P.pstart[split] : 0, c1 = role_a ? P.np : P.pstart[split];
+    for (int r = 0; r < 6; ++r) {
+      for (int k = c0; k < c1; ++k) rows[r * kRowStep + k] = 0.0;
+      if (!role_a)
+        for (int k = P.np; k < wpad; ++k) rows[r * kRowStep + k] = 0.0;
+    }
+    return 0.0;
+  }
+  const int jstop = role_a ? split : 0;  // last joint whose suffix this role needs
+  // joint values: role A needs the joints after `split` only
+  double sn[RK_CALIB_MAX_JOINTS], cs[RK_CALIB_MAX_JOINTS];
+#pragma unroll
+  for (int j = 0; j < RK_CALIB_MAX_JOINTS; ++j) {
+    sn[j] = 0.0, cs[j] = 1.0;
+    if (j < P.nj && (j > jstop || !role_a)) {
+      const double v = __dadd_rn(__dmul_rn(qv[j], P.jdir[j]), P.joff[j]);  // model_calibration.py:557
+      if (P.jkind[j] == 1)
+        fast_sincos(v, &sn[j], &cs[j]);
+      else
+        sn[j] = v;
+    }
+  }
+  Sfx S;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) S.Q[k] = (k % 4 == 0) ? 1.0 : 0.0;
+  S.s[0] = S.s[1] = S.s[2] = 0.0;
+#pragma unroll
+  for (int j = RK_CALIB_MAX_JOINTS - 1; j >= 0; --j) {
+    if (j < P.nj && j >= jstop) {
+      if (N.seg_trans[j]) {      // S_j = X_j Rot_{j+1} S_{j+1}
+        S.s[0] += P.seg[j][3], S.s[1] += P.seg[j][7], S.s[2] += P.seg[j][11];
+      } else {
+        sfx_premul(S, P.seg[j]);
+      }
+      if (role_a || j < split) {
+        for (int p = P.pstart[j]; p < P.pstart[j + 1]; ++p) {
+          const double ax = P.pax[p][0], ay = P.pax[p][1], az = P.pax[p][2];
+          // a' = Q^T a
+          const double a0 = S.Q[0] * ax + S.Q[3] * ay + S.Q[6] * az;
+          const double a1 = S.Q[1] * ax + S.Q[4] * ay + S.Q[7] * az;
+          const double a2 = S.Q[2] * ax + S.Q[5] * ay + S.Q[8] * az;
+          double y[6];
+          if (P.pkind[p] == 1) {
+            const double dx = S.s[0] - P.porg[p][0], dy = S.s[1] - P.porg[p][1], dz = S.s[2] - P.porg[p][2];
+            const double b0 = S.Q[0] * dx + S.Q[3] * dy + S.Q[6] * dz;
+            const double b1 = S.Q[1] * dx + S.Q[4] * dy + S.Q[7] * dz;
+            const double b2 = S.Q[2] * dx + S.Q[5] * dy + S.Q[8] * dz;
+            const double z[6] = {a1 * b2 - a2 * b1, a2 * b0 - a0 * b2, a0 * b1 - a1 * b0, a0, a1, a2};
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+              double acc = 0.0;
+#pragma unroll
+              for (int k = r; k < 6; ++k) acc = fma(N.R[r][k], z[k], acc);
+              y[r] = acc;
+            }
+          } else {
+            const double z[3] = {a0, a1, a2};
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+              double acc = 0.0;
+#pragma unroll
+              for (int k = r; k < 3; ++k) acc = fma(N.R[r][k], z[k], acc);
+              y[r] = acc;
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 6; ++r) rows[r * kRowStep + p] = y[r];
+        }
+      }
+      if (j > jstop || !role_a) sfx_joint(S, P.jaxis[j], P.jkind[j], sn[j], cs[j]);  // Rot_j S_j
+    }
+  }
+  if (role_a) return 0.0;
+  // role B: S = Rot_0 S_0; T_end = T_base S.  Residual of tool t in the end frame:
+  // rho_t = R_end^T (p_meas - p_end) - tool_t   (r = p_meas - T[:3,3], model_calibration.py:420)
+  sfx_premul(S, P.Tb);
+  double rho[3 * RK_CALIB_MAX_TOOLS];
+  double rr = 0.0;
+#pragma unroll
+  for (int t = 0; t < RK_CALIB_MAX_TOOLS; ++t) {
+    if (t < P.nt) {
+      const double dx = pv[3 * t] - S.s[0], dy = pv[3 * t + 1] - S.s[1], dz = pv[3 * t + 2] - S.s[2];
+      rho[3 * t + 0] = S.Q[0] * dx + S.Q[3] * dy + S.Q[6] * dz - P.tool[t][0];
+      rho[3 * t + 1] = S.Q[1] * dx + S.Q[4] * dy + S.Q[7] * dz - P.tool[t][1];
+      rho[3 * t + 2] = S.Q[2] * dx + S.Q[5] * dy + S.Q[8] * dz - P.tool[t][2];
+      rr += rho[3 * t] * rho[3 * t] + rho[3 * t + 1] * rho[3 * t + 1] + rho[3 * t + 2] * rho[3 * t + 2];
+    } else {
+      rho[3 * t] = rho[3 * t + 1] = rho[3 * t + 2] = 0.0;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3 * RK_CALIB_MAX_TOOLS; ++k) acc = fma(N.Qt[r][k], rho[k], acc);
+    rows[r * kRowStep + P.np] = acc;
+    for (int k = ncols; k < wpad; ++k) rows[r * kRowStep + k] = 0.0;
+  }
+  return rr;
+}
+
+__global__ void __launch_bounds__(kMeas, 3)
+calib_normal_eq6_kernel(const __grid_constant__ CalibP P, const __grid_constant__ CalibN N,
+                        const double* __restrict__ q, const double* __restrict__ pts, int64_t m,
+                        int ncols, double* __restrict__ partial, unsigned int* __restrict__ counter,
+                        double* __restrict__ out) {
+  extern __shared__ __align__(16) double slab[];  // [kMeas*3 = (kMeas/2)*6][kRS]
+  constexpr int kHalf = kMeas / 2;
+  const int tid = threadIdx.x;
+  const bool role_a = tid >= kHalf;  // warp-uniform
+  const int ms = tid & (kHalf - 1);
+  GramThread G;
+  G.init(tid, ncols);
+  double rr = 0.0;
+  // software pipeline: the joint vector (and, for role B, the measured points) of the NEXT pass
+  // are loaded before this pass's phase 2 and consumed after it
+  double qn[RK_CALIB_MAX_JOINTS], pn[3 * RK_CALIB_MAX_TOOLS];
+  auto prefetch = [&](int64_t i) {
+    const bool live = i < m;
+#pragma unroll
+    for (int j = 0; j < RK_CALIB_MAX_JOINTS; ++j) qn[j] = (live && j < P.nj) ? __ldcs(q + i * P.nj + j) : 0.0;
+#pragma unroll
+    for (int k = 0; k < 3 * RK_CALIB_MAX_TOOLS; ++k)
+      pn[k] = (live && !role_a && k < 3 * P.nt) ? __ldcs(pts + i * 3 * P.nt + k) : 0.0;
+  };
+  const int64_t stride = (int64_t)gridDim.x * kHalf;
+  int64_t base = (int64_t)blockIdx.x * kHalf;
+  prefetch(base + ms);
+  for (; base < m; base += stride) {
+    double qv[RK_CALIB_MAX_JOINTS], pv[3 * RK_CALIB_MAX_TOOLS];
+#pragma unroll
+    for (int j = 0; j < RK_CALIB_MAX_JOINTS; ++j) qv[j] = qn[j];
+#pragma unroll
+    for (int k = 0; k < 3 * RK_CALIB_MAX_TOOLS; ++k) pv[k] = pn[k];
+    __syncthreads();  // previous phase 2 is done with the slab
+    rr += fill_rows6(P, N, role_a, qv, pv, base + ms < m, ncols, slab + ms * kRS);
+    prefetch(base + stride + ms);
+    __syncthreads();
+    G.accumulate(slab);
+  }
+  gram_epilogue<MODE_NORMAL_EQ>(G, slab, ncols, partial, counter, out, true, rr);
 }
 
 // evaluate (model_calibration.py:480-505): sums of squares and maxima of the residuals
@@ -402,7 +741,7 @@ calib_eval_kernel(const __grid_constant__ CalibP P, const double* __restrict__ q
   if (tid == 0) *counter = 0;
 }
 
-constexpr size_t kWsCounterOffset = (size_t)kMaxGrid * kTileElems * sizeof(double);
+constexpr size_t kWsCounterOffset = (size_t)kMaxGrid * kPartStride * sizeof(double);
 constexpr size_t kWsBytes = kWsCounterOffset + 256;
 
 template <int MODE>
@@ -443,7 +782,32 @@ size_t rk_calib_workspace_bytes(void) { return rk::kWsBytes; }
 
 int rk_calib_normal_eq_f64(const RkCalibModel* model, const double* q, const double* pts, int64_t m,
                            double* out, void* workspace, size_t ws_bytes, void* stream) {
-  return rk::launch_accumulate<rk::MODE_NORMAL_EQ>(model, q, pts, m, out, workspace, ws_bytes, stream);
+  using namespace rk;
+  if (!model || !out || m < 0) return RK_ERR_INVALID_ARG;
+  if (!workspace || ws_bytes < kWsBytes) return RK_ERR_WORKSPACE;
+  if (m > 0 && (!q || !pts)) return RK_ERR_INVALID_ARG;
+  CalibP P;
+  int rc = make_calib(model, P, false);
+  if (rc != RK_OK) return rc;
+  const int ncols = P.np + 1;
+  if (ncols > kW) return RK_ERR_UNSUPPORTED;
+  CalibN N;
+  make_calibn(P, N);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)kMeas * 3 * kRS * sizeof(double);
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(calib_normal_eq6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess)
+      return check_launch();
+    attr_set = true;
+  }
+  int grid = persistent_grid(calib_normal_eq6_kernel, kMeas, smem, m > 0 ? 2 * m : 1);
+  if (grid > kMaxGrid) grid = kMaxGrid;
+  unsigned int* counter = reinterpret_cast<unsigned int*>((char*)workspace + kWsCounterOffset);
+  if (cudaMemsetAsync(counter, 0, sizeof(unsigned int), st) != cudaSuccess) return check_launch();
+  calib_normal_eq6_kernel<<<grid, kMeas, smem, st>>>(P, N, q, pts, m, ncols, (double*)workspace, counter, out);
+  return check_launch();
 }
 
 int rk_calib_tool_base_eq_f64(const RkCalibModel* model, const double* q, const double* pts, int64_t m,
