@@ -304,6 +304,9 @@ int rk_calib_tool_base_eq_f64(const RkCalibModel* model, const double* q, const 
  * per thread; *total_fma (host) receives the number of FP64 FMA instructions (per
  * thread-lane) executed so the caller can divide by the event time. */
 int rk_probe_dfma(int64_t iters, double* sink, int64_t* total_fma, void* stream);
+/* Same for the FP64 tensor-core path: 4 independent mma.sync.m8n8k4.f64 chains per warp;
+ * *total_fma receives the number of FP64 FMAs (256 per warp-level MMA). */
+int rk_probe_dmma(int64_t iters, double* sink, int64_t* total_fma, void* stream);
 
 /* out[i] = the library's internal FP64 atan2(y[i], x[i]) (octant reduction + degree-10
  * polynomial, used by the IK kernels instead of libm); exposed so the accuracy tests can

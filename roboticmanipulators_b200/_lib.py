@@ -97,6 +97,7 @@ _SIGNATURES = {
     "rk_calib_tool_base_eq_f64": (_int, [C.POINTER(RkCalibModel), _vp, _vp, _i64, _vp, _vp,
                                          C.c_size_t, _vp]),
     "rk_probe_dfma": (_int, [_i64, _vp, C.POINTER(C.c_int64), _vp]),
+    "rk_probe_dmma": (_int, [_i64, _vp, C.POINTER(C.c_int64), _vp]),
     "rk_probe_atan2": (_int, [_vp, _vp, _i64, _vp, _vp]),
     "rk_probe_stream": (_int, [_vp, _int, _vp, _int, _i64, _i64, _int, _int, _int, _vp]),
     "rk_probe_sincos": (_int, [_vp, _i64, _vp, _vp, _vp]),

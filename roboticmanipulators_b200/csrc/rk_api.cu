@@ -16,6 +16,24 @@ __global__ void __launch_bounds__(256) dfma_probe_kernel(int64_t iters, double* 
   double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
   if (r == 123.456) sink[0] = r;  // never true; keeps the loop alive
 }
+// FP64 tensor-core probe: 4 independent m8n8k4 DMMA accumulator chains per warp.
+__global__ void __launch_bounds__(256) dmma_probe_kernel(int64_t iters, double* sink) {
+  double c[4][2];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) c[k][0] = threadIdx.x * 1e-9 + k, c[k][1] = 1.0 + k;
+  const double a = 1.0000001, b = 0.9999999;
+  for (int64_t i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[k][0]), "+d"(c[k][1])
+                   : "d"(a), "d"(b));
+  }
+  double r = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) r += c[k][0] + c[k][1];
+  if (r == 123.456) sink[0] = r;
+}
 __global__ void atan2_probe_kernel(const double* y, const double* x, int64_t n, double* out) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
@@ -83,6 +101,18 @@ int rk_probe_dfma(int64_t iters, double* sink, int64_t* total_fma, void* stream)
   const int blocks = sms * 8, threads = 256;
   rk::dfma_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink);
   if (total_fma) *total_fma = (int64_t)blocks * threads * iters * 8;
+  return rk::check_launch();
+}
+
+int rk_probe_dmma(int64_t iters, double* sink, int64_t* total_fma, void* stream) {
+  if (iters < 0 || !sink) return RK_ERR_INVALID_ARG;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int blocks = sms * 8, threads = 256;
+  rk::dmma_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink);
+  // one m8n8k4 = 8*8*4 = 256 FMAs per warp
+  if (total_fma) *total_fma = (int64_t)blocks * (threads / 32) * iters * 4 * 256;
   return rk::check_launch();
 }
 

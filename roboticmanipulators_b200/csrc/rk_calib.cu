@@ -19,8 +19,13 @@ constexpr int kW = 20;         // logical row width: <= 19 columns + residual, 5
 constexpr int kRS = 22;        // slab row stride (doubles): 16-byte aligned, 2-way banked at worst
 constexpr int kMaxTiles = 15;  // upper-triangular 4x4 tiles of a 5x5 block grid
 constexpr int kTileElems = kMaxTiles * 16;
-constexpr int kPartStride = kTileElems + 8;  // per-CTA partial: tiles, then r^T r (6-row kernel)
 constexpr int kMaxGrid = 1024;
+// 6-row kernel (tensor-core Gram): rows of kW doubles at an odd stride (phase-1 stores and the
+// DMMA fragment loads are both bank-conflict free, see gram_dmma); 8x8 tiles of a 24x24 Gram
+constexpr int kRS6 = 21;
+constexpr int kTiles6 = 6;
+constexpr int kPart6 = kTiles6 * 64;                  // doubles per CTA partial
+constexpr int kPartStride = kPart6 + 8;               // + r^T r; also covers the 4x4-tile kernels
 
 struct CalibP {
   int nj, np, nt;
@@ -268,15 +273,13 @@ struct GramThread {
 };
 
 // k-slices -> CTA partial -> workspace; the last CTA to finish adds the partials in index order
-// (deterministic) and scatters the packed result.  `rr` (>= 0 entries) is an optional separately
-// accumulated r^T r per thread (6-row kernel), reduced the same way; pass use_rr = false otherwise.
+// (deterministic) and scatters the packed result.
 template <int MODE>
 __device__ __forceinline__ void gram_epilogue(GramThread& G, double* __restrict__ slab, int ncols,
                                               double* __restrict__ partial,
                                               unsigned int* __restrict__ counter,
-                                              double* __restrict__ out, bool use_rr, double rr) {
+                                              double* __restrict__ out) {
   __shared__ int s_last;
-  __shared__ double s_rr[kMeas / kWarp];
   const int tid = threadIdx.x;
   const int nblk = (ncols + 3) / 4;
   const int ntiles = G.ntiles, ksplit = G.ksplit;
@@ -287,21 +290,11 @@ __device__ __forceinline__ void gram_epilogue(GramThread& G, double* __restrict_
 #pragma unroll
       for (int b = 0; b < 4; ++b) slab[(G.ks * ntiles + G.tile) * 16 + a * 4 + b] = G.acc[a][b];
   }
-  if (use_rr) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) rr += __shfl_xor_sync(0xffffffffu, rr, o);
-    if ((tid & 31) == 0) s_rr[tid >> 5] = rr;
-  }
   __syncthreads();
   for (int e = tid; e < ntiles * 16; e += kMeas) {
     double sum = 0.0;
     for (int k = 0; k < ksplit; ++k) sum += slab[k * ntiles * 16 + e];
     partial[(int64_t)blockIdx.x * kPartStride + e] = sum;
-  }
-  if (use_rr && tid == 0) {
-    double sum = 0.0;
-    for (int w = 0; w < kMeas / kWarp; ++w) sum += s_rr[w];
-    partial[(int64_t)blockIdx.x * kPartStride + kTileElems] = sum;
   }
   __threadfence();
   __syncthreads();
@@ -314,11 +307,6 @@ __device__ __forceinline__ void gram_epilogue(GramThread& G, double* __restrict_
     double sum = 0.0;
     for (unsigned b = 0; b < gridDim.x; ++b) sum += __ldcg(partial + (int64_t)b * kPartStride + e);
     slab[e] = sum;
-  }
-  if (use_rr && tid == 0) {
-    double sum = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) sum += __ldcg(partial + (int64_t)b * kPartStride + kTileElems);
-    slab[kTileElems] = sum;
   }
   __syncthreads();
   for (int e = tid; e < ntiles * 16; e += kMeas) {
@@ -339,7 +327,7 @@ __device__ __forceinline__ void gram_epilogue(GramThread& G, double* __restrict_
       } else if (gi < np) {
         out[np * (np + 1) / 2 + gi] = v;                               // g
       } else {
-        out[np * (np + 1) / 2 + np] = use_rr ? slab[kTileElems] : v;   // r^T r
+        out[np * (np + 1) / 2 + np] = v;                               // r^T r
       }
     } else {
       const int dim = ncols - 1;
@@ -378,7 +366,7 @@ calib_accumulate_kernel(const __grid_constant__ CalibP P, const double* __restri
       G.accumulate(slab);
     }
   }
-  gram_epilogue<MODE>(G, slab, ncols, partial, counter, out, false, 0.0);
+  gram_epilogue<MODE>(G, slab, ncols, partial, counter, out);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -532,8 +520,8 @@ __device__ __forceinline__ double fill_rows6(const CalibP& P, const CalibN& N, b
                                              const double (&qv)[RK_CALIB_MAX_JOINTS],
                                              const double (&pv)[3 * RK_CALIB_MAX_TOOLS], bool live,
                                              int ncols, double* __restrict__ rows) {
-  constexpr int kRowStep = (kMeas / 2) * kRS;  // row r of measurement slot ms is slab row r*64 + ms
-  const int wpad = ((ncols + 3) / 4) * 4;
+  constexpr int kRowStep = (kMeas / 2) * kRS6;  // row r of measurement slot ms is slab row r*64 + ms
+  const int wpad = kW;  // the tensor-core Gram reads all kW columns of a row
   const int split = N.split;
   // columns owned by this role: A [pstart[split], np), B [0, pstart[split]) and [np, wpad)
   if (!live) {
@@ -638,18 +626,57 @@ __device__ __forceinline__ double fill_rows6(const CalibP& P, const CalibN& N, b
   return rr;
 }
 
+// Phase 2 of the 6-row kernel on the FP64 tensor cores: G += Y^T Y with mma.sync.m8n8k4.f64.
+// The Gram matrix is cut into 8x8 tiles (I, J), I <= J < 3 (columns 20..23 are zero padding).  For
+// a group of 4 slab rows k the fragment "row k, columns 8c..8c+7" -- lane l holds
+// Y[k = l%4][8c + l/4] -- is BOTH the A operand (Y^T block c, row-major) of tiles (c, .) and the B
+// operand (Y block c, column-major) of tiles (., c), so a group costs 3 LDS.64 and 6 DMMA
+// (= 1536 FMAs); the CUDA-core version needed 4 LDS.128 per 16 DFMA and ran into the
+// shared-memory bandwidth (ncu: L1 data pipe 68 %, FP64 pipe 42 %).  Measured DMMA rate on B200:
+// 1.86e13 FMA/s, the same as DFMA (rk_probe_dmma), so this is not about peak but about feeding it.
+// Rows of a group are {r, r+8, r+16, r+24}: with the odd row stride kRS6 the four rows start 16
+// banks apart, which makes the fragment load two conflict-free wavefronts.
+struct GramDmma {
+  double acc[kTiles6][2];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int t = 0; t < kTiles6; ++t) acc[t][0] = acc[t][1] = 0.0;
+  }
+  static __device__ __forceinline__ void mma(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
+  }
+  // all kMeas*3 slab rows; warp w takes the row groups g = w (mod 4)
+  __device__ __forceinline__ void accumulate(const double* __restrict__ slab, int warp, int lane) {
+    const int k = lane & 3, c = lane >> 2;
+    constexpr int kGroups = kMeas * 3 / 4;
+#pragma unroll 2
+    for (int g = warp; g < kGroups; g += kMeas / kWarp) {
+      const int row = (g >> 3) * 32 + (g & 7) + 8 * k;
+      const double* rp = slab + row * kRS6 + c;
+      const double v0 = rp[0], v1 = rp[8];
+      const double v2 = c < 4 ? rp[16] : 0.0;
+      mma(acc[0], v0, v0), mma(acc[1], v0, v1), mma(acc[2], v0, v2);
+      mma(acc[3], v1, v1), mma(acc[4], v1, v2), mma(acc[5], v2, v2);
+    }
+  }
+};
+
 __global__ void __launch_bounds__(kMeas, 3)
 calib_normal_eq6_kernel(const __grid_constant__ CalibP P, const __grid_constant__ CalibN N,
                         const double* __restrict__ q, const double* __restrict__ pts, int64_t m,
                         int ncols, double* __restrict__ partial, unsigned int* __restrict__ counter,
                         double* __restrict__ out) {
-  extern __shared__ __align__(16) double slab[];  // [kMeas*3 = (kMeas/2)*6][kRS]
+  extern __shared__ __align__(16) double slab[];  // [(kMeas/2)*6 rows][kRS6]
+  __shared__ int s_last;
+  __shared__ double s_rr[kMeas / kWarp];
   constexpr int kHalf = kMeas / 2;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool role_a = tid >= kHalf;  // warp-uniform
   const int ms = tid & (kHalf - 1);
-  GramThread G;
-  G.init(tid, ncols);
+  GramDmma G;
+  G.init();
   double rr = 0.0;
   // software pipeline: the joint vector (and, for role B, the measured points) of the NEXT pass
   // are loaded before this pass's phase 2 and consumed after it
@@ -672,12 +699,56 @@ calib_normal_eq6_kernel(const __grid_constant__ CalibP P, const __grid_constant_
 #pragma unroll
     for (int k = 0; k < 3 * RK_CALIB_MAX_TOOLS; ++k) pv[k] = pn[k];
     __syncthreads();  // previous phase 2 is done with the slab
-    rr += fill_rows6(P, N, role_a, qv, pv, base + ms < m, ncols, slab + ms * kRS);
+    rr += fill_rows6(P, N, role_a, qv, pv, base + ms < m, ncols, slab + ms * kRS6);
     prefetch(base + stride + ms);
     __syncthreads();
-    G.accumulate(slab);
+    G.accumulate(slab, warp, lane);
   }
-  gram_epilogue<MODE_NORMAL_EQ>(G, slab, ncols, partial, counter, out, true, rr);
+
+  // warps -> CTA partial (reuse the slab): lane l holds C[l/4][2(l%4) + e] of every tile
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < kTiles6; ++t)
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+      slab[(warp * kTiles6 + t) * 64 + (lane >> 2) * 8 + 2 * (lane & 3) + e] = G.acc[t][e];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rr += __shfl_xor_sync(0xffffffffu, rr, o);
+  if (lane == 0) s_rr[warp] = rr;
+  __syncthreads();
+  double* mine = partial + (int64_t)blockIdx.x * kPartStride;
+  for (int e = tid; e < kPart6; e += kMeas) {
+    double sum = 0.0;
+#pragma unroll
+    for (int w = 0; w < kMeas / kWarp; ++w) sum += slab[w * kPart6 + e];
+    mine[e] = sum;
+  }
+  if (tid == 0) mine[kPart6] = (s_rr[0] + s_rr[1]) + (s_rr[2] + s_rr[3]);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // last CTA: deterministic sum over CTAs (index order), then scatter into the packed format
+  const int np = ncols - 1;
+  for (int e = tid; e <= kPart6; e += kMeas) {
+    double sum = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) sum += __ldcg(partial + (int64_t)b * kPartStride + e);
+    if (e == kPart6) {
+      out[np * (np + 1) / 2 + np] = sum;  // r^T r
+      continue;
+    }
+    const int t = e >> 6, r = (e >> 3) & 7, c = e & 7;
+    const int I = t < 3 ? 0 : (t < 5 ? 1 : 2), J = t < 3 ? t : (t < 5 ? t - 2 : 2);
+    const int gi = 8 * I + r, gj = 8 * J + c;
+    if (gi > gj || gj >= ncols || gi >= np) continue;
+    if (gj < np)
+      out[gi * np - gi * (gi - 1) / 2 + (gj - gi)] = sum;  // packed upper H
+    else
+      out[np * (np + 1) / 2 + gi] = sum;                   // g
+  }
+  if (tid == 0) *counter = 0;  // workspace is reusable without a memset
 }
 
 // evaluate (model_calibration.py:480-505): sums of squares and maxima of the residuals
@@ -794,7 +865,7 @@ int rk_calib_normal_eq_f64(const RkCalibModel* model, const double* q, const dou
   CalibN N;
   make_calibn(P, N);
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = (size_t)kMeas * 3 * kRS * sizeof(double);
+  const size_t smem = (size_t)kMeas * 3 * kRS6 * sizeof(double);
   static thread_local bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(calib_normal_eq6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
