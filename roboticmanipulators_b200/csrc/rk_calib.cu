@@ -534,26 +534,15 @@ __device__ __forceinline__ double fill_rows6(const CalibP& P, const CalibN& N, b
     return 0.0;
   }
   const int jstop = role_a ? split : 0;  // last joint whose suffix this role needs
-  // joint values: role A needs the joints after `split` only
-  double sn[RK_CALIB_MAX_JOINTS], cs[RK_CALIB_MAX_JOINTS];
-#pragma unroll
-  for (int j = 0; j < RK_CALIB_MAX_JOINTS; ++j) {
-    sn[j] = 0.0, cs[j] = 1.0;
-    if (j < P.nj && (j > jstop || !role_a)) {
-      const double v = __dadd_rn(__dmul_rn(qv[j], P.jdir[j]), P.joff[j]);  // model_calibration.py:557
-      if (P.jkind[j] == 1)
-        fast_sincos(v, &sn[j], &cs[j]);
-      else
-        sn[j] = v;
-    }
-  }
   Sfx S;
 #pragma unroll
   for (int k = 0; k < 9; ++k) S.Q[k] = (k % 4 == 0) ? 1.0 : 0.0;
   S.s[0] = S.s[1] = S.s[2] = 0.0;
-#pragma unroll
-  for (int j = RK_CALIB_MAX_JOINTS - 1; j >= 0; --j) {
-    if (j < P.nj && j >= jstop) {
+  // rolled on purpose: unrolled over 8 joints the walk is ~38 KB of code (> the 32 KB L1.5
+  // instruction cache; ncu: no_instruction 0.8 per issue)
+#pragma unroll 1
+  for (int j = P.nj - 1; j >= jstop; --j) {
+    {
       if (N.seg_trans[j]) {      // S_j = X_j Rot_{j+1} S_{j+1}
         S.s[0] += P.seg[j][3], S.s[1] += P.seg[j][7], S.s[2] += P.seg[j][11];
       } else {
@@ -594,7 +583,15 @@ __device__ __forceinline__ double fill_rows6(const CalibP& P, const CalibN& N, b
           for (int r = 0; r < 6; ++r) rows[r * kRowStep + p] = y[r];
         }
       }
-      if (j > jstop || !role_a) sfx_joint(S, P.jaxis[j], P.jkind[j], sn[j], cs[j]);  // Rot_j S_j
+      if (j > jstop || !role_a) {  // S <- Rot_j(q_j) S_j  (role A never needs Rot_split)
+        double qj = qv[0];
+#pragma unroll
+        for (int k = 1; k < RK_CALIB_MAX_JOINTS; ++k) qj = (k == j) ? qv[k] : qj;
+        const double v = __dadd_rn(__dmul_rn(qj, P.jdir[j]), P.joff[j]);  // model_calibration.py:557
+        double sn = v, cs = 1.0;
+        if (P.jkind[j] == 1) fast_sincos(v, &sn, &cs);
+        sfx_joint(S, P.jaxis[j], P.jkind[j], sn, cs);
+      }
     }
   }
   if (role_a) return 0.0;
