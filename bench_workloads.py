@@ -260,6 +260,10 @@ class CalibWorkload:
         torch.cuda.synchronize()
         self.events, self.params, self.host_ms = [], None, []
         self.alg_bytes = {"calib_normal_eq": 120}
+        # FP64-bound kernel: algorithmic work per measurement: 6 compressed
+        # rows x 210 upper-triangular FMAs of [J|r]^T [J|r] + 1240 FMAs for the sincos, the chain walk,
+        # the 18 parameter columns and the residuals = 2500 FMAs = 5000 flop
+        self.alg_flop = {"calib_normal_eq": 5000.0}
         self.traffic = {k: v * m for k, v in ncu_traffic_per_unit().items()}
         self.launches_per_step = 1
         self.config = {
