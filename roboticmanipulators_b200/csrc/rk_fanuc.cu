@@ -627,6 +627,7 @@ __device__ __forceinline__ bool fanuc_ik8_pose(const FanucP<S>& P, const S (&R0)
         const S u[6] = {u0, u1, u2, u3, u4, u5};
         out.branch(mi * 4 + ki * 2 + w, ok, u);  // solution or the all-zero sentinel (:239, :300)
       }
+      out.pair_done(mi * 4 + ki * 2);
     }
   }
   return rare;
@@ -735,6 +736,7 @@ struct IkPlaneSink {
   __device__ __forceinline__ void ok(int b, bool f) {
     if (qp) vp[(int64_t)b * ld] = f ? 1 : 0;
   }
+  __device__ __forceinline__ void pair_done(int) {}
 };
 
 template <typename S>
@@ -800,6 +802,138 @@ fanuc_ik8_pose_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant
           sink.ok(mk * 2 + w, ok[w]);
         }
       }
+    }
+  }
+}
+
+// AOS twin of fanuc_ik8_pose_kernel (the reference's shapes: T [n][4][4] -> q [n][8][6],
+// valid [n][8]).  A warp's 32 poses are one contiguous 4 KB run of T: it arrives by one 2-D TMA
+// load of the [32 poses][16] box with the hardware swizzle (128 B rows for FP64, 64 B for FP32), so
+// that lane L reads ITS row with 16-byte loads and no bank conflict.  The two solutions of an
+// (m, k) pair (12 values per pose) are staged in a warp-private tile with a padded row stride
+// (conflict-free 16-byte stores) and copied out cooperatively: the pair is 32 runs of 12 values at
+// a 48-value pitch, walked in 16-byte pieces so that every store instruction writes whole runs
+// (FP32 stages the whole pose instead, see IkPoseTileAos).
+// The 8 validity bytes of a pose are packed into one 64-bit store.
+template <typename S>
+struct alignas(1024) IkPoseTileAos {
+  static constexpr int kPoses = kWarp;
+  // FP64: one (m, k) pair is staged at a time (its 96-byte runs are whole 32-byte sectors).  FP32: a
+  // pair's run is 48 bytes = 1.5 sectors, and partial-sector writes make L2 fetch the sector first,
+  // so the whole pose (8 x 6 values, 192 bytes) is staged and the tile leaves as one contiguous run.
+  static constexpr bool kFull = sizeof(S) == 4;
+  static constexpr int kRun = kFull ? 48 : 12;
+  // staging row stride (elements): rows stay 16-byte aligned and 8 consecutive rows start in 8
+  // different 16-byte bank groups (112 B for FP64, 208 B for FP32)
+  static constexpr int kStage = kFull ? 52 : 14;
+  S in[2][kPoses][16];
+  S stage[kPoses][kStage];
+  uint64_t bar[2];
+};
+
+template <typename S>
+struct IkAosSink {
+  using Tile = IkPoseTileAos<S>;
+  Tile& sm;
+  S* qwarp;       // q_out of the warp's first pose
+  int lane, cnt;  // cnt = live poses of this tile
+  unsigned long long okbits;
+  static constexpr int kPer16 = 16 / sizeof(S);         // elements per 16-byte piece
+  static constexpr int kPieces = Tile::kRun / kPer16;   // pieces per staged run
+  __device__ __forceinline__ void branch(int b, bool okf, const S (&u)[6]) {
+    const int col = Tile::kFull ? b * 6 : (b & 1) * 6;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) sm.stage[lane][col + j] = okf ? u[j] : S(0);
+    okbits |= (unsigned long long)(okf ? 1 : 0) << (8 * b);
+  }
+  __device__ __forceinline__ void pair_done(int b0) {
+    if (Tile::kFull && b0 != 6) return;  // (m, k) = (-1, -1) is the last pair of a pose
+    __syncwarp();
+    const int total = cnt * kPieces;
+    const int goff = Tile::kFull ? 0 : b0 * 6;
+    for (int p = lane; p < total; p += kWarp) {
+      const int pose = p / kPieces, part = p - pose * kPieces;
+      const uint4 v = *reinterpret_cast<const uint4*>(&sm.stage[pose][part * kPer16]);
+      __stcs(reinterpret_cast<uint4*>(qwarp + (int64_t)pose * 48 + goff + part * kPer16), v);
+    }
+    __syncwarp();
+  }
+};
+
+template <typename S, bool STD>
+__global__ void __launch_bounds__(kBlock, sizeof(S) == 4 ? 6 : 4)
+fanuc_ik8_pose_aos_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant__ CUtensorMap tmT,
+                          S* __restrict__ q_out, uint8_t* __restrict__ valid, int64_t n, int64_t ntiles) {
+  using Tile = IkPoseTileAos<S>;
+  constexpr int TP = Tile::kPoses;
+  constexpr int WPB = kBlock / kWarp;
+  constexpr int kPer16 = 16 / sizeof(S);
+  constexpr unsigned kSwz = sizeof(S) == 8 ? 7u : 3u;  // 128-byte / 64-byte swizzle of the row
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = uniform_warp_idx();
+  // the swizzle pattern is a function of the absolute shared-memory address: tiles start on 1 KB
+  unsigned char* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  Tile& sm = reinterpret_cast<Tile*>(smem_al)[warp];
+  if (lane == 0) {
+    mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  auto issue_load = [&](int64_t tile, int buf) {  // one lane
+    mbar_expect_tx(&sm.bar[buf], 16 * TP * sizeof(S));
+    tma_load_2d(&sm.in[buf][0][0], &tmT, 0, (int)(tile * TP), &sm.bar[buf]);
+  };
+  const int64_t stride = (int64_t)gridDim.x * WPB;
+  int64_t tile = (int64_t)blockIdx.x * WPB + warp;
+  if (lane == 0 && tile < ntiles) issue_load(tile, 0);
+  int it = 0;
+  for (; tile < ntiles; tile += stride, ++it) {
+    const int buf = it & 1;
+    const int64_t next = tile + stride;
+    if (lane == 0 && next < ntiles) issue_load(next, buf ^ 1);
+    mbar_wait(&sm.bar[buf], (it >> 1) & 1);
+    // lane L owns row L; 16-byte piece c of the row sits at piece c ^ (swizzle bits of the address)
+    S Tin[12];
+    const unsigned char* rowp = reinterpret_cast<const unsigned char*>(&sm.in[buf][lane][0]);
+    const unsigned rowoff = (unsigned)(lane * 16 * sizeof(S));
+#pragma unroll
+    for (int c = 0; c < 12 / kPer16; ++c) {
+      const unsigned off = ((unsigned)c ^ ((rowoff >> 7) & kSwz)) << 4;
+      const uint4 v = *reinterpret_cast<const uint4*>(rowp + off);
+      S tmp[kPer16];
+      *reinterpret_cast<uint4*>(tmp) = v;
+#pragma unroll
+      for (int e = 0; e < kPer16; ++e) Tin[c * kPer16 + e] = tmp[e];
+    }
+    __syncwarp();
+    // every lane runs (fanuc_ik8_pose votes across the warp); rows past the end were zero-filled
+    const int64_t base = tile * TP;
+    const int64_t i = base + lane;
+    const int64_t rem = n - base;
+    S R0[9], p0[3];
+    fanuc_ik_t0(P, Tin, R0, p0);
+    IkAosSink<S> sink{sm, q_out + base * 48, lane, rem < TP ? (int)rem : TP, 0ull};
+    const bool rare = fanuc_ik8_pose<S, STD>(P, R0, p0, sink);
+    if (i < n) {
+      if (rare) {
+        // measure-zero configurations: the branch-by-branch routine with all its special cases
+        sink.okbits = 0ull;
+#pragma unroll 1
+        for (int mk = 0; mk < 4; ++mk) {
+          const int wl[2] = {0, 1};
+          S qo[2][6];
+          bool ok[2];
+          fanuc_ik_mk<S, 2, false>(P, R0, p0, (mk & 2) ? -1 : 1, (mk & 1) ? -1 : 1, wl, qo, ok);
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) q_out[i * 48 + (mk * 2 + w) * 6 + j] = qo[w][j];
+            sink.okbits |= (unsigned long long)(ok[w] ? 1 : 0) << (8 * (mk * 2 + w));
+          }
+        }
+      }
+      *reinterpret_cast<unsigned long long*>(valid + i * 8) = sink.okbits;
     }
   }
 }
@@ -928,8 +1062,26 @@ static int launch_ik(const RkFanuc* robot, const S* T, int64_t n, int64_t ld, in
         fanuc_ik8_kernel<S, true, 4><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
       }
     } else {
-      int grid = persistent_grid(fanuc_ik8_kernel<S, false, 4>, kBlock, 0, n * 4);
-      fanuc_ik8_kernel<S, false, 4><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
+      // thread-per-pose kernel when the arrays allow 16-byte accesses, 4-lanes-per-pose kernel otherwise
+      constexpr int TP = IkPoseTileAos<S>::kPoses;
+      CUtensorMap tmT;
+      const bool aligned = (((uintptr_t)q_out & 15) == 0) && (((uintptr_t)valid & 7) == 0);
+      if (aligned && make_tmap_2d(&tmT, TmapType<S>::value, sizeof(S), T, 16, n, 16 * sizeof(S), 16, TP,
+                                  sizeof(S) == 8 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)) {
+        const int64_t ntiles = (n + TP - 1) / TP;
+        const size_t smem = sizeof(IkPoseTileAos<S>) * (kBlock / kWarp) + 1024;
+        auto kern = P.std_limits ? fanuc_ik8_pose_aos_kernel<S, true> : fanuc_ik8_pose_aos_kernel<S, false>;
+        static thread_local bool attr_done[2] = {false, false};
+        if (!attr_done[P.std_limits]) {
+          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          attr_done[P.std_limits] = true;
+        }
+        int grid = persistent_grid(kern, kBlock, smem, ntiles * kWarp);
+        kern<<<grid, kBlock, smem, st>>>(P, tmT, q_out, valid, n, ntiles);
+      } else {
+        int grid = persistent_grid(fanuc_ik8_kernel<S, false, 4>, kBlock, 0, n * 4);
+        fanuc_ik8_kernel<S, false, 4><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
+      }
     }
     return check_launch();
   }
