@@ -115,6 +115,53 @@ arm_ik_kernel(const __grid_constant__ ArmP P, const __grid_constant__ ArmBranche
   }
 }
 
+// Canonical branch set (RRR: 4 = m outer, k inner; RR: 2), one thread per target: the work shared
+// by the branches is done once (rrr_ik4_pose / rr_ik2_pose).  The arms' IK is position-only, so
+// without a base / tool transform only the translation column of T is read (24 of 128 bytes).
+template <int NQ, bool SOA>
+__global__ void __launch_bounds__(kBlock)
+arm_ik_pose_kernel(const __grid_constant__ ArmP P, const double* __restrict__ T, int64_t n, int64_t ld,
+                   double* __restrict__ q_out, uint8_t* __restrict__ valid) {
+  constexpr int NB = (NQ == 3) ? 4 : 2;
+  const bool full = P.has_base || P.has_tool;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double p0[3];
+    if (full) {
+      double Tin[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) Tin[k] = SOA ? __ldcs(T + k * ld + i) : T[i * 16 + k];
+      arm_ik_p0(P, Tin, p0);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) p0[k] = SOA ? __ldcs(T + (4 * k + 3) * ld + i) : T[i * 16 + 4 * k + 3];
+    }
+    double qo[NB][NQ];
+    bool ok[NB];
+    if constexpr (NQ == 3)
+      rrr_ik4_pose(P, p0, qo, ok);
+    else
+      rr_ik2_pose(P, p0, qo, ok);
+    if (SOA) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) __stcs(q_out + (int64_t)(b * NQ + j) * ld + i, qo[b][j]);
+        valid[(int64_t)b * ld + i] = ok[b] ? 1 : 0;
+      }
+    } else {
+      // [n][NB][NQ]: a thread's NB*NQ values are contiguous (96 / 32 bytes)
+      double* qp = q_out + i * (NB * NQ);
+#pragma unroll
+      for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int j = 0; j < NQ; j += 1) qp[b * NQ + j] = qo[b][j];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) valid[i * NB + b] = ok[b] ? 1 : 0;
+    }
+  }
+}
+
 template <int NQ>
 static int launch_arm_fk(const RkArm* robot, const double* q, int64_t n, int64_t ld, int flags,
                          double* T, double* J, void* stream) {
@@ -163,6 +210,21 @@ static int launch_arm_ik(const RkArm* robot, const double* T, int64_t n, int64_t
     BL.mk[b * 2 + 1] = (int8_t)k;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  bool canonical = nb == canon;
+  for (int b = 0; b < nb && canonical; ++b) {
+    const int m = (NQ == 3) ? ((b & 2) ? -1 : 1) : (b ? -1 : 1), k = (NQ == 3) ? ((b & 1) ? -1 : 1) : 1;
+    canonical = BL.mk[b * 2] == m && BL.mk[b * 2 + 1] == k;
+  }
+  if (canonical) {
+    if (soa) {
+      int grid = persistent_grid(arm_ik_pose_kernel<NQ, true>, kBlock, 0, n);
+      arm_ik_pose_kernel<NQ, true><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
+    } else {
+      int grid = persistent_grid(arm_ik_pose_kernel<NQ, false>, kBlock, 0, n);
+      arm_ik_pose_kernel<NQ, false><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
+    }
+    return check_launch();
+  }
   if (soa) {
     int grid = persistent_grid(arm_ik_kernel<NQ, true>, kBlock, 0, n * nb);
     arm_ik_kernel<NQ, true><<<grid, kBlock, 0, st>>>(P, BL, T, n, ld, q_out, valid);

@@ -118,60 +118,112 @@ __device__ __forceinline__ void arm_ik_p0(const ArmP& P, const double (&Tin)[12]
   p0[0] = B[3], p0[1] = B[7], p0[2] = B[11];
 }
 
-// RRRRobot.inverse_kinematics (rrr_robot.py:137-201); zeros + false on failure.
+// RRRRobot.inverse_kinematics (rrr_robot.py:137-201) for the elbow sign m, both shoulder-independent
+// pieces shared by the caller: everything the reference takes a sine or cosine of is an angle it
+// has just produced with acos/atan2, so those are formed from the operands (as in the Fanuc IK):
+// sin(q2) = m sqrt(1 - cc^2); A = l1 cos q1 + l2 cos(q1 + q2) (:181) is the radial coordinate of the
+// target, i.e. x' itself up to rounding.  acos(cc) = atan2(sqrt((1-cc)(1+cc)), cc).
+struct RrrK {          // what depends on the target and on k only
+  double xp, zp, cc, sabs, acosc, beta, gamma;
+  bool reach;
+};
+
+__device__ __forceinline__ RrrK rrr_ik_k(const ArmP& P, const double (&p0)[3], double rxy, int k) {
+  using M = Sc<double>;
+  const double l0 = P.l[0], l1 = P.l[1], l2 = P.l[2];
+  RrrK r;
+  r.xp = k > 0 ? rxy : -rxy;                                                     // :162
+  r.zp = M::sub(l0, p0[2]);                                                      // :163
+  const double num = M::sub(M::sub(M::add(M::mul(r.xp, r.xp), M::mul(r.zp, r.zp)), M::mul(l1, l1)),
+                            M::mul(l2, l2));                                     // :165-166
+  r.cc = M::div(num, M::mul(M::mul(2.0, l1), l2));                               // :167-168
+  r.reach = !(fabs(r.cc) > 1.0);                                                 // :171
+  const double c = r.reach ? r.cc : 0.5;   // unreachable: computed on harmless operands, discarded
+  r.sabs = fast_sqrt((1.0 - c) * (1.0 + c));
+  r.acosc = fast_atan2(r.sabs, c);                                               // :175 (|q2|)
+  r.beta = fast_atan2(l2 * r.sabs, l1 + l2 * c);                                 // :177-178, m = +1
+  r.gamma = fast_atan2(r.zp, r.xp);                                              // :179
+  return r;
+}
+
+// finishes branch (m, k): limits (:191-196) and the zeros-on-failure convention
+__device__ __forceinline__ bool rrr_ik_finish(const ArmP& P, const RrrK& r, double q0atan, int m,
+                                              double (&qo)[3]) {
+  using M = Sc<double>;
+  const double q2 = m > 0 ? r.acosc : -r.acosc;                                  // :175
+  const double q1 = m > 0 ? M::sub(r.gamma, r.beta) : M::add(r.gamma, r.beta);   // :179
+  const double q0 = (fabs(r.xp) < P.eps) ? 0.0 : q0atan;                         // :181-187
+  const double qs[3] = {q0, q1, q2};
+  bool out = !r.reach;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) out = out || (qs[j] < P.lo[j]) || (qs[j] > P.hi[j]);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) qo[j] = out ? 0.0 : qs[j];
+  return !out;
+}
+
 __device__ __forceinline__ bool rrr_ik_branch(const ArmP& P, const double (&p0)[3], int m, int k,
                                               double (&qo)[3]) {
   using M = Sc<double>;
-  const double fm = (double)m, fk = (double)k;
-  const double l0 = P.l[0], l1 = P.l[1], l2 = P.l[2];
-  const double x = p0[0], y = p0[1], z = p0[2];
-  qo[0] = qo[1] = qo[2] = 0.0;
-  const double xp = M::mul(fk, M::sqrt(M::add(M::mul(x, x), M::mul(y, y))));   // :162
-  const double zp = M::sub(l0, z);                                             // :163
-  const double num = M::sub(M::sub(M::add(M::mul(xp, xp), M::mul(zp, zp)), M::mul(l1, l1)),
-                            M::mul(l2, l2));                                   // :165-166
-  const double cc = M::div(num, M::mul(M::mul(2.0, l1), l2));                  // :167-168
-  if (fabs(cc) > 1.0) return false;                                            // :171
-  const double q2 = fm * acos(cc);                                             // :175
-  double s2, c2;
-  fast_sincos(q2, &s2, &c2);
-  const double beta = atan2(l2 * (fm * s2), l1 + l2 * c2);                     // :177-178
-  const double q1 = M::sub(atan2(zp, xp), M::mul(fm, beta));                   // :179
-  const double A = l1 * cos(q1) + l2 * cos(M::add(q1, q2));                    // :181
-  const double q0 = (fabs(A) < P.eps) ? 0.0 : atan2(y, x);                     // :183-187
-  const double qs[3] = {q0, q1, q2};
-  bool out = false;
-#pragma unroll
-  for (int j = 0; j < 3; ++j) out = out || (qs[j] < P.lo[j]) || (qs[j] > P.hi[j]);  // :191-196
-  if (out) return false;
-  qo[0] = q0, qo[1] = q1, qo[2] = q2;
-  return true;
+  const double x = p0[0], y = p0[1];
+  const double rxy = M::sqrt(M::add(M::mul(x, x), M::mul(y, y)));                // :162
+  const RrrK r = rrr_ik_k(P, p0, rxy, k);
+  return rrr_ik_finish(P, r, fast_atan2(y, x), m, qo);
 }
 
-// RRRobot.inverse_kinematics (rr_robot.py:147-195)
-__device__ __forceinline__ bool rr_ik_branch(const ArmP& P, const double (&p0)[3], int m,
-                                             double (&qo)[2]) {
+// The canonical 4 branches (m outer, k inner) of one target in one thread: atan2(y, x) once,
+// acos / beta / gamma once per k (beta is odd in m) -- 7 atan2 instead of 16.
+__device__ __forceinline__ void rrr_ik4_pose(const ArmP& P, const double (&p0)[3], double (&qo)[4][3],
+                                             bool (&ok)[4]) {
   using M = Sc<double>;
-  const double fm = (double)m;
+  const double x = p0[0], y = p0[1];
+  const double rxy = M::sqrt(M::add(M::mul(x, x), M::mul(y, y)));
+  const double q0 = fast_atan2(y, x);
+#pragma unroll
+  for (int ki = 0; ki < 2; ++ki) {
+    const RrrK r = rrr_ik_k(P, p0, rxy, ki ? -1 : 1);
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) ok[mi * 2 + ki] = rrr_ik_finish(P, r, q0, mi ? -1 : 1, qo[mi * 2 + ki]);
+  }
+}
+
+// RRRobot.inverse_kinematics (rr_robot.py:147-195): both elbow signs share acos, beta (odd in m)
+// and atan2(y, x).
+__device__ __forceinline__ void rr_ik2_pose(const ArmP& P, const double (&p0)[3], double (&qo)[2][2],
+                                            bool (&ok)[2]) {
+  using M = Sc<double>;
   const double l0 = P.l[0], l1 = P.l[1];
   const double x = p0[0], y = p0[1];
-  qo[0] = qo[1] = 0.0;
   const double num = M::sub(M::sub(M::add(M::mul(x, x), M::mul(y, y)), M::mul(l0, l0)),
-                            M::mul(l1, l1));                                   // :167
-  const double cc = M::div(num, M::mul(M::mul(2.0, l0), l1));                  // :168-169
-  if (fabs(cc) > 1.0) return false;                                            // :172
-  const double q1 = fm * acos(cc);                                             // :176
-  double s1, c1;
-  fast_sincos(q1, &s1, &c1);
-  const double beta = atan2(l1 * (fm * s1), l0 + l1 * c1);                     // :177-178
-  const double q0 = M::sub(atan2(y, x), M::mul(fm, beta));                     // :179
-  const double qs[2] = {q0, q1};
-  bool out = false;
+                            M::mul(l1, l1));                                     // :167
+  const double cc = M::div(num, M::mul(M::mul(2.0, l0), l1));                    // :168-169
+  const bool reach = !(fabs(cc) > 1.0);                                          // :172
+  const double c = reach ? cc : 0.5;
+  const double sabs = fast_sqrt((1.0 - c) * (1.0 + c));
+  const double acosc = fast_atan2(sabs, c);                                      // :176
+  const double beta = fast_atan2(l1 * sabs, l0 + l1 * c);                        // :177-178, m = +1
+  const double th = fast_atan2(y, x);
 #pragma unroll
-  for (int j = 0; j < 2; ++j) out = out || (qs[j] < P.lo[j]) || (qs[j] > P.hi[j]);
-  if (out) return false;
-  qo[0] = q0, qo[1] = q1;
-  return true;
+  for (int mi = 0; mi < 2; ++mi) {
+    const double q1 = mi ? -acosc : acosc;
+    const double q0 = mi ? M::add(th, beta) : M::sub(th, beta);                  // :179
+    const double qs[2] = {q0, q1};
+    bool out = !reach;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) out = out || (qs[j] < P.lo[j]) || (qs[j] > P.hi[j]);
+    qo[mi][0] = out ? 0.0 : q0, qo[mi][1] = out ? 0.0 : q1;
+    ok[mi] = !out;
+  }
+}
+
+__device__ __forceinline__ bool rr_ik_branch(const ArmP& P, const double (&p0)[3], int m,
+                                             double (&qo)[2]) {
+  double q2[2][2];
+  bool ok[2];
+  rr_ik2_pose(P, p0, q2, ok);
+  const int mi = m > 0 ? 0 : 1;
+  qo[0] = q2[mi][0], qo[1] = q2[mi][1];
+  return ok[mi];
 }
 
 }  // namespace rk

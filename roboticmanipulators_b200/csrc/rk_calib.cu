@@ -1,31 +1,27 @@
 // Geometric calibration reductions (utils/model_calibration.py).
 //
-// K5 rk_calib_normal_eq_f64: H = sum J^T J, g = sum J^T r over (measurement, tool).
-// Each CTA alternates two phases on a tile of kMeas measurements, one tool at a time:
-//   phase 1  thread = measurement: joint sincos, walk the reduced chain (constant token
-//            runs pre-multiplied by the host), emit the 3 rows [J | r] of width <= 20 into
-//            a shared-memory slab (row stride 20 doubles);
-//   phase 2  thread = (4x4 tile of the upper triangle of [J|r]^T [J|r], k-slice): two
-//            LDS.128 pairs feed 16 register FMAs per row.
-// Accumulators stay in registers for the whole grid-stride loop; then k-slices are summed
-// through shared memory, CTA partials go to the workspace, and the last CTA to finish adds
-// them in index order (deterministic) and writes the packed result.
+// K5 rk_calib_normal_eq_f64: H = sum J^T J, g = sum J^T r over (measurement, tool) -- a CTA
+//    alternates phase 1 (two warp roles walk the reduced chain backwards once per measurement and
+//    emit 6 QR-compressed rows [J | r] in the end-effector frame into a shared-memory slab) and
+//    phase 2 (Gram accumulation of the slab on the FP64 tensor cores); see calib_normal_eq6_kernel.
+// K6 rk_calib_tool_base_eq_f64: the blocks of estimate_tool_base's A^T A / A^T dp are sums of 45
+//    per-measurement numbers, accumulated in registers (calib_tool_base_stats_kernel);
+//    rk_calib_eval_f64: residual sums and maxima.
+// Every reduction ends the same way: CTA partials go to the workspace and the last CTA to finish
+// (atomic ticket) adds them in index order, so results are deterministic.
 #include "rk_common.cuh"
 
 namespace rk {
 
-constexpr int kMeas = 128;     // measurements per CTA iteration (= threads per CTA)
-constexpr int kW = 20;         // logical row width: <= 19 columns + residual, 5 blocks of 4
-constexpr int kRS = 22;        // slab row stride (doubles): 16-byte aligned, 2-way banked at worst
-constexpr int kMaxTiles = 15;  // upper-triangular 4x4 tiles of a 5x5 block grid
-constexpr int kTileElems = kMaxTiles * 16;
+constexpr int kMeas = 128;     // threads per CTA
+constexpr int kW = 20;         // logical row width: <= 19 columns + residual
 constexpr int kMaxGrid = 1024;
 // 6-row kernel (tensor-core Gram): rows of kW doubles at an odd stride (phase-1 stores and the
 // DMMA fragment loads are both bank-conflict free, see gram_dmma); 8x8 tiles of a 24x24 Gram
 constexpr int kRS6 = 21;
 constexpr int kTiles6 = 6;
 constexpr int kPart6 = kTiles6 * 64;                  // doubles per CTA partial
-constexpr int kPartStride = kPart6 + 8;               // + r^T r; also covers the 4x4-tile kernels
+constexpr int kPartStride = kPart6 + 8;               // + r^T r; also covers the other reductions
 
 struct CalibP {
   int nj, np, nt;
@@ -37,6 +33,7 @@ struct CalibP {
   double pax[RK_CALIB_MAX_PARAMS][3], porg[RK_CALIB_MAX_PARAMS][3];
   double Tb[12];
   double tool[RK_CALIB_MAX_TOOLS][3];
+  int seg_trans[RK_CALIB_MAX_JOINTS];  // seg[j] is a pure translation (true at the nominal model)
 };
 
 static int make_calib(const RkCalibModel* m, CalibP& P, bool identity_base) {
@@ -67,6 +64,12 @@ static int make_calib(const RkCalibModel* m, CalibP& P, bool identity_base) {
       P.pax[q][k] = on ? m->param_axis[q][k] : 0.0;
       P.porg[q][k] = on ? m->param_origin[q][k] : 0.0;
     }
+  }
+  for (int j = 0; j < RK_CALIB_MAX_JOINTS; ++j) {
+    bool ident = true;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) ident = ident && P.seg[j][r * 4 + c] == ((r == c) ? 1.0 : 0.0);
+    P.seg_trans[j] = ident ? 1 : 0;
   }
   for (int k = 0; k < 12; ++k)
     P.Tb[k] = identity_base ? ((k % 5 == 0) ? 1.0 : 0.0) : m->T_base[k];
@@ -155,218 +158,15 @@ __device__ __forceinline__ void chain_end(const CalibP& P, const double (&s)[RK_
   for (int j = 0; j < RK_CALIB_MAX_JOINTS; ++j) {
     if (j < P.nj) {
       fr_joint(F, P.jaxis[j], P.jkind[j], s[j], c[j]);
-      fr_mul(F, P.seg[j]);
-    }
-  }
-}
-
-enum { MODE_NORMAL_EQ = 0, MODE_TOOL_BASE = 1 };
-
-// Phase 1: the three slab rows of (measurement, tool t).
-template <int MODE>
-__device__ __forceinline__ void fill_rows(const CalibP& P, const double (&s)[RK_CALIB_MAX_JOINTS],
-                                          const double (&c)[RK_CALIB_MAX_JOINTS], const Fr& Fend,
-                                          const double* __restrict__ pts, int64_t i, bool live, int t,
-                                          int ncols, double* __restrict__ rows /* [3][kRS] */) {
-  const int wpad = ((ncols + 3) / 4) * 4;
-  if (!live || MODE == MODE_TOOL_BASE) {
-    for (int r = 0; r < 3; ++r)
-      for (int k = 0; k < wpad; ++k) rows[r * kRS + k] = 0.0;
-    if (!live) return;
-  } else {
-    for (int r = 0; r < 3; ++r)
-      for (int k = ncols; k < wpad; ++k) rows[r * kRS + k] = 0.0;
-  }
-  const double* pm = pts + (i * P.nt + t) * 3;
-  if (MODE == MODE_NORMAL_EQ) {
-    const double On[3] = {
-        Fend.p[0] + Fend.R[0] * P.tool[t][0] + Fend.R[1] * P.tool[t][1] + Fend.R[2] * P.tool[t][2],
-        Fend.p[1] + Fend.R[3] * P.tool[t][0] + Fend.R[4] * P.tool[t][1] + Fend.R[5] * P.tool[t][2],
-        Fend.p[2] + Fend.R[6] * P.tool[t][0] + Fend.R[7] * P.tool[t][1] + Fend.R[8] * P.tool[t][2]};
-    Fr F;
-    fr_init(F, P.Tb);
+      if (P.seg_trans[j]) {
 #pragma unroll
-    for (int j = 0; j < RK_CALIB_MAX_JOINTS; ++j) {
-      if (j < P.nj) {
-        fr_joint(F, P.jaxis[j], P.jkind[j], s[j], c[j]);
-        for (int p = P.pstart[j]; p < P.pstart[j + 1]; ++p) {
-          const V3<double> ax = {P.pax[p][0], P.pax[p][1], P.pax[p][2]};
-          const V3<double> u = rot(F.R, ax);
-          V3<double> col = u;                         // translation parameter: u
-          if (P.pkind[p] == 1) {                      // rotation parameter: u x (O_n - O_p)
-            const V3<double> og = {P.porg[p][0], P.porg[p][1], P.porg[p][2]};
-            const V3<double> ro = rot(F.R, og);
-            const V3<double> d = {On[0] - (F.p[0] + ro.x), On[1] - (F.p[1] + ro.y),
-                                  On[2] - (F.p[2] + ro.z)};
-            col = cross(u, d);
-          }
-          rows[0 * kRS + p] = col.x;
-          rows[1 * kRS + p] = col.y;
-          rows[2 * kRS + p] = col.z;
-        }
+        for (int i = 0; i < 3; ++i)
+          F.p[i] += F.R[i * 3] * P.seg[j][3] + F.R[i * 3 + 1] * P.seg[j][7] + F.R[i * 3 + 2] * P.seg[j][11];
+      } else {
         fr_mul(F, P.seg[j]);
       }
     }
-    // residual column: r = p_meas - T[:3,3] (model_calibration.py:420)
-#pragma unroll
-    for (int r = 0; r < 3; ++r) rows[r * kRS + P.np] = pm[r] - On[r];
-  } else {
-    // estimate_tool_base rows [I | skew(p)^T | R at tool block | dp] (model_calibration.py:306-329)
-    const double px = Fend.p[0], py = Fend.p[1], pz = Fend.p[2];
-    const double St[9] = {0.0, pz, -py, -pz, 0.0, px, py, -px, 0.0};
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      rows[r * kRS + r] = 1.0;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        rows[r * kRS + 3 + k] = St[r * 3 + k];
-        rows[r * kRS + 6 + 3 * t + k] = Fend.R[r * 3 + k];
-      }
-      rows[r * kRS + ncols - 1] = pm[r] - Fend.p[r];
-    }
   }
-}
-
-// ---- phase 2 and the epilogue, shared by both accumulation kernels -------------------------
-// Thread (tile, k-slice): tile = 4x4 block (bi, bj), bi <= bj, of [J|r]^T [J|r].
-struct GramThread {
-  int ntiles, ksplit, tile, ks, bi, bj;
-  bool worker;
-  double acc[4][4];
-  __device__ __forceinline__ void init(int tid, int ncols) {
-    const int nblk = (ncols + 3) / 4;
-    ntiles = nblk * (nblk + 1) / 2;
-    ksplit = kMeas / ntiles;
-    worker = tid < ntiles * ksplit;
-    tile = tid % ntiles, ks = tid / ntiles;
-    bi = 0;
-    int rem = tile;
-    while (rem >= nblk - bi) {
-      rem -= nblk - bi;
-      ++bi;
-    }
-    bj = bi + rem;
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-  }
-  // accumulate the kMeas*3 slab rows (two LDS.128 pairs feed 16 register FMAs per row)
-  __device__ __forceinline__ void accumulate(const double* __restrict__ slab) {
-    if (!worker) return;
-    const double* ra = slab + bi * 4;
-    const double* rb = slab + bj * 4;
-#pragma unroll 4
-    for (int sl = ks; sl < kMeas * 3; sl += ksplit) {
-      const double2 a01 = *reinterpret_cast<const double2*>(ra + sl * kRS);
-      const double2 a23 = *reinterpret_cast<const double2*>(ra + sl * kRS + 2);
-      const double2 b01 = *reinterpret_cast<const double2*>(rb + sl * kRS);
-      const double2 b23 = *reinterpret_cast<const double2*>(rb + sl * kRS + 2);
-      const double av[4] = {a01.x, a01.y, a23.x, a23.y};
-      const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
-    }
-  }
-};
-
-// k-slices -> CTA partial -> workspace; the last CTA to finish adds the partials in index order
-// (deterministic) and scatters the packed result.
-template <int MODE>
-__device__ __forceinline__ void gram_epilogue(GramThread& G, double* __restrict__ slab, int ncols,
-                                              double* __restrict__ partial,
-                                              unsigned int* __restrict__ counter,
-                                              double* __restrict__ out) {
-  __shared__ int s_last;
-  const int tid = threadIdx.x;
-  const int nblk = (ncols + 3) / 4;
-  const int ntiles = G.ntiles, ksplit = G.ksplit;
-  __syncthreads();
-  if (G.worker) {
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) slab[(G.ks * ntiles + G.tile) * 16 + a * 4 + b] = G.acc[a][b];
-  }
-  __syncthreads();
-  for (int e = tid; e < ntiles * 16; e += kMeas) {
-    double sum = 0.0;
-    for (int k = 0; k < ksplit; ++k) sum += slab[k * ntiles * 16 + e];
-    partial[(int64_t)blockIdx.x * kPartStride + e] = sum;
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1 : 0;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  // last CTA: deterministic sum over CTAs, then scatter into the caller's format
-  for (int e = tid; e < ntiles * 16; e += kMeas) {
-    double sum = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) sum += __ldcg(partial + (int64_t)b * kPartStride + e);
-    slab[e] = sum;
-  }
-  __syncthreads();
-  for (int e = tid; e < ntiles * 16; e += kMeas) {
-    const int tl = e / 16, a = (e % 16) / 4, b = e % 4;
-    int ti = 0, rem = tl;
-    while (rem >= nblk - ti) {
-      rem -= nblk - ti;
-      ++ti;
-    }
-    const int tj = ti + rem;
-    const int gi = ti * 4 + a, gj = tj * 4 + b;
-    if (gi > gj || gj >= ncols) continue;
-    const double v = slab[e];
-    if (MODE == MODE_NORMAL_EQ) {
-      const int np = ncols - 1;
-      if (gj < np) {
-        out[gi * np - gi * (gi - 1) / 2 + (gj - gi)] = v;             // packed upper H
-      } else if (gi < np) {
-        out[np * (np + 1) / 2 + gi] = v;                               // g
-      } else {
-        out[np * (np + 1) / 2 + np] = v;                               // r^T r
-      }
-    } else {
-      const int dim = ncols - 1;
-      if (gj < dim) {
-        out[gi * dim + gj] = v;
-        out[gj * dim + gi] = v;
-      } else if (gi < dim) {
-        out[dim * dim + gi] = v;
-      }
-    }
-  }
-  if (tid == 0) *counter = 0;  // workspace is reusable without a memset
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(kMeas, 3)
-calib_accumulate_kernel(const __grid_constant__ CalibP P, const double* __restrict__ q,
-                        const double* __restrict__ pts, int64_t m, int ncols,
-                        double* __restrict__ partial, unsigned int* __restrict__ counter,
-                        double* __restrict__ out) {
-  extern __shared__ __align__(16) double slab[];  // [kMeas*3][kRS]
-  const int tid = threadIdx.x;
-  GramThread G;
-  G.init(tid, ncols);
-  for (int64_t base = (int64_t)blockIdx.x * kMeas; base < m; base += (int64_t)gridDim.x * kMeas) {
-    const int64_t i = base + tid;
-    const bool live = i < m;
-    double sj[RK_CALIB_MAX_JOINTS], cj[RK_CALIB_MAX_JOINTS];
-    load_joints(P, q, i, live, sj, cj);
-    Fr Fend;
-    chain_end(P, sj, cj, Fend);
-    for (int t = 0; t < P.nt; ++t) {
-      __syncthreads();  // previous phase 2 is done with the slab
-      fill_rows<MODE>(P, sj, cj, Fend, pts, i, live, t, ncols, slab + tid * 3 * kRS);
-      __syncthreads();
-      G.accumulate(slab);
-    }
-  }
-  gram_epilogue<MODE>(G, slab, ncols, partial, counter, out);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -392,7 +192,6 @@ struct CalibN {
   double R[6][6];                         // upper triangular (trapezoidal for one tool)
   double Qt[6][3 * RK_CALIB_MAX_TOOLS];   // first 6 rows of Q^T
   int split;
-  int seg_trans[RK_CALIB_MAX_JOINTS];     // X_j is a pure translation (true at the nominal model)
 };
 
 // Householder QR of the (3 nt) x 6 matrix M = [I | -[tool_t]x]; rows of R / Q^T beyond
@@ -458,12 +257,6 @@ static void make_calibn(const CalibP& P, CalibN& N) {
     if (cost < best_cost) best_cost = cost, best = sp;
   }
   N.split = best;
-  for (int j = 0; j < RK_CALIB_MAX_JOINTS; ++j) {
-    bool ident = true;
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c) ident = ident && P.seg[j][r * 4 + c] == ((r == c) ? 1.0 : 0.0);
-    N.seg_trans[j] = ident ? 1 : 0;
-  }
 }
 
 // Suffix transform S = (Q, s), 3x4 row-major in registers.
@@ -515,7 +308,7 @@ __device__ __forceinline__ void sfx_premul(Sfx& S, const double* X) {
 }
 
 // Phase 1 of the 6-row kernel for one (measurement, role): writes this role's columns of the six
-// slab rows (rows + r * 64 * kRS, r < 6); returns this measurement's r^T r (role B) or 0.
+// slab rows (rows + r * 64 * kRS6, r < 6); returns this measurement's r^T r (role B) or 0.
 __device__ __forceinline__ double fill_rows6(const CalibP& P, const CalibN& N, bool role_a,
                                              const double (&qv)[RK_CALIB_MAX_JOINTS],
                                              const double (&pv)[3 * RK_CALIB_MAX_TOOLS], bool live,
@@ -543,7 +336,7 @@ __device__ __forceinline__ double fill_rows6(const CalibP& P, const CalibN& N, b
 #pragma unroll 1
   for (int j = P.nj - 1; j >= jstop; --j) {
     {
-      if (N.seg_trans[j]) {      // S_j = X_j Rot_{j+1} S_{j+1}
+      if (P.seg_trans[j]) {      // S_j = X_j Rot_{j+1} S_{j+1}
         S.s[0] += P.seg[j][3], S.s[1] += P.seg[j][7], S.s[2] += P.seg[j][11];
       } else {
         sfx_premul(S, P.seg[j]);
@@ -748,6 +541,130 @@ calib_normal_eq6_kernel(const __grid_constant__ CalibP P, const __grid_constant_
   if (tid == 0) *counter = 0;  // workspace is reusable without a memset
 }
 
+// -------------------------------------------------------------------------------------------
+// estimate_tool_base (model_calibration.py:296-332) without forming the rows.  The reference sums
+// A^T A and A^T dp over (measurement i, tool t) with A = [I | skew(p_i)^T | R_i in block t],
+// dp = p_meas(i,t) - p_i, where (R_i, p_i) is the flange pose.  Every block of those sums is a
+// plain sum of a few per-measurement quantities:
+//   I^T I = n nt I;  I^T skew^T = nt skew(sum p)^T;  I^T R = sum R;  skew skew^T = nt sum(|p|^2 I - p p^T);
+//   skew R = sum [p x R[:,b]];  R^T R = n I (orthonormal);  and for the right-hand side
+//   sum_t dp = d,  skew dp -> p x d,  R^T dp per tool.
+// So a thread accumulates 33 + 3 nt numbers per measurement (~150 FMAs after the chain) instead
+// of feeding 9 rows of width 16 to a Gram accumulation (1224 FMAs); the last CTA assembles the
+// caller's dim x dim + dim layout.
+// -------------------------------------------------------------------------------------------
+constexpr int kTbAcc = 33 + 3 * RK_CALIB_MAX_TOOLS;
+
+__global__ void __launch_bounds__(kMeas, 3)
+calib_tool_base_stats_kernel(const __grid_constant__ CalibP P, const double* __restrict__ q,
+                             const double* __restrict__ pts, int64_t m, double* __restrict__ partial,
+                             unsigned int* __restrict__ counter, double* __restrict__ out) {
+  __shared__ double red[kMeas / kWarp][kTbAcc];
+  __shared__ double tot[kTbAcc];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double acc[kTbAcc];
+#pragma unroll
+  for (int k = 0; k < kTbAcc; ++k) acc[k] = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * kMeas + tid; i < m; i += (int64_t)gridDim.x * kMeas) {
+    double sj[RK_CALIB_MAX_JOINTS], cj[RK_CALIB_MAX_JOINTS];
+    load_joints(P, q, i, true, sj, cj);
+    Fr F;
+    chain_end(P, sj, cj, F);
+    const double px = F.p[0], py = F.p[1], pz = F.p[2];
+    acc[0] += px, acc[1] += py, acc[2] += pz;
+    acc[3] += px * px, acc[4] += px * py, acc[5] += px * pz;
+    acc[6] += py * py, acc[7] += py * pz, acc[8] += pz * pz;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[9 + k] += F.R[k];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {  // p x R[:, b]
+      const double rx = F.R[b], ry = F.R[3 + b], rz = F.R[6 + b];
+      acc[18 + 0 * 3 + b] += py * rz - pz * ry;
+      acc[18 + 1 * 3 + b] += pz * rx - px * rz;
+      acc[18 + 2 * 3 + b] += px * ry - py * rx;
+    }
+    double dx = 0.0, dy = 0.0, dz = 0.0;
+#pragma unroll
+    for (int t = 0; t < RK_CALIB_MAX_TOOLS; ++t) {
+      if (t < P.nt) {
+        const double* pm = pts + (i * P.nt + t) * 3;
+        const double ex = pm[0] - px, ey = pm[1] - py, ez = pm[2] - pz;  // dp (:328)
+        dx += ex, dy += ey, dz += ez;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc[33 + 3 * t + k] += F.R[k] * ex + F.R[3 + k] * ey + F.R[6 + k] * ez;
+      }
+    }
+    acc[27] += dx, acc[28] += dy, acc[29] += dz;
+    acc[30] += py * dz - pz * dy, acc[31] += pz * dx - px * dz, acc[32] += px * dy - py * dx;
+  }
+#pragma unroll
+  for (int k = 0; k < kTbAcc; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][k] = v;
+  }
+  __syncthreads();
+  if (tid < kTbAcc) {
+    double v = 0.0;
+    for (int w = 0; w < kMeas / kWarp; ++w) v += red[w][tid];
+    partial[(int64_t)blockIdx.x * kPartStride + tid] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid < kTbAcc) {
+    double v = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(partial + (int64_t)b * kPartStride + tid);
+    tot[tid] = v;
+  }
+  __syncthreads();
+  // assemble A^T A (dim x dim, row-major) and A^T dp (dim)
+  const int nt = P.nt, dim = 6 + 3 * nt;
+  const double n = (double)m, fnt = (double)nt;
+  for (int e = tid; e < dim * dim + dim; e += kMeas) {
+    double v = 0.0;
+    if (e >= dim * dim) {
+      const int r = e - dim * dim;
+      v = r < 3 ? tot[27 + r] : (r < 6 ? tot[30 + (r - 3)] : tot[33 + (r - 6)]);
+    } else {
+      int r = e / dim, c = e - r * dim;
+      if (r > c) {  // symmetric
+        const int t = r;
+        r = c, c = t;
+      }
+      if (c < 3) {
+        v = (r == c) ? n * fnt : 0.0;
+      } else if (c < 6) {
+        const int k = c - 3;
+        if (r < 3) {  // nt * skew(sum p)^T = [[0, Pz, -Py], [-Pz, 0, Px], [Py, -Px, 0]]
+          const double St[9] = {0.0, tot[2], -tot[1], -tot[2], 0.0, tot[0], tot[1], -tot[0], 0.0};
+          v = fnt * St[r * 3 + k];
+        } else {      // nt * sum(|p|^2 I - p p^T)
+          const int a = r - 3;
+          const double pp[9] = {tot[3], tot[4], tot[5], tot[4], tot[6], tot[7], tot[5], tot[7], tot[8]};
+          v = fnt * (((a == k) ? (tot[3] + tot[6] + tot[8]) : 0.0) - pp[a * 3 + k]);
+        }
+      } else {
+        const int k = (c - 6) % 3;
+        if (r < 3) {
+          v = tot[9 + r * 3 + k];          // sum R
+        } else if (r < 6) {
+          v = tot[18 + (r - 3) * 3 + k];   // sum skew(p) R
+        } else {
+          v = (r == c) ? n : 0.0;          // R^T R = I; different tools do not couple
+        }
+      }
+    }
+    out[e] = v;
+  }
+  if (tid == 0) *counter = 0;
+}
+
 // evaluate (model_calibration.py:480-505): sums of squares and maxima of the residuals
 __global__ void __launch_bounds__(kMeas)
 calib_eval_kernel(const __grid_constant__ CalibP P, const double* __restrict__ q,
@@ -812,35 +729,6 @@ calib_eval_kernel(const __grid_constant__ CalibP P, const double* __restrict__ q
 constexpr size_t kWsCounterOffset = (size_t)kMaxGrid * kPartStride * sizeof(double);
 constexpr size_t kWsBytes = kWsCounterOffset + 256;
 
-template <int MODE>
-static int launch_accumulate(const RkCalibModel* model, const double* q, const double* pts, int64_t m,
-                             double* out, void* workspace, size_t ws_bytes, void* stream) {
-  if (!model || !out || m < 0) return RK_ERR_INVALID_ARG;
-  if (!workspace || ws_bytes < kWsBytes) return RK_ERR_WORKSPACE;
-  if (m > 0 && (!q || !pts)) return RK_ERR_INVALID_ARG;
-  CalibP P;
-  int rc = make_calib(model, P, MODE == MODE_TOOL_BASE);
-  if (rc != RK_OK) return rc;
-  const int ncols = (MODE == MODE_NORMAL_EQ) ? P.np + 1 : 6 + 3 * P.nt + 1;
-  if (ncols > kW) return RK_ERR_UNSUPPORTED;
-  cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = (size_t)kMeas * 3 * kRS * sizeof(double);
-  static thread_local bool attr_set[2] = {false, false};
-  if (!attr_set[MODE]) {
-    if (cudaFuncSetAttribute(calib_accumulate_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem) != cudaSuccess)
-      return check_launch();
-    attr_set[MODE] = true;
-  }
-  int grid = persistent_grid(calib_accumulate_kernel<MODE>, kMeas, smem, m > 0 ? m : 1);
-  if (grid > kMaxGrid) grid = kMaxGrid;
-  unsigned int* counter = reinterpret_cast<unsigned int*>((char*)workspace + kWsCounterOffset);
-  if (cudaMemsetAsync(counter, 0, sizeof(unsigned int), st) != cudaSuccess) return check_launch();
-  calib_accumulate_kernel<MODE><<<grid, kMeas, smem, st>>>(P, q, pts, m, ncols, (double*)workspace,
-                                                           counter, out);
-  return check_launch();
-}
-
 }  // namespace rk
 
 extern "C" {
@@ -880,7 +768,20 @@ int rk_calib_normal_eq_f64(const RkCalibModel* model, const double* q, const dou
 
 int rk_calib_tool_base_eq_f64(const RkCalibModel* model, const double* q, const double* pts, int64_t m,
                               double* out, void* workspace, size_t ws_bytes, void* stream) {
-  return rk::launch_accumulate<rk::MODE_TOOL_BASE>(model, q, pts, m, out, workspace, ws_bytes, stream);
+  using namespace rk;
+  if (!model || !out || m < 0) return RK_ERR_INVALID_ARG;
+  if (!workspace || ws_bytes < kWsBytes) return RK_ERR_WORKSPACE;
+  if (m > 0 && (!q || !pts)) return RK_ERR_INVALID_ARG;
+  CalibP P;
+  int rc = make_calib(model, P, true);
+  if (rc != RK_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = persistent_grid(calib_tool_base_stats_kernel, kMeas, 0, m > 0 ? m : 1);
+  if (grid > kMaxGrid) grid = kMaxGrid;
+  unsigned int* counter = reinterpret_cast<unsigned int*>((char*)workspace + kWsCounterOffset);
+  if (cudaMemsetAsync(counter, 0, sizeof(unsigned int), st) != cudaSuccess) return check_launch();
+  calib_tool_base_stats_kernel<<<grid, kMeas, 0, st>>>(P, q, pts, m, (double*)workspace, counter, out);
+  return check_launch();
 }
 
 int rk_calib_eval_f64(const RkCalibModel* model, const double* q, const double* pts, int64_t m,
