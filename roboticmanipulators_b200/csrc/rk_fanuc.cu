@@ -991,29 +991,41 @@ static int launch_fk_jac(const RkFanuc* robot, const S* q, int64_t n, int64_t ld
   FanucP<S> P = make_params<S>(robot, flags);
   cudaStream_t st = (cudaStream_t)stream;
   if (soa) {
+    // Whole 128-pose tiles go through the TMA kernel; the ragged tail (< 1 tile) through the LSU
+    // kernel.  TMA stores clip a box at 16-byte granularity, so a tensor map whose extent is not a
+    // multiple of 16 bytes would let the last store spill one element into the caller's padding
+    // (tests/test_more_gpu.py::test_no_out_of_range_writes); full tiles never clip.
     constexpr int TP = FkTile<S>::kPoses;
-    CUtensorMap tmq, tmT, tmJ, tmD;
-    const uint64_t pitch = (uint64_t)ld * sizeof(S);
-    // a missing output gets a (never used) alias of q so the kernel signature stays fixed
-    const bool tma_ok =
-        make_tmap_2d(&tmq, TmapType<S>::value, sizeof(S), q, n, 6, pitch, TP, 6) &&
-        make_tmap_2d(&tmT, TmapType<S>::value, sizeof(S), T ? T : (S*)q, n, T ? 16 : 6, pitch, TP, T ? 16 : 6) &&
-        make_tmap_2d(&tmJ, TmapType<S>::value, sizeof(S), J ? J : (S*)q, n, J ? 36 : 6, pitch, TP, J ? 36 : 6) &&
-        make_tmap_2d(&tmD, TmapType<S>::value, sizeof(S), det ? det : (S*)q, n, 1, pitch, TP, 1);
-    if (tma_ok) {
-      const int64_t ntiles = (n + TP - 1) / TP;
-      const size_t smem = sizeof(FkTile<S>);
-      static thread_local bool attr_done = false;
-      if (!attr_done) {
-        cudaFuncSetAttribute(fanuc_fk_jac_tma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_done = true;
+    int64_t n_main = (n / TP) * TP;
+    if (n_main > 0) {
+      CUtensorMap tmq, tmT, tmJ, tmD;
+      const uint64_t pitch = (uint64_t)ld * sizeof(S);
+      // a missing output gets a (never used) alias of q so the kernel signature stays fixed
+      const bool tma_ok =
+          make_tmap_2d(&tmq, TmapType<S>::value, sizeof(S), q, n_main, 6, pitch, TP, 6) &&
+          make_tmap_2d(&tmT, TmapType<S>::value, sizeof(S), T ? T : (S*)q, n_main, T ? 16 : 6, pitch, TP, T ? 16 : 6) &&
+          make_tmap_2d(&tmJ, TmapType<S>::value, sizeof(S), J ? J : (S*)q, n_main, J ? 36 : 6, pitch, TP, J ? 36 : 6) &&
+          make_tmap_2d(&tmD, TmapType<S>::value, sizeof(S), det ? det : (S*)q, n_main, 1, pitch, TP, 1);
+      if (tma_ok) {
+        const int64_t ntiles = n_main / TP;
+        const size_t smem = sizeof(FkTile<S>);
+        static thread_local bool attr_done = false;
+        if (!attr_done) {
+          cudaFuncSetAttribute(fanuc_fk_jac_tma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+          attr_done = true;
+        }
+        int grid = persistent_grid(fanuc_fk_jac_tma_kernel<S>, kBlock, smem, ntiles * kBlock);
+        fanuc_fk_jac_tma_kernel<S><<<grid, kBlock, smem, st>>>(P, tmq, tmT, tmJ, tmD, ntiles, T != nullptr,
+                                                               J != nullptr, det != nullptr);
+      } else {
+        n_main = 0;  // unaligned planes: everything through the LSU kernel
       }
-      int grid = persistent_grid(fanuc_fk_jac_tma_kernel<S>, kBlock, smem, ntiles * kBlock);
-      fanuc_fk_jac_tma_kernel<S><<<grid, kBlock, smem, st>>>(P, tmq, tmT, tmJ, tmD, ntiles, T != nullptr,
-                                                             J != nullptr, det != nullptr);
-    } else {
-      int grid = persistent_grid(fanuc_fk_jac_soa_kernel<S>, kBlock, 0, n);
-      fanuc_fk_jac_soa_kernel<S><<<grid, kBlock, 0, st>>>(P, q, n, ld, T, J, det);
+    }
+    if (n_main < n) {
+      const int64_t tail = n - n_main;
+      int grid = persistent_grid(fanuc_fk_jac_soa_kernel<S>, kBlock, 0, tail);
+      fanuc_fk_jac_soa_kernel<S><<<grid, kBlock, 0, st>>>(P, q + n_main, tail, ld, T ? T + n_main : nullptr,
+                                                          J ? J + n_main : nullptr, det ? det + n_main : nullptr);
     }
   } else {
     int grid = persistent_grid(fanuc_fk_jac_aos_kernel<S>, kBlock, 0, n);

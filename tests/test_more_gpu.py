@@ -141,3 +141,62 @@ def test_ik_f32_with_base_and_tool(golden):
         d = qb.cpu().numpy().astype(np.float64) - q_ref
         d[..., [3, 5]] = (d[..., [3, 5]] + np.pi) % (2 * np.pi) - np.pi
         assert np.nanpercentile(np.abs(d[both]), 99) < 5e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+def test_no_out_of_range_writes(dtype, layout):
+    """Ragged batch sizes (tiles cut short, TMA clipping, fallbacks for unaligned pitches), SOA
+    planes with a padded leading dimension: every output sits inside a canary-filled buffer and the
+    canaries must survive; results must equal the plain (unpadded) call."""
+    import ctypes as C
+    from roboticmanipulators_b200 import _lib
+    from roboticmanipulators_b200.robots.fanuc import Fanuc165F
+    lib = _lib.load()
+    robot, c = Fanuc165F(), O.FanucConst()
+    st = robot._struct()
+    sfx = "f64" if dtype == torch.float64 else "f32"
+    rng = np.random.default_rng(5)
+    CAN = 12345.0
+    for n, pad in ((1, 0), (31, 1), (32, 0), (33, 2), (100, 4), (1000, 0), (4097, 3), (4098, 6)):
+        q = torch.tensor(rng.uniform(c.lim[:, 0], c.lim[:, 1], size=(n, 6)), device="cuda", dtype=dtype)
+        T_ref, J_ref, det_ref = robot.forward_kinematics_batch(q, jacobian=True, measure=True, layout=layout)
+        q_ref, v_ref = robot.inverse_kinematics_batch(T_ref.contiguous(), layout=layout)
+        ld = n + pad if layout == "soa" else n
+        G = 64                                              # guard elements on both sides
+
+        def guarded(ncomp, dt=dtype, fill=CAN):
+            buf = torch.full((G + ncomp * ld + G,), fill, dtype=dt, device="cuda")
+            return buf, buf[G:G + ncomp * ld]
+        if layout == "soa":
+            qs = torch.full((6, ld), CAN, dtype=dtype, device="cuda")
+            qs[:, :n] = q.t()
+        else:
+            qs = q.contiguous()
+        Tb, Tv = guarded(16)
+        Jb, Jv = guarded(36)
+        Db, Dv = guarded(1)
+        flags = _lib.RK_SOA if layout == "soa" else _lib.RK_AOS
+        _lib.check(getattr(lib, "rk_fanuc_fk_jac_" + sfx)(
+            C.byref(st), _lib.ptr(qs), n, ld, flags, _lib.ptr(Tv), _lib.ptr(Jv), _lib.ptr(Dv), _lib.stream_ptr()))
+        Qb, Qv = guarded(48)
+        Vb, Vv = guarded(8, torch.uint8, 77)
+        _lib.check(getattr(lib, "rk_fanuc_ik_" + sfx)(
+            C.byref(st), _lib.ptr(Tv), n, ld, flags, None, 8, _lib.ptr(Qv), _lib.ptr(Vv), _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        for buf, view, ncomp, can in ((Tb, Tv, 16, CAN), (Jb, Jv, 36, CAN), (Db, Dv, 1, CAN), (Qb, Qv, 48, CAN),
+                                      (Vb, Vv, 8, 77)):
+            assert bool((buf[:G] == can).all()) and bool((buf[-G:] == can).all()), (n, pad, ncomp)
+            if layout == "soa" and pad:
+                assert bool((view.view(ncomp, ld)[:, n:] == can).all()), (n, pad, ncomp)
+
+        def logical(view, ncomp):
+            return view.view(ncomp, ld)[:, :n].t() if layout == "soa" else view.view(n, ncomp)
+        assert torch.equal(logical(Tv, 16), T_ref.reshape(n, 16))
+        assert torch.equal(logical(Jv, 36), J_ref.reshape(n, 36))
+        # the padded and the plain call may run different kernels (tile vs fallback): same masks,
+        # angles equal to rounding (q3/q5 modulo 2 pi at the atan2 cut)
+        assert torch.equal(logical(Vv, 8).bool(), v_ref.reshape(n, 8))
+        dq = (logical(Qv, 48).reshape(n, 8, 6) - q_ref).double().cpu().numpy()
+        dq[..., [3, 5]] = (dq[..., [3, 5]] + np.pi) % (2 * np.pi) - np.pi
+        assert np.nanmax(np.abs(dq)) < (1e-9 if dtype == torch.float64 else 2e-2)
