@@ -345,8 +345,10 @@ __device__ __forceinline__ void fence_async_smem() {
 }
 
 // 2-D tiled tensor maps: one TMA instruction moves a whole [rows][cols] box between the SOA
-// planes in HBM and a dense shared-memory tile; out-of-range columns are zero-filled on load and
-// clipped on store, so ragged tails need no special code.
+// planes in HBM and a dense shared-memory tile; out-of-range columns are zero-filled on load, so
+// ragged LOAD tails need no special code.  Stores are clipped too, but at 16-byte granularity
+// (measured: an 8-byte extent that ends on an odd element spills one element), so callers store
+// whole tiles only.
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y,
                                             uint64_t* bar) {
   asm volatile(
