@@ -130,3 +130,44 @@ def test_generic_chain_large_vs_oracle():
     Tg, Jg = jc2.calculate_numerically_batch(dev(O.fanuc_values(qm, O.FanucConst().ls)), with_pose=True)
     assert (Tf - Tg).abs().max().item() < 1e-11
     assert (Jf - Jg).abs().max().item() < 1e-10
+
+
+@pytest.mark.parametrize("layout", ["aos", "soa"])
+def test_arm_ik_special_targets(layout):
+    """Targets on the special cases of rrr_robot.py:137-201 / rr_robot.py:147-195: on the base axis
+    ("up position", q0 := 0), at and just beyond the reach limits (|arccos argument| = 1), the
+    elbow fully folded, far away, the origin."""
+    from roboticmanipulators_b200.robots import RRRRobot, RRRobot
+    rrr, rr = RRRRobot(), RRRobot()
+    l0, l1, l2 = [float(v) for v in rrr.ls]
+    pts = [(0.0, 0.0, l0 + 0.7), (0.0, 0.0, l0 - 0.4), (1e-7, -1e-7, l0 + 1.0), (3e-6, 4e-6, l0 + 0.3),
+           (l1 + l2, 0.0, l0), (0.0, l1 + l2, l0), ((l1 + l2) * (1 + 1e-15), 0.0, l0),
+           ((l1 + l2) * (1 - 1e-15), 0.0, l0), (l1 + l2 + 1e-9, 0.0, l0), (abs(l1 - l2) + 1e-12, 0.0, l0),
+           (0.0, 0.0, l0 + l1 + l2), (0.0, 0.0, l0), (5.0, 5.0, 5.0), (0.0, 0.0, 0.0), (-0.7, 0.0, l0 + 0.2),
+           (0.3, -0.9, 0.1), (1.2, 0.4, 1.9)]
+    T = np.tile(np.eye(4), (len(pts), 1, 1))
+    T[:, :3, 3] = pts
+    T = np.tile(T, (8, 1, 1))                          # more than one warp
+    qb, vb = rrr.inverse_kinematics_batch(dev(T), layout=layout)
+    with np.errstate(all="ignore"):
+        for b, (m, k) in enumerate(((1, 1), (1, -1), (-1, 1), (-1, -1))):
+            q_ref, v_ref = O.rrr_ik(T, m, k)
+            assert np.array_equal(vb[:, b].cpu().numpy(), v_ref), (m, k)
+            # the wrist folded onto the shoulder (l1 == l2, arccos argument exactly -1) leaves q1
+            # arbitrary: the reference's value there is atan2(l2 sin(pi), 0) = atan2(1.2e-16, 0)
+            folded = np.linalg.norm(T[:, :3, 3] - np.array([0.0, 0.0, l0]), axis=1) < 1e-6
+            d = np.abs(qb[:, b].cpu().numpy() - q_ref)[~folded]
+            assert np.nanmax(d) < 1e-6, (m, k)                                       # acos at +-1
+    a0, a1 = [float(v) for v in rr._lengths()][:2]
+    pts2 = [(a0 + a1, 0.0), (0.0, a0 + a1), ((a0 + a1) * (1 + 1e-15), 0.0), (a0 + a1 + 1e-9, 0.0),
+            (abs(a0 - a1) + 1e-13, 0.0), (0.0, 0.0), (0.5, -0.3), (-1.1, 0.2), (9.0, 9.0), (1e-9, 1e-9)]
+    T2 = np.tile(np.eye(4), (len(pts2), 1, 1))
+    T2[:, :2, 3] = pts2
+    T2 = np.tile(T2, (8, 1, 1))
+    qb, vb = rr.inverse_kinematics_batch(dev(T2), layout=layout)
+    with np.errstate(all="ignore"):
+        for b, m in enumerate((1, -1)):
+            q_ref, v_ref = O.rr_ik(T2, m, ls=(a0, a1))
+            assert np.array_equal(vb[:, b].cpu().numpy(), v_ref), m
+            folded = np.linalg.norm(T2[:, :2, 3], axis=1) < 1e-6                     # same corner
+            assert np.nanmax(np.abs(qb[:, b].cpu().numpy() - q_ref)[~folded]) < 1e-6, m
