@@ -173,10 +173,10 @@ static int launch_arm_fk(const RkArm* robot, const double* q, int64_t n, int64_t
   ArmP P = make_arm(robot);
   cudaStream_t st = (cudaStream_t)stream;
   if (soa) {
-    int grid = persistent_grid(arm_fk_jac_kernel<NQ, true>, kBlock, 0, n);
+    int grid = stream_grid(arm_fk_jac_kernel<NQ, true>, kBlock, 0, n);
     arm_fk_jac_kernel<NQ, true><<<grid, kBlock, 0, st>>>(P, q, n, ld, T, J);
   } else {
-    int grid = persistent_grid(arm_fk_jac_kernel<NQ, false>, kBlock, 0, n);
+    int grid = stream_grid(arm_fk_jac_kernel<NQ, false>, kBlock, 0, n);
     arm_fk_jac_kernel<NQ, false><<<grid, kBlock, 0, st>>>(P, q, n, ld, T, J);
   }
   return check_launch();
@@ -217,19 +217,19 @@ static int launch_arm_ik(const RkArm* robot, const double* T, int64_t n, int64_t
   }
   if (canonical) {
     if (soa) {
-      int grid = persistent_grid(arm_ik_pose_kernel<NQ, true>, kBlock, 0, n);
+      int grid = stream_grid(arm_ik_pose_kernel<NQ, true>, kBlock, 0, n);
       arm_ik_pose_kernel<NQ, true><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
     } else {
-      int grid = persistent_grid(arm_ik_pose_kernel<NQ, false>, kBlock, 0, n);
+      int grid = stream_grid(arm_ik_pose_kernel<NQ, false>, kBlock, 0, n);
       arm_ik_pose_kernel<NQ, false><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
     }
     return check_launch();
   }
   if (soa) {
-    int grid = persistent_grid(arm_ik_kernel<NQ, true>, kBlock, 0, n * nb);
+    int grid = stream_grid(arm_ik_kernel<NQ, true>, kBlock, 0, n * nb);
     arm_ik_kernel<NQ, true><<<grid, kBlock, 0, st>>>(P, BL, T, n, ld, q_out, valid);
   } else {
-    int grid = persistent_grid(arm_ik_kernel<NQ, false>, kBlock, 0, n * nb);
+    int grid = stream_grid(arm_ik_kernel<NQ, false>, kBlock, 0, n * nb);
     arm_ik_kernel<NQ, false><<<grid, kBlock, 0, st>>>(P, BL, T, n, ld, q_out, valid);
   }
   return check_launch();

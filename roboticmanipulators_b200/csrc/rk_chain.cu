@@ -183,10 +183,10 @@ extern "C" int rk_chain_fk_jac_f64(const RkChain* chain, const double* values, i
   if (J && n_active == 0) J = nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   if (soa) {
-    int grid = rk::persistent_grid(rk::chain_fk_jac_kernel<true>, rk::kBlock, 0, n);
+    int grid = rk::stream_grid(rk::chain_fk_jac_kernel<true>, rk::kBlock, 0, n);
     rk::chain_fk_jac_kernel<true><<<grid, rk::kBlock, 0, st>>>(*chain, values, nvals, n_active, n, ld, T, J);
   } else {
-    int grid = rk::persistent_grid(rk::chain_fk_jac_kernel<false>, rk::kBlock, 0, n);
+    int grid = rk::stream_grid(rk::chain_fk_jac_kernel<false>, rk::kBlock, 0, n);
     rk::chain_fk_jac_kernel<false><<<grid, rk::kBlock, 0, st>>>(*chain, values, nvals, n_active, n, ld, T, J);
   }
   return rk::check_launch();

@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kBlock, 3)
 fanuc_fk_jac_tma_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant__ CUtensorMap tmq,
                         const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUtensorMap tmJ,
                         const __grid_constant__ CUtensorMap tmD, int64_t ntiles, int wantT, int wantJ,
-                        int wantD) {
+                        int wantD, int chunk) {
   using Tile = FkTile<S>;
   constexpr int TP = Tile::kPoses;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -295,14 +295,19 @@ fanuc_fk_jac_tma_kernel(const __grid_constant__ FanucP<S> P, const __grid_consta
     mbar_expect_tx(&sm.bar[buf], 6 * TP * sizeof(S));
     tma_load_2d(&sm.q[buf][0][0], &tmq, (int)(tile * TP), 0, &sm.bar[buf]);
   };
-  int64_t tile = blockIdx.x;
-  if (tid == 0 && tile < ntiles) issue_load(tile, 0);
+  // A CTA owns `chunk` consecutive tiles and the grid has one CTA per chunk: the hardware block
+  // scheduler hands chunks to SMs as they free up, so SMs that get more memory bandwidth process
+  // more poses.  (A persistent grid with a static tile stride left the average SM idle 14 % of the
+  // kernel: ncu sm__cycles_active min / avg / max = 6.7 / 9.4 / 10.9 M cycles; 5.6 -> 5.0 ms.)
+  int64_t tile = (int64_t)blockIdx.x * chunk;
+  const int64_t tend = (tile + chunk < ntiles) ? tile + chunk : ntiles;
+  if (tid == 0 && tile < tend) issue_load(tile, 0);
   TileSink<S> sink{sm, tid};
   int it = 0;
-  for (; tile < ntiles; tile += gridDim.x, ++it) {
+  for (; tile < tend; ++tile, ++it) {
     const int buf = it & 1;
-    const int64_t next = tile + gridDim.x;
-    if (tid == 0 && next < ntiles) issue_load(next, buf ^ 1);
+    const int64_t next = tile + 1;
+    if (tid == 0 && next < tend) issue_load(next, buf ^ 1);
     mbar_wait(&sm.bar[buf], (it >> 1) & 1);
     S qv[6];
 #pragma unroll
@@ -1014,21 +1019,25 @@ static int launch_fk_jac(const RkFanuc* robot, const S* q, int64_t n, int64_t ld
           cudaFuncSetAttribute(fanuc_fk_jac_tma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
           attr_done = true;
         }
-        int grid = persistent_grid(fanuc_fk_jac_tma_kernel<S>, kBlock, smem, ntiles * kBlock);
-        fanuc_fk_jac_tma_kernel<S><<<grid, kBlock, smem, st>>>(P, tmq, tmT, tmJ, tmD, ntiles, T != nullptr,
-                                                               J != nullptr, det != nullptr);
+        // tiles per CTA: 8 (measured 4: 4.86, 8: 4.87, 16: 4.90, 64: 5.03 ms per 2^26) when that
+        // gives at least 4 waves, otherwise one resident wave of equal chunks (see stream_grid)
+        const int64_t cap = persistent_grid(fanuc_fk_jac_tma_kernel<S>, kBlock, smem, ntiles * kBlock);
+        const int chunk = (ntiles / 8 >= 4 * cap) ? 8 : (int)((ntiles + cap - 1) / cap);
+        const int64_t grid = (ntiles + chunk - 1) / chunk;
+        fanuc_fk_jac_tma_kernel<S><<<(unsigned)grid, kBlock, smem, st>>>(P, tmq, tmT, tmJ, tmD, ntiles, T != nullptr,
+                                                                         J != nullptr, det != nullptr, chunk);
       } else {
         n_main = 0;  // unaligned planes: everything through the LSU kernel
       }
     }
     if (n_main < n) {
       const int64_t tail = n - n_main;
-      int grid = persistent_grid(fanuc_fk_jac_soa_kernel<S>, kBlock, 0, tail);
+      int grid = stream_grid(fanuc_fk_jac_soa_kernel<S>, kBlock, 0, tail);
       fanuc_fk_jac_soa_kernel<S><<<grid, kBlock, 0, st>>>(P, q + n_main, tail, ld, T ? T + n_main : nullptr,
                                                           J ? J + n_main : nullptr, det ? det + n_main : nullptr);
     }
   } else {
-    int grid = persistent_grid(fanuc_fk_jac_aos_kernel<S>, kBlock, 0, n);
+    int grid = stream_grid(fanuc_fk_jac_aos_kernel<S>, kBlock, 0, n);
     fanuc_fk_jac_aos_kernel<S><<<grid, kBlock, 0, st>>>(P, q, n, T, J, det);
   }
   return check_launch();
@@ -1067,10 +1076,10 @@ static int launch_ik(const RkFanuc* robot, const S* T, int64_t n, int64_t ld, in
         const int64_t ntiles = (n + TP - 1) / TP;
         const size_t smem = sizeof(IkPoseTile<S>) * (kBlock / kWarp);
         auto kern = P.std_limits ? fanuc_ik8_pose_kernel<S, true> : fanuc_ik8_pose_kernel<S, false>;
-        int grid = persistent_grid(kern, kBlock, smem, ntiles * kWarp);
+        int grid = stream_grid(kern, kBlock, smem, ntiles * kWarp, 16);  // 4: 6.08, 16: 5.95, 32: 6.02 ms
         kern<<<grid, kBlock, smem, st>>>(P, tmT, q_out, valid, n, ld, ntiles);
       } else {
-        int grid = persistent_grid(fanuc_ik8_kernel<S, true, 4>, kBlock, 0, n * 4);
+        int grid = stream_grid(fanuc_ik8_kernel<S, true, 4>, kBlock, 0, n * 4);
         fanuc_ik8_kernel<S, true, 4><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
       }
     } else {
@@ -1088,10 +1097,10 @@ static int launch_ik(const RkFanuc* robot, const S* T, int64_t n, int64_t ld, in
           cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
           attr_done[P.std_limits] = true;
         }
-        int grid = persistent_grid(kern, kBlock, smem, ntiles * kWarp);
+        int grid = stream_grid(kern, kBlock, smem, ntiles * kWarp, 16);
         kern<<<grid, kBlock, smem, st>>>(P, tmT, q_out, valid, n, ntiles);
       } else {
-        int grid = persistent_grid(fanuc_ik8_kernel<S, false, 4>, kBlock, 0, n * 4);
+        int grid = stream_grid(fanuc_ik8_kernel<S, false, 4>, kBlock, 0, n * 4);
         fanuc_ik8_kernel<S, false, 4><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
       }
     }
@@ -1107,10 +1116,10 @@ static int launch_ik(const RkFanuc* robot, const S* T, int64_t n, int64_t ld, in
     BL.mkw[b * 3] = (int8_t)m, BL.mkw[b * 3 + 1] = (int8_t)k, BL.mkw[b * 3 + 2] = (int8_t)w;
   }
   if (soa) {
-    int grid = persistent_grid(fanuc_ik_list_kernel<S, true>, kBlock, 0, n * nb);
+    int grid = stream_grid(fanuc_ik_list_kernel<S, true>, kBlock, 0, n * nb);
     fanuc_ik_list_kernel<S, true><<<grid, kBlock, 0, st>>>(P, BL, T, n, ld, q_out, valid);
   } else {
-    int grid = persistent_grid(fanuc_ik_list_kernel<S, false>, kBlock, 0, n * nb);
+    int grid = stream_grid(fanuc_ik_list_kernel<S, false>, kBlock, 0, n * nb);
     fanuc_ik_list_kernel<S, false><<<grid, kBlock, 0, st>>>(P, BL, T, n, ld, q_out, valid);
   }
   return check_launch();

@@ -324,7 +324,7 @@ static int launch_traj(const ArmP& P, const double* q0, const double* qf, int64_
                        double vmax, double amax, double freq, double* q, double* dq, double* ddq,
                        double* t, int32_t* len, double* o1, double* o2, uint8_t* valid,
                        cudaStream_t st) {
-  int grid = persistent_grid(traj_kernel<NJ, MODE>, kBlock, 0, ntraj * kWarp);
+  int grid = stream_grid(traj_kernel<NJ, MODE>, kBlock, 0, ntraj * kWarp);
   traj_kernel<NJ, MODE><<<grid, kBlock, 0, st>>>(P, q0, qf, ntraj, nsteps, vmax, amax, freq, q, dq,
                                                  ddq, t, len, o1, o2, valid);
   return check_launch();
@@ -360,7 +360,7 @@ int rk_trap_coefficients_f64(const double* q0, const double* qf, int64_t n, doub
   if (n < 0) return RK_ERR_INVALID_ARG;
   if (n == 0) return RK_OK;
   if (!q0 || !qf || !t1 || !tau) return RK_ERR_INVALID_ARG;
-  int grid = rk::persistent_grid(rk::trap_coefficients_kernel, rk::kBlock, 0, n);
+  int grid = rk::stream_grid(rk::trap_coefficients_kernel, rk::kBlock, 0, n);
   rk::trap_coefficients_kernel<<<grid, rk::kBlock, 0, (cudaStream_t)stream>>>(
       q0, qf, n, v_max, a_max, control_freq, t1, tau);
   return rk::check_launch();
@@ -372,7 +372,7 @@ int rk_trap_sample_f64(const double* q_init, const double* v_cur, const double* 
   if (nprof < 0 || nsteps < 1) return RK_ERR_INVALID_ARG;
   if (nprof == 0) return RK_OK;
   if (!q_init || !v_cur || !a_cur || !t1 || !tau || !len) return RK_ERR_INVALID_ARG;
-  int grid = rk::persistent_grid(rk::trap_sample_kernel, rk::kBlock, 0, nprof * rk::kWarp);
+  int grid = rk::stream_grid(rk::trap_sample_kernel, rk::kBlock, 0, nprof * rk::kWarp);
   rk::trap_sample_kernel<<<grid, rk::kBlock, 0, (cudaStream_t)stream>>>(
       q_init, v_cur, a_cur, t1, tau, nprof, nsteps, q, dq, ddq, t, len);
   return rk::check_launch();
@@ -383,7 +383,7 @@ int rk_poly5_f64(const double* b0, const double* bf, const double* t0, const dou
   if (nprof < 0 || nsteps < 1) return RK_ERR_INVALID_ARG;
   if (nprof == 0) return RK_OK;
   if (!b0 || !bf || !t0 || !tf) return RK_ERR_INVALID_ARG;
-  int grid = rk::persistent_grid(rk::poly5_kernel, rk::kBlock, 0, nprof * rk::kWarp);
+  int grid = rk::stream_grid(rk::poly5_kernel, rk::kBlock, 0, nprof * rk::kWarp);
   rk::poly5_kernel<<<grid, rk::kBlock, 0, (cudaStream_t)stream>>>(b0, bf, t0, tf, nprof, nsteps, coef, q,
                                                                     dq, ddq);
   return rk::check_launch();
