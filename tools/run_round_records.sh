@@ -1,0 +1,11 @@
+# Regenerates the bench records and ncu summaries kept under profiles/ (run on a GPU box).
+set -x
+python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
+python bench.py --dtype f32 --no-cpu > gpurun_out/bench_f32.json 2> gpurun_out/bench_f32.err
+python bench.py --layout aos --no-cpu > gpurun_out/bench_aos.json 2> gpurun_out/bench_aos.err
+python bench.py --workload traj > gpurun_out/bench_traj.json 2> gpurun_out/bench_traj.err
+python bench.py --workload calib > gpurun_out/bench_calib.json 2> gpurun_out/bench_calib.err
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:fanuc --csv --log-file gpurun_out/launches_fanuc.csv python bench.py --steps 2 --warmup 3 --batch 8388608 --no-cpu > gpurun_out/ncu1.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:fanuc -s 6 -c 2 -o gpurun_out/prof_fanuc -f python bench.py --steps 2 --warmup 3 --batch 8388608 --no-cpu > gpurun_out/ncu2.log 2>&1
+tail -2 gpurun_out/ncu2.log
