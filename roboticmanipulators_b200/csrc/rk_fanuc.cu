@@ -727,20 +727,17 @@ fanuc_ik8_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict__ T, i
 // moment it exists (a warp store = one contiguous 256-byte run; `st.global.cs`).
 template <typename S>
 struct IkPlaneSink {
-  S* qp;
-  uint8_t* vp;
+  S* qp;        // q_out + pose index
+  uint8_t* vp;  // valid + pose index
   int64_t ld;
-  __device__ __forceinline__ void q(int b, int j, S v) {
-    if (qp) __stcs(qp + (int64_t)(b * 6 + j) * ld, v);
-  }
+  __device__ __forceinline__ void q(int b, int j, S v) { __stcs(qp + (int64_t)(b * 6 + j) * ld, v); }
   __device__ __forceinline__ void branch(int b, bool okf, const S (&u)[6]) {
+    S* p = qp + (int64_t)(b * 6) * ld;  // one 64-bit multiply per branch, then a running pointer
 #pragma unroll
-    for (int j = 0; j < 6; ++j) q(b, j, okf ? u[j] : S(0));
+    for (int j = 0; j < 6; ++j, p += ld) __stcs(p, okf ? u[j] : S(0));
     ok(b, okf);
   }
-  __device__ __forceinline__ void ok(int b, bool f) {
-    if (qp) vp[(int64_t)b * ld] = f ? 1 : 0;
-  }
+  __device__ __forceinline__ void ok(int b, bool f) { vp[(int64_t)b * ld] = f ? 1 : 0; }
   __device__ __forceinline__ void pair_done(int) {}
 };
 
@@ -782,16 +779,18 @@ fanuc_ik8_pose_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant
     // sm.in[buf ^ 1] was consumed by every lane one iteration ago (the __syncwarp below)
     if (lane == 0 && next < ntiles) issue_load(next, buf ^ 1);
     mbar_wait(&sm.bar[buf], (it >> 1) & 1);
+    // every lane runs (fanuc_ik8_pose votes across the warp) and stores without a guard: lanes
+    // past the end of a ragged last tile redo the last pose and write the same values again
+    const int64_t rem = n - tile * TP;
+    const int src = lane < rem ? lane : (int)rem - 1;
     S Tin[12];
 #pragma unroll
-    for (int c = 0; c < 12; ++c) Tin[c] = sm.in[buf][c][lane];
+    for (int c = 0; c < 12; ++c) Tin[c] = sm.in[buf][c][src];
     __syncwarp();
-    // every lane runs (fanuc_ik8_pose votes across the warp); lanes past the end of a ragged last
-    // tile compute on the zeros the TMA load filled in and store nothing
-    const int64_t i = tile * TP + lane;
+    const int64_t i = tile * TP + src;
     S R0[9], p0[3];
     fanuc_ik_t0(P, Tin, R0, p0);
-    IkPlaneSink<S> sink{i < n ? q_out + i : nullptr, valid + i, ld};
+    IkPlaneSink<S> sink{q_out + i, valid + i, ld};
     if (fanuc_ik8_pose<S, STD>(P, R0, p0, sink)) {
       // measure-zero configurations: the branch-by-branch routine with all its special cases
 #pragma unroll 1
