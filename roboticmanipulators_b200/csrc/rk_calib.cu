@@ -189,7 +189,8 @@ __device__ __forceinline__ void chain_end(const CalibP& P, const double (&s)[RK_
 // whole chain and owns joints < split, the residual and the padding; role A walks joints >= split.
 // -------------------------------------------------------------------------------------------
 struct CalibN {
-  double R[6][6];                         // upper triangular (trapezoidal for one tool)
+  double tbar[3];                         // centroid of the tools
+  double R[6][6];                         // block diagonal: R11 diagonal, R22 upper triangular
   double Qt[6][3 * RK_CALIB_MAX_TOOLS];   // first 6 rows of Q^T
   int split;
 };
@@ -199,8 +200,14 @@ struct CalibN {
 static void make_calibn(const CalibP& P, CalibN& N) {
   const int mrows = 3 * P.nt;
   double A[3 * RK_CALIB_MAX_TOOLS][6], Qm[3 * RK_CALIB_MAX_TOOLS][3 * RK_CALIB_MAX_TOOLS];
+  // tools are taken relative to their centroid (the kernel adds the centroid to b'): then the
+  // skew blocks sum to zero and R = diag(R11 (diagonal 3x3), R22 (upper triangular 3x3))
+  for (int k = 0; k < 3; ++k) {
+    N.tbar[k] = 0.0;
+    for (int t = 0; t < P.nt; ++t) N.tbar[k] += P.tool[t][k] / P.nt;
+  }
   for (int t = 0; t < P.nt; ++t) {
-    const double* w = P.tool[t];
+    const double w[3] = {P.tool[t][0] - N.tbar[0], P.tool[t][1] - N.tbar[1], P.tool[t][2] - N.tbar[2]};
     const double K[3][3] = {{0.0, w[2], -w[1]}, {-w[2], 0.0, w[0]}, {w[1], -w[0], 0.0}};  // -[w]x
     for (int r = 0; r < 3; ++r)
       for (int c = 0; c < 3; ++c) {
@@ -238,7 +245,9 @@ static void make_calibn(const CalibP& P, CalibN& N) {
     }
   }
   for (int i = 0; i < 6; ++i) {
-    for (int c = 0; c < 6; ++c) N.R[i][c] = (i < mrows && c >= i) ? A[i][c] : 0.0;
+    // the off-diagonal block and the off-diagonal of R11 vanish analytically (rounding noise only)
+    for (int c = 0; c < 6; ++c)
+      N.R[i][c] = (i < mrows && c >= i && (i < 3 ? c == i : true)) ? A[i][c] : 0.0;
     for (int c = 0; c < 3 * RK_CALIB_MAX_TOOLS; ++c) N.Qt[i][c] = (i < mrows && c < mrows) ? Qm[i][c] : 0.0;
   }
   // role balance (FP64 operation estimates: sincos 45, walk step 55, rotation / translation
@@ -350,37 +359,27 @@ __device__ __forceinline__ double fill_rows6(const CalibP& P, const CalibN& N, b
           const double a2 = S.Q[2] * ax + S.Q[5] * ay + S.Q[8] * az;
           double y[6];
           if (P.pkind[p] == 1) {
+            // b'' = Q^T (s - o) + centroid of the tools
             const double dx = S.s[0] - P.porg[p][0], dy = S.s[1] - P.porg[p][1], dz = S.s[2] - P.porg[p][2];
-            const double b0 = S.Q[0] * dx + S.Q[3] * dy + S.Q[6] * dz;
-            const double b1 = S.Q[1] * dx + S.Q[4] * dy + S.Q[7] * dz;
-            const double b2 = S.Q[2] * dx + S.Q[5] * dy + S.Q[8] * dz;
-            const double z[6] = {a1 * b2 - a2 * b1, a2 * b0 - a0 * b2, a0 * b1 - a1 * b0, a0, a1, a2};
-#pragma unroll
-            for (int r = 0; r < 6; ++r) {
-              double acc = 0.0;
-#pragma unroll
-              for (int k = r; k < 6; ++k) acc = fma(N.R[r][k], z[k], acc);
-              y[r] = acc;
-            }
+            const double b0 = S.Q[0] * dx + S.Q[3] * dy + S.Q[6] * dz + N.tbar[0];
+            const double b1 = S.Q[1] * dx + S.Q[4] * dy + S.Q[7] * dz + N.tbar[1];
+            const double b2 = S.Q[2] * dx + S.Q[5] * dy + S.Q[8] * dz + N.tbar[2];
+            y[0] = N.R[0][0] * (a1 * b2 - a2 * b1);
+            y[1] = N.R[1][1] * (a2 * b0 - a0 * b2);
+            y[2] = N.R[2][2] * (a0 * b1 - a1 * b0);
+            y[3] = N.R[3][3] * a0 + N.R[3][4] * a1 + N.R[3][5] * a2;
+            y[4] = N.R[4][4] * a1 + N.R[4][5] * a2;
+            y[5] = N.R[5][5] * a2;
           } else {
-            const double z[3] = {a0, a1, a2};
-#pragma unroll
-            for (int r = 0; r < 6; ++r) {
-              double acc = 0.0;
-#pragma unroll
-              for (int k = r; k < 3; ++k) acc = fma(N.R[r][k], z[k], acc);
-              y[r] = acc;
-            }
+            y[0] = N.R[0][0] * a0, y[1] = N.R[1][1] * a1, y[2] = N.R[2][2] * a2;
+            y[3] = y[4] = y[5] = 0.0;
           }
 #pragma unroll
           for (int r = 0; r < 6; ++r) rows[r * kRowStep + p] = y[r];
         }
       }
       if (j > jstop || !role_a) {  // S <- Rot_j(q_j) S_j  (role A never needs Rot_split)
-        double qj = qv[0];
-#pragma unroll
-        for (int k = 1; k < RK_CALIB_MAX_JOINTS; ++k) qj = (k == j) ? qv[k] : qj;
-        const double v = __dadd_rn(__dmul_rn(qj, P.jdir[j]), P.joff[j]);  // model_calibration.py:557
+        const double v = __dadd_rn(__dmul_rn(qv[j], P.jdir[j]), P.joff[j]);  // model_calibration.py:557
         double sn = v, cs = 1.0;
         if (P.jkind[j] == 1) fast_sincos(v, &sn, &cs);
         sfx_joint(S, P.jaxis[j], P.jkind[j], sn, cs);
@@ -411,7 +410,10 @@ __device__ __forceinline__ double fill_rows6(const CalibP& P, const CalibN& N, b
 #pragma unroll
     for (int k = 0; k < 3 * RK_CALIB_MAX_TOOLS; ++k) acc = fma(N.Qt[r][k], rho[k], acc);
     rows[r * kRowStep + P.np] = acc;
-    for (int k = ncols; k < wpad; ++k) rows[r * kRowStep + k] = 0.0;
+  }
+  for (int k = ncols; k < wpad; ++k) {
+#pragma unroll
+    for (int r = 0; r < 6; ++r) rows[r * kRowStep + k] = 0.0;
   }
   return rr;
 }

@@ -858,7 +858,9 @@ struct IkAosSink {
     for (int p = lane; p < total; p += kWarp) {
       const int pose = p / kPieces, part = p - pose * kPieces;
       const uint4 v = *reinterpret_cast<const uint4*>(&sm.stage[pose][part * kPer16]);
-      __stcs(reinterpret_cast<uint4*>(qwarp + (int64_t)pose * 48 + goff + part * kPer16), v);
+      // default (write-back) policy: a 128-byte line receives the runs of two different pairs a few
+      // microseconds apart and should stay in L2 until it is complete
+      *reinterpret_cast<uint4*>(qwarp + (int64_t)pose * 48 + goff + part * kPer16) = v;
     }
     __syncwarp();
   }
