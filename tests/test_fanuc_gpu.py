@@ -370,3 +370,23 @@ def test_ik8_special_poses(layout):
     assert ok.sum() > 1000
     assert np.max(np.abs(d[..., :3][ok])) < 1e-9
     assert np.max(np.abs(d[..., 3:][ok])) < 1e-7
+
+
+def test_ik8_masks_large_sample():
+    """3e5 uniformly sampled poses (x 8 branches = 2.4e6 reachability + limit decisions): the
+    validity masks of the thread-per-pose kernel must equal the oracle's exactly."""
+    from roboticmanipulators_b200.robots.fanuc import Fanuc165F
+    c = O.FanucConst()
+    q = rand_q(300000, seed=99)
+    T = O.fanuc_fk(q, c)
+    T[::50, :3, 3] *= 1.6                              # 2 % far targets, some of them unreachable
+    q_ref, v_ref = O.fanuc_ik_branches(T, O.CANONICAL_8, c)
+    Tt = torch.tensor(T, device="cuda")
+    for layout in ("soa", "aos"):
+        qg, vg = Fanuc165F().inverse_kinematics_batch(Tt, layout=layout)
+        vg, qg = vg.cpu().numpy(), qg.cpu().numpy()
+        assert np.array_equal(vg, v_ref), int((vg != v_ref).sum())
+        d = qg - q_ref
+        d[..., [3, 5]] = (d[..., [3, 5]] + np.pi) % (2 * np.pi) - np.pi
+        assert np.nanmax(np.abs(d)) < 1e-8
+        assert np.nanpercentile(np.abs(d), 99.9) < 1e-12
