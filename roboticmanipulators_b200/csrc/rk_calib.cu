@@ -753,13 +753,7 @@ int rk_calib_normal_eq_f64(const RkCalibModel* model, const double* q, const dou
   make_calibn(P, N);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)kMeas * 3 * kRS6 * sizeof(double);
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(calib_normal_eq6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-        cudaSuccess)
-      return check_launch();
-    attr_set = true;
-  }
+  if (!allow_dynamic_smem(calib_normal_eq6_kernel, smem)) return RK_ERR_CUDA;
   int grid = persistent_grid(calib_normal_eq6_kernel, kMeas, smem, m > 0 ? 2 * m : 1);
   if (grid > kMaxGrid) grid = kMaxGrid;
   unsigned int* counter = reinterpret_cast<unsigned int*>((char*)workspace + kWsCounterOffset);

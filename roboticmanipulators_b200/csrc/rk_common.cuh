@@ -23,6 +23,18 @@ inline int check_launch() {
   return RK_OK;
 }
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory.  Called before every such launch:
+// the attribute is per device and per context, the call costs about a microsecond, and a cached
+// "already done" flag would be wrong as soon as one host thread drives two GPUs.
+template <typename K>
+inline bool allow_dynamic_smem(K kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return true;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess)
+    return true;
+  g_last_cuda = cudaGetLastError();
+  return false;
+}
+
 // Grid for a kernel that must stay resident for the whole problem (per-CTA accumulators that are
 // reduced at the end): enough CTAs to fill every SM at the kernel's occupancy, never more than
 // the work needs ("a multiple of 148 x resident CTAs per SM").

@@ -1015,11 +1015,7 @@ static int launch_fk_jac(const RkFanuc* robot, const S* q, int64_t n, int64_t ld
       if (tma_ok) {
         const int64_t ntiles = n_main / TP;
         const size_t smem = sizeof(FkTile<S>);
-        static thread_local bool attr_done = false;
-        if (!attr_done) {
-          cudaFuncSetAttribute(fanuc_fk_jac_tma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          attr_done = true;
-        }
+        if (!allow_dynamic_smem(fanuc_fk_jac_tma_kernel<S>, smem)) return RK_ERR_CUDA;
         // tiles per CTA: 8 (measured 4: 4.86, 8: 4.87, 16: 4.90, 64: 5.03 ms per 2^26) when that
         // gives at least 4 waves, otherwise one resident wave of equal chunks (see stream_grid)
         const int64_t cap = persistent_grid(fanuc_fk_jac_tma_kernel<S>, kBlock, smem, ntiles * kBlock);
@@ -1093,11 +1089,7 @@ static int launch_ik(const RkFanuc* robot, const S* T, int64_t n, int64_t ld, in
         const int64_t ntiles = (n + TP - 1) / TP;
         const size_t smem = sizeof(IkPoseTileAos<S>) * (kBlock / kWarp) + 1024;
         auto kern = P.std_limits ? fanuc_ik8_pose_aos_kernel<S, true> : fanuc_ik8_pose_aos_kernel<S, false>;
-        static thread_local bool attr_done[2] = {false, false};
-        if (!attr_done[P.std_limits]) {
-          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          attr_done[P.std_limits] = true;
-        }
+        if (!allow_dynamic_smem(kern, smem)) return RK_ERR_CUDA;
         int grid = stream_grid(kern, kBlock, smem, ntiles * kWarp, 16);
         kern<<<grid, kBlock, smem, st>>>(P, tmT, q_out, valid, n, ntiles);
       } else {
