@@ -843,24 +843,38 @@ struct IkAosSink {
   int lane, cnt;  // cnt = live poses of this tile
   unsigned long long okbits;
   static constexpr int kPer16 = 16 / sizeof(S);         // elements per 16-byte piece
-  static constexpr int kPieces = Tile::kRun / kPer16;   // pieces per staged run
+  static constexpr int kPieces = Tile::kRun / kPer16;   // pieces per staged run (6 for FP64, 12 for FP32)
   __device__ __forceinline__ void branch(int b, bool okf, const S (&u)[6]) {
     const int col = Tile::kFull ? b * 6 : (b & 1) * 6;
 #pragma unroll
     for (int j = 0; j < 6; ++j) sm.stage[lane][col + j] = okf ? u[j] : S(0);
     okbits |= (unsigned long long)(okf ? 1 : 0) << (8 * b);
   }
+  // Copy-out: the staged runs are walked in 16-byte pieces, piece p = it * 32 + lane of run
+  // p / kPieces, so one store instruction writes 512 contiguous staged bytes = whole runs.  (run,
+  // piece-in-run) advance by fixed steps per iteration: the loop carries two byte offsets instead of
+  // dividing.
   __device__ __forceinline__ void pair_done(int b0) {
     if (Tile::kFull && b0 != 6) return;  // (m, k) = (-1, -1) is the last pair of a pose
     __syncwarp();
-    const int total = cnt * kPieces;
-    const int goff = Tile::kFull ? 0 : b0 * 6;
-    for (int p = lane; p < total; p += kWarp) {
-      const int pose = p / kPieces, part = p - pose * kPieces;
-      const uint4 v = *reinterpret_cast<const uint4*>(&sm.stage[pose][part * kPer16]);
+    constexpr int kRowB = Tile::kStage * (int)sizeof(S);   // staging row pitch in bytes
+    constexpr int kPoseB = 48 * (int)sizeof(S);            // pose pitch in q_out
+    constexpr int kStepRun = kWarp / kPieces, kStepPart = kWarp % kPieces;
+    int run = lane / kPieces, part = lane - run * kPieces;
+    const unsigned char* sp = reinterpret_cast<const unsigned char*>(&sm.stage[0][0]) + run * kRowB + part * 16;
+    unsigned char* gp = reinterpret_cast<unsigned char*>(qwarp + (Tile::kFull ? 0 : b0 * 6)) +
+                        (int64_t)run * kPoseB + part * 16;
+#pragma unroll
+    for (int it = 0; it < kPieces; ++it) {
       // default (write-back) policy: a 128-byte line receives the runs of two different pairs a few
       // microseconds apart and should stay in L2 until it is complete
-      *reinterpret_cast<uint4*>(qwarp + (int64_t)pose * 48 + goff + part * kPer16) = v;
+      if (run < cnt) *reinterpret_cast<uint4*>(gp) = *reinterpret_cast<const uint4*>(sp);
+      run += kStepRun, part += kStepPart;
+      sp += kStepRun * kRowB + kStepPart * 16, gp += kStepRun * kPoseB + kStepPart * 16;
+      if (part >= kPieces) {
+        part -= kPieces, run += 1;
+        sp += kRowB - kPieces * 16, gp += kPoseB - kPieces * 16;
+      }
     }
     __syncwarp();
   }
