@@ -27,7 +27,7 @@ ArmP make_arm_params(const RkArm* r) { return make_arm(r); }
 
 // One thread per pose; AOS goes through the warp-private staging tile.
 template <int NQ, bool SOA>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 4)
 arm_fk_jac_kernel(const __grid_constant__ ArmP P, const double* __restrict__ q, int64_t n,
                   int64_t ld, double* __restrict__ T, double* __restrict__ J) {
   constexpr int NJ = 6 * NQ;
@@ -43,7 +43,7 @@ arm_fk_jac_kernel(const __grid_constant__ ArmP P, const double* __restrict__ q, 
     double* stage = stage_all + (SOA ? 0 : warp * kWarp * NST);
     if (SOA) {
 #pragma unroll
-      for (int k = 0; k < NQ; ++k) qv[k] = (lane < cnt) ? q[k * ld + i] : 0.0;
+      for (int k = 0; k < NQ; ++k) qv[k] = (lane < cnt) ? __ldcs(q + k * ld + i) : 0.0;
     } else {
       warp_load_aos<double, NQ>(stage, qv, q + base * NQ, cnt, lane);
       if (lane >= cnt) {
@@ -59,11 +59,11 @@ arm_fk_jac_kernel(const __grid_constant__ ArmP P, const double* __restrict__ q, 
       if (lane < cnt) {
         if (T) {
 #pragma unroll
-          for (int k = 0; k < 16; ++k) T[k * ld + i] = Tv[k];
+          for (int k = 0; k < 16; ++k) __stcs(T + k * ld + i, Tv[k]);
         }
         if (J) {
 #pragma unroll
-          for (int k = 0; k < NJ; ++k) J[k * ld + i] = Jv[k];
+          for (int k = 0; k < NJ; ++k) __stcs(J + k * ld + i, Jv[k]);
         }
       }
     } else {
