@@ -251,7 +251,10 @@ fanuc_fk_jac_soa_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict
 // instead of through 53 LSU store instructions per thread (ncu: lg_throttle + long_scoreboard).
 template <typename S>
 struct FkTile {
-  static constexpr int kPoses = kBlock;
+  // 1 KB rows in both precisions: FP32 threads own two poses of a tile (half the barriers and TMA
+  // instructions per pose, two independent chains per thread)
+  static constexpr int kPerThread = sizeof(S) == 4 ? 2 : 1;
+  static constexpr int kPoses = kBlock * kPerThread;
   S q[2][6][kPoses];
   S T[16][kPoses];
   S J[36][kPoses];
@@ -264,14 +267,18 @@ struct FkTile {
 template <typename S>
 struct TileSink {
   FkTile<S>& sm;
-  int tid;
+  int tid;     // thread index (elects the waiter)
+  int col;     // pose within the tile
+  bool first;  // first pose of the trip: wait for the previous trip's stores
   __device__ __forceinline__ void det(S v) {
-    if (tid == 0) bulk_wait_read0();
-    __syncthreads();
-    sm.det[tid] = v;
+    if (first) {
+      if (tid == 0) bulk_wait_read0();
+      __syncthreads();
+    }
+    sm.det[col] = v;
   }
-  __device__ __forceinline__ void T(int k, S v) { sm.T[k][tid] = v; }
-  __device__ __forceinline__ void J(int k, S v) { sm.J[k][tid] = v; }
+  __device__ __forceinline__ void T(int k, S v) { sm.T[k][col] = v; }
+  __device__ __forceinline__ void J(int k, S v) { sm.J[k][col] = v; }
 };
 
 template <typename S>
@@ -302,17 +309,21 @@ fanuc_fk_jac_tma_kernel(const __grid_constant__ FanucP<S> P, const __grid_consta
   int64_t tile = (int64_t)blockIdx.x * chunk;
   const int64_t tend = (tile + chunk < ntiles) ? tile + chunk : ntiles;
   if (tid == 0 && tile < tend) issue_load(tile, 0);
-  TileSink<S> sink{sm, tid};
   int it = 0;
   for (; tile < tend; ++tile, ++it) {
     const int buf = it & 1;
     const int64_t next = tile + 1;
     if (tid == 0 && next < tend) issue_load(next, buf ^ 1);
     mbar_wait(&sm.bar[buf], (it >> 1) & 1);
-    S qv[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) qv[k] = sm.q[buf][k][tid];
-    fanuc_fk_jac_emit(P, qv, sink);
+    for (int h = 0; h < Tile::kPerThread; ++h) {
+      const int col = tid + h * kBlock;
+      S qv[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) qv[k] = sm.q[buf][k][col];
+      TileSink<S> sink{sm, tid, col, h == 0};
+      fanuc_fk_jac_emit(P, qv, sink);
+    }
     fence_async_smem();
     __syncthreads();  // tile complete; also everyone is done with sm.q[buf]
     if (tid == 0) {
