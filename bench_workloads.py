@@ -25,7 +25,7 @@ def ncu_traffic_per_unit():
                 if "traffic_bytes_per_unit" not in rec:
                     continue
                 for key, pat in (("fanuc_fk_jac", "fanuc_fk_jac"), ("fanuc_ik8", "fanuc_ik8"),
-                                 ("calib_normal_eq", "calib_accumulate"), ("rrr_p2p_fk", "traj_kernel")):
+                                 ("calib_normal_eq", "calib_normal_eq"), ("rrr_p2p_fk", "traj_kernel")):
                     if pat in rec["kernel"]:
                         out[key] = rec["traffic_bytes_per_unit"]
         except (OSError, ValueError):

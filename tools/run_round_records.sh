@@ -10,6 +10,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k regex:fanuc --csv -
 ncu --set full --clock-control none --import-source on -k regex:fanuc -s 6 -c 2 -o gpurun_out/prof_fanuc -f python bench.py --steps 2 --warmup 3 --batch 8388608 --no-cpu > gpurun_out/ncu2.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:calib_normal -s 3 -c 1 -o gpurun_out/prof_calib -f python bench.py --steps 2 --warmup 3 --batch 8388608 --no-cpu --workload calib > gpurun_out/ncu3.log 2>&1
 python tools/bench_rows.py > gpurun_out/rows.json 2> gpurun_out/rows.err
-tail -2 gpurun_out/ncu2.log gpurun_out/ncu3.log
+tail -n 2 gpurun_out/ncu2.log; tail -n 2 gpurun_out/ncu3.log
 # then, in the repo: python tools/ncu_summary.py gpurun_out/prof_fanuc.ncu-rep 8388608 > profiles/rNN_fanuc_ncu_full_summary.json
 #                    python tools/ncu_summary.py gpurun_out/prof_calib.ncu-rep 8388608 > profiles/rNN_calib_ncu_full_summary.json
