@@ -969,42 +969,96 @@ fanuc_ik8_pose_aos_kernel(const __grid_constant__ FanucP<S> P, const __grid_cons
   }
 }
 
-// Arbitrary branch list: one thread per (pose, branch).
+// Arbitrary branch list: one thread per pose.  The host groups the requested branches by (m, k);
+// a group's position and wrist solve is done once (fanuc_ik_mk) for the wrist flags it needs --
+// NW = 1: every group asks for a single w (e.g. one branch per pose); NW = 3: w = 0, 1, -1 are all
+// evaluated and each requested branch picks its own.  Every store is a coalesced plane access in
+// SOA (the earlier thread-per-(pose, branch) mapping scattered 8-byte pieces over nb planes:
+// 12.4 ms per 2^24 poses for the reference's 12-branch list, now ~2 ms).
 struct BranchList {
-  int8_t mkw[3 * 16];
-  int nb;
+  int nb, ngroups;
+  int8_t gm[4], gk[4];   // distinct (m, k) pairs in order of first appearance
+  int8_t gw[4];          // NW = 1: the group's single w
+  int8_t grp[16];        // group of branch b
+  int8_t wi[16];         // NW = 3: index of branch b's w in {0, 1, -1}; NW = 1: 0
 };
 
-template <typename S, bool SOA>
+template <typename S, bool SOA, int NW>
 __global__ void __launch_bounds__(kBlock)
 fanuc_ik_list_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant__ BranchList BL,
                      const S* __restrict__ T, int64_t n, int64_t ld, S* __restrict__ q_out,
                      uint8_t* __restrict__ valid) {
   const int nb = BL.nb;
-  const int64_t total = n * nb;
+  // AOS ([n][nb][6]): a warp's 32 poses are one contiguous run of 32 * nb * 6 values; the lanes stage
+  // their rows in shared memory (odd row stride) and the warp copies the run out linearly
+  extern __shared__ __align__(16) unsigned char stage_raw[];
+  const int lane = threadIdx.x & 31;
+  const int row = nb * 6 + 1;
+  S* stage = reinterpret_cast<S*>(stage_raw) + (size_t)(threadIdx.x >> 5) * kWarp * row;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t tix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tix < total; tix += stride) {
-    const int64_t i = tix / nb;
-    const int b = (int)(tix - i * nb);
+  const int64_t nround = (n + kWarp - 1) / kWarp * kWarp;  // whole warps stay in the loop (AOS copy-out)
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nround; i0 += stride) {
+    const int64_t i = i0 < n ? i0 : n - 1;  // lanes past the end redo the last pose
     S Tin[12];
     load_T12<S, SOA>(T, i, ld, Tin);
     S R0[9], p0[3];
     fanuc_ik_t0(P, Tin, R0, p0);
-    const int wl[1] = {BL.mkw[b * 3 + 2]};
-    S qo[1][6];
-    bool ok[1];
-    fanuc_ik_mk<S, 1, false>(P, R0, p0, BL.mkw[b * 3 + 0], BL.mkw[b * 3 + 1], wl, qo, ok);
+#pragma unroll 1
+    for (int g = 0; g < BL.ngroups; ++g) {
+      int wl[NW];
+      if (NW == 1) {
+        wl[0] = BL.gw[g];
+      } else {
+        wl[0] = 0, wl[NW > 1 ? 1 : 0] = 1, wl[NW > 2 ? 2 : 0] = -1;
+      }
+      S qo[NW][6];
+      bool ok[NW];
+      fanuc_ik_mk<S, NW, false>(P, R0, p0, BL.gm[g], BL.gk[g], wl, qo, ok);
+#pragma unroll 1
+      for (int b = 0; b < nb; ++b) {
+        if (BL.grp[b] != g) continue;
+        const int w = BL.wi[b];
+        bool okb = ok[0];
+        S v[6];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      if (SOA)
-        q_out[(int64_t)(b * 6 + j) * ld + i] = qo[0][j];
-      else
-        q_out[(i * nb + b) * 6 + j] = qo[0][j];
+        for (int j = 0; j < 6; ++j) v[j] = qo[0][j];
+        if (NW > 1) {
+          if (w == 1) okb = ok[NW > 1 ? 1 : 0];
+          if (w == 2) okb = ok[NW > 2 ? 2 : 0];
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            if (w == 1) v[j] = qo[NW > 1 ? 1 : 0][j];
+            if (w == 2) v[j] = qo[NW > 2 ? 2 : 0][j];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          if (SOA)
+            __stcs(q_out + (int64_t)(b * 6 + j) * ld + i, v[j]);
+          else
+            stage[lane * row + b * 6 + j] = v[j];
+        }
+        if (SOA)
+          valid[(int64_t)b * ld + i] = okb ? 1 : 0;
+        else if (i0 < n)
+          valid[i * nb + b] = okb ? 1 : 0;
+      }
     }
-    if (SOA)
-      valid[(int64_t)b * ld + i] = ok[0] ? 1 : 0;
-    else
-      valid[i * nb + b] = ok[0] ? 1 : 0;
+    if (!SOA) {
+      __syncwarp();
+      const int64_t base = i0 - lane;                       // first pose of this warp pass
+      const int64_t rem = n - base;
+      const int total = (int)(rem < kWarp ? rem : kWarp) * (row - 1);
+      S* g = q_out + base * (row - 1);
+      int item = 0, c = lane;                                // element (item, c) = staged row, column
+      while (c >= row - 1) c -= row - 1, ++item;
+      for (int idx = lane; idx < total; idx += kWarp) {
+        g[idx] = stage[item * row + c];
+        c += kWarp;
+        while (c >= row - 1) c -= row - 1, ++item;
+      }
+      __syncwarp();
+    }
   }
 }
 
@@ -1124,21 +1178,43 @@ static int launch_ik(const RkFanuc* robot, const S* T, int64_t n, int64_t ld, in
     }
     return check_launch();
   }
-  BranchList BL;
+  BranchList BL = {};
   BL.nb = nb;
+  bool single_w = true;
+  int per_group[4] = {0, 0, 0, 0};
   for (int b = 0; b < nb; ++b) {
     int m = branches[b * 3], k = branches[b * 3 + 1], w = branches[b * 3 + 2];
     if (m != 1 && m != -1) m = 1;               // fanuc.py:210-212
     if (k != 1 && k != -1) k = 1;               // :214-216
     if (w != 1 && w != -1 && w != 0) w = 1;     // :218-220
-    BL.mkw[b * 3] = (int8_t)m, BL.mkw[b * 3 + 1] = (int8_t)k, BL.mkw[b * 3 + 2] = (int8_t)w;
+    int g = 0;
+    while (g < BL.ngroups && (BL.gm[g] != m || BL.gk[g] != k)) ++g;
+    if (g == BL.ngroups) {
+      BL.gm[g] = (int8_t)m, BL.gk[g] = (int8_t)k, BL.gw[g] = (int8_t)w;
+      ++BL.ngroups;
+    }
+    BL.grp[b] = (int8_t)g;
+    BL.wi[b] = (int8_t)(w == 0 ? 0 : (w == 1 ? 1 : 2));
+    if (++per_group[g] > 1 && w != BL.gw[g]) single_w = false;
   }
-  if (soa) {
-    int grid = stream_grid(fanuc_ik_list_kernel<S, true>, kBlock, 0, n * nb);
-    fanuc_ik_list_kernel<S, true><<<grid, kBlock, 0, st>>>(P, BL, T, n, ld, q_out, valid);
+  const size_t aos_smem = (size_t)kBlock * (nb * 6 + 1) * sizeof(S);  // AOS staging rows
+  if (single_w) {
+    for (int b = 0; b < nb; ++b) BL.wi[b] = 0;
+    if (soa) {
+      int grid = stream_grid(fanuc_ik_list_kernel<S, true, 1>, kBlock, 0, n);
+      fanuc_ik_list_kernel<S, true, 1><<<grid, kBlock, 0, st>>>(P, BL, T, n, ld, q_out, valid);
+    } else {
+      if (!allow_dynamic_smem(fanuc_ik_list_kernel<S, false, 1>, aos_smem)) return RK_ERR_CUDA;
+      int grid = stream_grid(fanuc_ik_list_kernel<S, false, 1>, kBlock, aos_smem, n);
+      fanuc_ik_list_kernel<S, false, 1><<<grid, kBlock, aos_smem, st>>>(P, BL, T, n, ld, q_out, valid);
+    }
+  } else if (soa) {
+    int grid = stream_grid(fanuc_ik_list_kernel<S, true, 3>, kBlock, 0, n);
+    fanuc_ik_list_kernel<S, true, 3><<<grid, kBlock, 0, st>>>(P, BL, T, n, ld, q_out, valid);
   } else {
-    int grid = stream_grid(fanuc_ik_list_kernel<S, false>, kBlock, 0, n * nb);
-    fanuc_ik_list_kernel<S, false><<<grid, kBlock, 0, st>>>(P, BL, T, n, ld, q_out, valid);
+    if (!allow_dynamic_smem(fanuc_ik_list_kernel<S, false, 3>, aos_smem)) return RK_ERR_CUDA;
+    int grid = stream_grid(fanuc_ik_list_kernel<S, false, 3>, kBlock, aos_smem, n);
+    fanuc_ik_list_kernel<S, false, 3><<<grid, kBlock, aos_smem, st>>>(P, BL, T, n, ld, q_out, valid);
   }
   return check_launch();
 }
