@@ -841,9 +841,11 @@ struct alignas(1024) IkPoseTileAos {
   // staging row stride (elements): rows stay 16-byte aligned and 8 consecutive rows start in 8
   // different 16-byte bank groups (112 B for FP64, 208 B for FP32)
   static constexpr int kStage = kFull ? 52 : 14;
-  S in[2][kPoses][16];
+  // one input buffer: a lane copies its row to registers as soon as the tile has landed, so the
+  // next tile's TMA load can be issued into the same buffer right away
+  S in[1][kPoses][16];
   S stage[kPoses][kStage];
-  uint64_t bar[2];
+  uint64_t bar[1];
 };
 
 template <typename S>
@@ -907,26 +909,23 @@ fanuc_ik8_pose_aos_kernel(const __grid_constant__ FanucP<S> P, const __grid_cons
   Tile& sm = reinterpret_cast<Tile*>(smem_al)[warp];
   if (lane == 0) {
     mbar_init(&sm.bar[0], 1);
-    mbar_init(&sm.bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  auto issue_load = [&](int64_t tile, int buf) {  // one lane
-    mbar_expect_tx(&sm.bar[buf], 16 * TP * sizeof(S));
-    tma_load_2d(&sm.in[buf][0][0], &tmT, 0, (int)(tile * TP), &sm.bar[buf]);
+  auto issue_load = [&](int64_t tile) {  // one lane
+    mbar_expect_tx(&sm.bar[0], 16 * TP * sizeof(S));
+    tma_load_2d(&sm.in[0][0][0], &tmT, 0, (int)(tile * TP), &sm.bar[0]);
   };
   const int64_t stride = (int64_t)gridDim.x * WPB;
   int64_t tile = (int64_t)blockIdx.x * WPB + warp;
-  if (lane == 0 && tile < ntiles) issue_load(tile, 0);
+  if (lane == 0 && tile < ntiles) issue_load(tile);
   int it = 0;
   for (; tile < ntiles; tile += stride, ++it) {
-    const int buf = it & 1;
     const int64_t next = tile + stride;
-    if (lane == 0 && next < ntiles) issue_load(next, buf ^ 1);
-    mbar_wait(&sm.bar[buf], (it >> 1) & 1);
+    mbar_wait(&sm.bar[0], it & 1);
     // lane L owns row L; 16-byte piece c of the row sits at piece c ^ (swizzle bits of the address)
     S Tin[12];
-    const unsigned char* rowp = reinterpret_cast<const unsigned char*>(&sm.in[buf][lane][0]);
+    const unsigned char* rowp = reinterpret_cast<const unsigned char*>(&sm.in[0][lane][0]);
     const unsigned rowoff = (unsigned)(lane * 16 * sizeof(S));
 #pragma unroll
     for (int c = 0; c < 12 / kPer16; ++c) {
@@ -938,6 +937,7 @@ fanuc_ik8_pose_aos_kernel(const __grid_constant__ FanucP<S> P, const __grid_cons
       for (int e = 0; e < kPer16; ++e) Tin[c * kPer16 + e] = tmp[e];
     }
     __syncwarp();
+    if (lane == 0 && next < ntiles) issue_load(next);  // the buffer is free again
     // every lane runs (fanuc_ik8_pose votes across the warp); rows past the end were zero-filled
     const int64_t base = tile * TP;
     const int64_t i = base + lane;
