@@ -755,8 +755,10 @@ struct IkPlaneSink {
 template <typename S>
 struct alignas(128) IkPoseTile {
   static constexpr int kPoses = kWarp;
-  S in[2][12][kPoses];
-  uint64_t bar[2];
+  // one buffer: a lane copies its 12 inputs to registers as soon as the tile has landed, so the
+  // next tile's TMA load is issued into the same buffer right away
+  S in[12][kPoses];
+  uint64_t bar;
 };
 
 template <typename S, bool STD>
@@ -771,33 +773,30 @@ fanuc_ik8_pose_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant
   const int lane = threadIdx.x & 31, warp = uniform_warp_idx();
   Tile& sm = reinterpret_cast<Tile*>(smem_raw)[warp];
   if (lane == 0) {
-    mbar_init(&sm.bar[0], 1);
-    mbar_init(&sm.bar[1], 1);
+    mbar_init(&sm.bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  auto issue_load = [&](int64_t tile, int buf) {  // one lane
-    mbar_expect_tx(&sm.bar[buf], 12 * TP * sizeof(S));
-    tma_load_2d(&sm.in[buf][0][0], &tmT, (int)(tile * TP), 0, &sm.bar[buf]);
+  auto issue_load = [&](int64_t tile) {  // one lane
+    mbar_expect_tx(&sm.bar, 12 * TP * sizeof(S));
+    tma_load_2d(&sm.in[0][0], &tmT, (int)(tile * TP), 0, &sm.bar);
   };
   const int64_t stride = (int64_t)gridDim.x * WPB;
   int64_t tile = (int64_t)blockIdx.x * WPB + warp;
-  if (lane == 0 && tile < ntiles) issue_load(tile, 0);
+  if (lane == 0 && tile < ntiles) issue_load(tile);
   int it = 0;
   for (; tile < ntiles; tile += stride, ++it) {
-    const int buf = it & 1;
     const int64_t next = tile + stride;
-    // sm.in[buf ^ 1] was consumed by every lane one iteration ago (the __syncwarp below)
-    if (lane == 0 && next < ntiles) issue_load(next, buf ^ 1);
-    mbar_wait(&sm.bar[buf], (it >> 1) & 1);
+    mbar_wait(&sm.bar, it & 1);
     // every lane runs (fanuc_ik8_pose votes across the warp) and stores without a guard: lanes
     // past the end of a ragged last tile redo the last pose and write the same values again
     const int64_t rem = n - tile * TP;
     const int src = lane < rem ? lane : (int)rem - 1;
     S Tin[12];
 #pragma unroll
-    for (int c = 0; c < 12; ++c) Tin[c] = sm.in[buf][c][src];
+    for (int c = 0; c < 12; ++c) Tin[c] = sm.in[c][src];
     __syncwarp();
+    if (lane == 0 && next < ntiles) issue_load(next);  // the buffer is free again
     const int64_t i = tile * TP + src;
     S R0[9], p0[3];
     fanuc_ik_t0(P, Tin, R0, p0);
