@@ -733,9 +733,11 @@ fanuc_ik8_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict__ T, i
 // fanuc_ik8_pose (about half the instructions per pose of the 4-lanes-per-pose mapping, which
 // replicates the pose- and k-level work and spends ~200 instructions per lane on uniform-register
 // spills and lane pairing).  Every warp runs its own pipeline over 32-pose tiles: the tile's 12
-// input planes arrive by one 2-D TMA load ([12][32] box, double buffered, issued one tile ahead,
-// per-warp mbarriers -- no CTA barrier anywhere); each result is stored to its SOA plane the
-// moment it exists (a warp store = one contiguous 256-byte run; `st.global.cs`).
+// input planes arrive by one 2-D TMA load ([12][32] box; the next tile's load is issued as soon as
+// the lanes hold the current inputs in registers; per-warp mbarrier -- no CTA barrier anywhere);
+// each result is stored to its SOA plane the moment it exists (a warp store = one contiguous
+// 256-byte run; `st.global.cs`), without a guard: lanes past the end of a ragged tile redo the
+// last pose.
 template <typename S>
 struct IkPlaneSink {
   S* qp;        // q_out + pose index
