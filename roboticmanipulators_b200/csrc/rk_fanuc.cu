@@ -406,13 +406,12 @@ __device__ __forceinline__ void fanuc_ik_t0(const FanucP<S>& P, const S (&Tin)[1
 // sin(psi) = -m sqrt(1 - psi_cos^2), cos(gamma) = x'/|(x',z')|, ...; acos(c) is
 // atan2(sqrt((1-c)(1+c)), c); and r13 / cos(q5) is +-hypot(r12, r13), which makes
 // q4(w=+-1) = -q4(w=0).  That leaves 4 atan2 that depend only on (pose, k) -- acos(c),
-// beta, gamma, q0 -- and 3 per (m,k) -- the wrist.  With PAIRED the two lanes of a pose
-// that share k (m = +1 / -1) compute two of the four shared atan2 each and swap them with
-// one warp shuffle, so a lane evaluates 5 atan2 in total and nothing else transcendental.
+// beta, gamma, q0 -- and 3 per (m,k) -- the wrist (fanuc_ik8_pose shares them across the
+// branches of a pose; this routine, the general one with every special case, does not).
 // Differences to the reference's literal evaluation are rounding-level (<= 1e-15), except
 // within 1e-11 of the measure-zero corners where the reference itself divides by
 // cos(a5 - pi) ~ 1e-5.
-template <typename S, int NW, bool PAIRED>
+template <typename S, int NW>
 __device__ __forceinline__ void fanuc_ik_mk(const FanucP<S>& P, const S (&R0)[9], const S (&p0)[3],
                                             int m, int k, const int (&wl)[NW], S (&qout)[NW][6],
                                             bool (&valid)[NW]) {
@@ -435,23 +434,10 @@ __device__ __forceinline__ void fanuc_ik_mk(const FanucP<S>& P, const S (&R0)[9]
 
   const S sabs = M::sqrt_fast((S(1) - c) * (S(1) + c));  // sin(acos c) >= 0
   const S sb = -d * sabs, cb = l3 + d * c;          // beta = atan2(d sin(m psi), l3 + d cos psi)
-  S acosc, beta, gamma, q0;
-  if (PAIRED) {
-    const bool first = (m == 1);
-    const S r1 = M::atan2_fast(first ? sabs : zp, first ? c : xp);
-    const S r2 = M::atan2_fast(first ? sb : y, first ? cb : x);
-    const S o1 = __shfl_xor_sync(0xffffffffu, r1, 2);
-    const S o2 = __shfl_xor_sync(0xffffffffu, r2, 2);
-    acosc = first ? r1 : o1;
-    beta = first ? r2 : o2;
-    gamma = first ? o1 : r1;
-    q0 = first ? o2 : r2;
-  } else {
-    acosc = M::atan2_fast(sabs, c);   // :241  acos(psi_cos)
-    beta = M::atan2_fast(sb, cb);     // :242-243
-    gamma = M::atan2_fast(zp, xp);    // :244
-    q0 = M::atan2_fast(y, x);         // :246
-  }
+  const S acosc = M::atan2_fast(sabs, c);   // :241  acos(psi_cos)
+  const S beta = M::atan2_fast(sb, cb);     // :242-243
+  const S gamma = M::atan2_fast(zp, xp);    // :244
+  S q0 = M::atan2_fast(y, x);               // :246
   const S psi = -fm * acosc;                      // :241
   const S q1 = M::sub(gamma, M::mul(fm, beta));   // :247
   const S q2 = M::add(psi, P.dq);                 // :248
@@ -518,8 +504,7 @@ __device__ __forceinline__ void fanuc_ik_mk(const FanucP<S>& P, const S (&R0)[9]
 
 // All 8 canonical branches of ONE pose in ONE thread (the SOA fast path of K2).  What depends
 // only on the pose (q0, the Rz(-q0) R0 rows) is computed once, what depends only on k (acos,
-// beta, gamma and their unit vectors) twice, the wrist four times -- the 4-lanes-per-pose mapping
-// of fanuc_ik8_kernel replicates the first two.  m and k act as sign-bit flips.  The code has no
+// beta, gamma and their unit vectors) twice, the wrist four times.  m and k act as sign-bit flips.  The code has no
 // data-dependent branch: the wrist-singular case (:272, 0.15 % of uniformly sampled poses) is a
 // warp-voted select, and the measure-zero special cases of fanuc_ik_mk (arm on the axis :253-255,
 // |r13| <= eps :279-282, degenerate lengths, operands outside fast_atan2_core's domain) only
@@ -659,79 +644,9 @@ __device__ __forceinline__ void load_T12(const S* __restrict__ T, int64_t i, int
   }
 }
 
-// Canonical 8 branches: 4 lanes per pose, lane = (pose, (m,k)); each lane emits w = 0, 1.
-// Branch index b = 4*[m==-1] + 2*[k==-1] + w.  Validity bits of the 4 lanes of a pose
-// are gathered with warp shuffles so one lane writes the pose's 8 validity bytes.
-template <typename S, bool SOA, int MINB>
-__global__ void __launch_bounds__(kBlock, MINB)
-fanuc_ik8_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict__ T, int64_t n, int64_t ld,
-                 S* __restrict__ q_out, uint8_t* __restrict__ valid) {
-  constexpr int PPW = kWarp / 4;  // poses per warp
-  __shared__ S stage_all[SOA ? 1 : (kBlock / kWarp) * kWarp * Stride<12>::value];
-  const int lane = threadIdx.x & 31, warp_in_blk = threadIdx.x >> 5;
-  const int mk = lane & 3, pl = lane >> 2;
-  const int m = (mk & 2) ? -1 : 1, k = (mk & 1) ? -1 : 1;
-  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t warp_id = (((int64_t)blockIdx.x * blockDim.x) >> 5) + warp_in_blk;
-  for (int64_t base = warp_id * PPW; base < n; base += warps * PPW) {
-    const int64_t i = base + pl;
-    const bool live = i < n;
-    S Tin[12];
-    if (live) {
-      load_T12<S, SOA>(T, i, ld, Tin);
-    } else {
-#pragma unroll
-      for (int c = 0; c < 12; ++c) Tin[c] = (c % 5 == 0) ? S(1) : S(0);
-    }
-    S R0[9], p0[3];
-    fanuc_ik_t0(P, Tin, R0, p0);
-    const int wl[2] = {0, 1};
-    S qo[2][6];
-    bool ok[2];
-    fanuc_ik_mk<S, 2, true>(P, R0, p0, m, k, wl, qo, ok);
-
-    // validity (AOS): 2 bits per lane -> the pose's 8 bytes, gathered with two shuffles
-    unsigned long long packed = 0;
-    if constexpr (!SOA) {
-      const unsigned mine = (ok[0] ? 1u : 0u) | (ok[1] ? 0x100u : 0u);
-      const unsigned other = __shfl_xor_sync(0xffffffffu, mine, 1);
-      const unsigned pair = (mk & 1) ? (other | (mine << 16)) : (mine | (other << 16));
-      const unsigned pair2 = __shfl_xor_sync(0xffffffffu, pair, 2);
-      packed = (mk & 2) ? ((unsigned long long)pair2 | ((unsigned long long)pair << 32))
-                        : ((unsigned long long)pair | ((unsigned long long)pair2 << 32));
-    }
-    if (SOA) {
-      if (live) {
-        S* qp = q_out + (int64_t)(mk * 12) * ld + i;
-#pragma unroll
-        for (int w = 0; w < 2; ++w) {
-#pragma unroll
-          for (int j = 0; j < 6; ++j) {
-            __stcs(qp, qo[w][j]);
-            qp += ld;
-          }
-          valid[(int64_t)(mk * 2 + w) * ld + i] = ok[w] ? 1 : 0;
-        }
-      }
-    } else {
-      // pose-major [n][8][6]: this warp owns a contiguous run of PPW*48 values
-      S flat[12];
-#pragma unroll
-      for (int w = 0; w < 2; ++w)
-#pragma unroll
-        for (int j = 0; j < 6; ++j) flat[w * 6 + j] = qo[w][j];
-      const int64_t rem = n - base;
-      const int cnt = rem < PPW ? (int)rem : PPW;
-      S* stage = stage_all + warp_in_blk * kWarp * Stride<12>::value;
-      warp_store_aos<S, 12>(stage, flat, q_out + base * 48, cnt * 4, lane);
-      if (live && mk == 0) *reinterpret_cast<unsigned long long*>(valid + i * 8) = packed;
-    }
-  }
-}
-
 // SOA fast path, thread-per-pose: one thread computes all 8 branches of its pose with
-// fanuc_ik8_pose (about half the instructions per pose of the 4-lanes-per-pose mapping, which
-// replicates the pose- and k-level work and spends ~200 instructions per lane on uniform-register
+// fanuc_ik8_pose (about half the instructions per pose of the earlier 4-lanes-per-pose mapping, which
+// replicated the pose- and k-level work and spent ~200 instructions per lane on uniform-register
 // spills and lane pairing).  Every warp runs its own pipeline over 32-pose tiles: the tile's 12
 // input planes arrive by one 2-D TMA load ([12][32] box; the next tile's load is issued as soon as
 // the lanes hold the current inputs in registers; per-warp mbarrier -- no CTA barrier anywhere);
@@ -810,7 +725,7 @@ fanuc_ik8_pose_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant
         const int wl[2] = {0, 1};
         S qo[2][6];
         bool ok[2];
-        fanuc_ik_mk<S, 2, false>(P, R0, p0, (mk & 2) ? -1 : 1, (mk & 1) ? -1 : 1, wl, qo, ok);
+        fanuc_ik_mk<S, 2>(P, R0, p0, (mk & 2) ? -1 : 1, (mk & 1) ? -1 : 1, wl, qo, ok);
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
 #pragma unroll
@@ -956,7 +871,7 @@ fanuc_ik8_pose_aos_kernel(const __grid_constant__ FanucP<S> P, const __grid_cons
           const int wl[2] = {0, 1};
           S qo[2][6];
           bool ok[2];
-          fanuc_ik_mk<S, 2, false>(P, R0, p0, (mk & 2) ? -1 : 1, (mk & 1) ? -1 : 1, wl, qo, ok);
+          fanuc_ik_mk<S, 2>(P, R0, p0, (mk & 2) ? -1 : 1, (mk & 1) ? -1 : 1, wl, qo, ok);
 #pragma unroll
           for (int w = 0; w < 2; ++w) {
 #pragma unroll
@@ -1014,7 +929,7 @@ fanuc_ik_list_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant_
       }
       S qo[NW][6];
       bool ok[NW];
-      fanuc_ik_mk<S, NW, false>(P, R0, p0, BL.gm[g], BL.gk[g], wl, qo, ok);
+      fanuc_ik_mk<S, NW>(P, R0, p0, BL.gm[g], BL.gk[g], wl, qo, ok);
 #pragma unroll 1
       for (int b = 0; b < nb; ++b) {
         if (BL.grp[b] != g) continue;
@@ -1141,12 +1056,13 @@ static int launch_ik(const RkFanuc* robot, const S* T, int64_t n, int64_t ld, in
           if (branches[b * 3] != m || branches[b * 3 + 1] != k || branches[b * 3 + 2] != w)
             canonical = false;
   }
+  // the canonical 8 as an explicit list, for the general (list) kernel when the fast paths below
+  // cannot be used
+  static const int8_t kCanonical8[24] = {1, 1, 0, 1, 1, 1, 1, -1, 0, 1, -1, 1, -1, 1, 0, -1, 1, 1, -1, -1, 0, -1, -1, 1};
   if (canonical) {
-    // 128 registers / 4 CTAs per SM measured best (3: 8.1 ms, 4: 7.2 ms, 5: 7.2 ms, 6 spills: 8.1 ms
-    // per 2^25 poses)
+    branches = kCanonical8;
     if (soa) {
-      // thread-per-pose kernel when T satisfies the tensor-map alignment rules (16-byte base and
-      // pitch), 4-lanes-per-pose LSU kernel otherwise
+      // thread-per-pose kernel when T satisfies the tensor-map alignment rules (16-byte base and pitch)
       constexpr int TP = IkPoseTile<S>::kPoses;
       CUtensorMap tmT;
       if (make_tmap_2d(&tmT, TmapType<S>::value, sizeof(S), T, n, 12, ld * sizeof(S), TP, 12)) {
@@ -1155,12 +1071,10 @@ static int launch_ik(const RkFanuc* robot, const S* T, int64_t n, int64_t ld, in
         auto kern = P.std_limits ? fanuc_ik8_pose_kernel<S, true> : fanuc_ik8_pose_kernel<S, false>;
         int grid = stream_grid(kern, kBlock, smem, ntiles * kWarp, 16);  // 4: 6.08, 16: 5.95, 32: 6.02 ms
         kern<<<grid, kBlock, smem, st>>>(P, tmT, q_out, valid, n, ld, ntiles);
-      } else {
-        int grid = stream_grid(fanuc_ik8_kernel<S, true, 4>, kBlock, 0, n * 4);
-        fanuc_ik8_kernel<S, true, 4><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
+        return check_launch();
       }
     } else {
-      // thread-per-pose kernel when the arrays allow 16-byte accesses, 4-lanes-per-pose kernel otherwise
+      // thread-per-pose kernel when the arrays allow 16-byte accesses
       constexpr int TP = IkPoseTileAos<S>::kPoses;
       CUtensorMap tmT;
       const bool aligned = (((uintptr_t)q_out & 15) == 0) && (((uintptr_t)valid & 7) == 0);
@@ -1172,12 +1086,9 @@ static int launch_ik(const RkFanuc* robot, const S* T, int64_t n, int64_t ld, in
         if (!allow_dynamic_smem(kern, smem)) return RK_ERR_CUDA;
         int grid = stream_grid(kern, kBlock, smem, ntiles * kWarp, 16);
         kern<<<grid, kBlock, smem, st>>>(P, tmT, q_out, valid, n, ntiles);
-      } else {
-        int grid = stream_grid(fanuc_ik8_kernel<S, false, 4>, kBlock, 0, n * 4);
-        fanuc_ik8_kernel<S, false, 4><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
+        return check_launch();
       }
     }
-    return check_launch();
   }
   BranchList BL = {};
   BL.nb = nb;
