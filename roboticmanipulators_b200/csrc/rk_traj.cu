@@ -141,7 +141,7 @@ __device__ __forceinline__ Equalized<NJ> equalize(const double* __restrict__ q0,
 
 // mode 0: joint-space sampler; 1: + RRR FK/Jacobian per sample; 2: Cartesian + RRR IK + dq
 template <int NJ, int MODE>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, MODE == 2 ? 4 : (MODE == 1 ? 2 : 3))
 traj_kernel(const __grid_constant__ ArmP P, const double* __restrict__ q0, const double* __restrict__ qf,
             int64_t ntraj, int nsteps, double vmax, double amax, double freq, double* __restrict__ q,
             double* __restrict__ dq, double* __restrict__ ddq, double* __restrict__ t,
