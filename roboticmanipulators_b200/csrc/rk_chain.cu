@@ -96,13 +96,27 @@ __global__ void __launch_bounds__(kBlock)
 chain_fk_jac_kernel(const __grid_constant__ RkChain Ch, const double* __restrict__ values,
                     int nvals, int n_active, int64_t n, int64_t ld, double* __restrict__ T,
                     double* __restrict__ J) {
+  extern __shared__ __align__(16) double smem_d[];  // token values [ntok][kBlock]
+  double* tokv = smem_d + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    auto val = [&](int t) -> double {
-      const int s = Ch.src[t];
-      if (s < 0) return Ch.cst[t];
-      return SOA ? values[(int64_t)s * ld + i] : values[i * nvals + s];
-    };
+    // All token values are fetched before the walk, eight independent loads at a time: fetched
+    // inside the walk, every token waited for its own DRAM round trip (ncu: long_scoreboard 7.7
+    // per issue, the kernel ran at one third of its memory roofline).
+    for (int t0 = 0; t0 < Ch.ntok; t0 += 8) {
+      double v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int t = t0 + k;
+        const int sc = t < Ch.ntok ? Ch.src[t] : -1;
+        v[k] = sc < 0 ? (t < Ch.ntok ? Ch.cst[t] : 0.0)
+                      : (SOA ? __ldcs(values + (int64_t)sc * ld + i) : values[i * nvals + sc]);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (t0 + k < Ch.ntok) tokv[(t0 + k) * kBlock] = v[k];
+    }
+    auto val = [&](int t) -> double { return tokv[t * kBlock]; };
     Frame F;
     if (Ch.has_base)
       frame_from12(F, Ch.T_base);
@@ -116,7 +130,7 @@ chain_fk_jac_kernel(const __grid_constant__ RkChain Ch, const double* __restrict
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         if (SOA)
-          T[(int64_t)k * ld + i] = Tv[k];
+          __stcs(T + (int64_t)k * ld + i, Tv[k]);
         else
           T[i * 16 + k] = Tv[k];
       }
@@ -147,7 +161,7 @@ chain_fk_jac_kernel(const __grid_constant__ RkChain Ch, const double* __restrict
 #pragma unroll
           for (int r = 0; r < 6; ++r) {
             if (SOA)
-              J[(int64_t)(r * n_active + col) * ld + i] = cv[r];
+              __stcs(J + (int64_t)(r * n_active + col) * ld + i, cv[r]);
             else
               J[(i * 6 + r) * n_active + col] = cv[r];
           }
@@ -182,12 +196,13 @@ extern "C" int rk_chain_fk_jac_f64(const RkChain* chain, const double* values, i
   if (soa && ld < n) return RK_ERR_INVALID_ARG;
   if (J && n_active == 0) J = nullptr;
   cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)chain->ntok * rk::kBlock * sizeof(double);
   if (soa) {
-    int grid = rk::stream_grid(rk::chain_fk_jac_kernel<true>, rk::kBlock, 0, n);
-    rk::chain_fk_jac_kernel<true><<<grid, rk::kBlock, 0, st>>>(*chain, values, nvals, n_active, n, ld, T, J);
+    int grid = rk::stream_grid(rk::chain_fk_jac_kernel<true>, rk::kBlock, smem, n);
+    rk::chain_fk_jac_kernel<true><<<grid, rk::kBlock, smem, st>>>(*chain, values, nvals, n_active, n, ld, T, J);
   } else {
-    int grid = rk::stream_grid(rk::chain_fk_jac_kernel<false>, rk::kBlock, 0, n);
-    rk::chain_fk_jac_kernel<false><<<grid, rk::kBlock, 0, st>>>(*chain, values, nvals, n_active, n, ld, T, J);
+    int grid = rk::stream_grid(rk::chain_fk_jac_kernel<false>, rk::kBlock, smem, n);
+    rk::chain_fk_jac_kernel<false><<<grid, rk::kBlock, smem, st>>>(*chain, values, nvals, n_active, n, ld, T, J);
   }
   return rk::check_launch();
 }
