@@ -136,12 +136,16 @@ __device__ __forceinline__ void fr_mul(Fr& F, const double* X) {
 __device__ __forceinline__ void load_joints(const CalibP& P, const double* __restrict__ q, int64_t i,
                                             bool live, double (&s)[RK_CALIB_MAX_JOINTS],
                                             double (&c)[RK_CALIB_MAX_JOINTS]) {
+  // all joint values are fetched before the first sincos (independent loads in flight together;
+  // inside the loop below every uniform branch would fence the next load behind it)
+  double raw[RK_CALIB_MAX_JOINTS];
+#pragma unroll
+  for (int j = 0; j < RK_CALIB_MAX_JOINTS; ++j) raw[j] = (live && j < P.nj) ? __ldcs(q + i * P.nj + j) : 0.0;
 #pragma unroll
   for (int j = 0; j < RK_CALIB_MAX_JOINTS; ++j) {
     s[j] = 0.0, c[j] = 1.0;
     if (j < P.nj) {
-      const double raw = live ? q[i * P.nj + j] : 0.0;
-      const double v = __dadd_rn(__dmul_rn(raw, P.jdir[j]), P.joff[j]);  // model_calibration.py:557
+      const double v = __dadd_rn(__dmul_rn(raw[j], P.jdir[j]), P.joff[j]);  // model_calibration.py:557
       if (P.jkind[j] == 1)
         fast_sincos(v, &s[j], &c[j]);
       else
@@ -570,6 +574,9 @@ calib_tool_base_stats_kernel(const __grid_constant__ CalibP P, const double* __r
   for (int k = 0; k < kTbAcc; ++k) acc[k] = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * kMeas + tid; i < m; i += (int64_t)gridDim.x * kMeas) {
     double sj[RK_CALIB_MAX_JOINTS], cj[RK_CALIB_MAX_JOINTS];
+    double pv[3 * RK_CALIB_MAX_TOOLS];
+#pragma unroll
+    for (int k = 0; k < 3 * RK_CALIB_MAX_TOOLS; ++k) pv[k] = k < 3 * P.nt ? __ldcs(pts + i * 3 * P.nt + k) : 0.0;
     load_joints(P, q, i, true, sj, cj);
     Fr F;
     chain_end(P, sj, cj, F);
@@ -590,8 +597,7 @@ calib_tool_base_stats_kernel(const __grid_constant__ CalibP P, const double* __r
 #pragma unroll
     for (int t = 0; t < RK_CALIB_MAX_TOOLS; ++t) {
       if (t < P.nt) {
-        const double* pm = pts + (i * P.nt + t) * 3;
-        const double ex = pm[0] - px, ey = pm[1] - py, ez = pm[2] - pz;  // dp (:328)
+        const double ex = pv[3 * t] - px, ey = pv[3 * t + 1] - py, ez = pv[3 * t + 2] - pz;  // dp (:328)
         dx += ex, dy += ey, dz += ez;
 #pragma unroll
         for (int k = 0; k < 3; ++k) acc[33 + 3 * t + k] += F.R[k] * ex + F.R[3 + k] * ey + F.R[6 + k] * ez;
@@ -678,11 +684,16 @@ calib_eval_kernel(const __grid_constant__ CalibP P, const double* __restrict__ q
   double acc[8] = {0.0, 0.0, 0.0, 0.0, -1.0, -1.0, -1.0, -1.0};  // maxima start at -1 (:481)
   for (int64_t i = (int64_t)blockIdx.x * kMeas + tid; i < m; i += (int64_t)gridDim.x * kMeas) {
     double sj[RK_CALIB_MAX_JOINTS], cj[RK_CALIB_MAX_JOINTS];
+    double pv[3 * RK_CALIB_MAX_TOOLS];
+#pragma unroll
+    for (int k = 0; k < 3 * RK_CALIB_MAX_TOOLS; ++k) pv[k] = k < 3 * P.nt ? __ldcs(pts + i * 3 * P.nt + k) : 0.0;
     load_joints(P, q, i, true, sj, cj);
     Fr F;
     chain_end(P, sj, cj, F);
-    for (int t = 0; t < P.nt; ++t) {
-      const double* pm = pts + (i * P.nt + t) * 3;
+#pragma unroll
+    for (int t = 0; t < RK_CALIB_MAX_TOOLS; ++t) {
+      if (t >= P.nt) break;
+      const double* pm = pv + 3 * t;
       double d[3];
 #pragma unroll
       for (int r = 0; r < 3; ++r)
