@@ -513,9 +513,19 @@ __device__ __forceinline__ void warp_load_aos(S* stage, S (&v)[NC], const S* g_w
   constexpr int ST = Stride<NC>::value;
   __syncwarp();
   const int total = n_items * NC;
-  for (int idx = lane; idx < total; idx += kWarp) {
-    int item = idx / NC, c = idx - item * NC;
-    stage[item * ST + c] = g_warp_base[idx];
+  // the warp's run is NC * 32 elements: NC independent loads in flight, then the stores (a rolled
+  // loop would make every store wait for its own load before the next load is issued)
+  S tmp[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    const int idx = lane + k * kWarp;
+    tmp[k] = idx < total ? g_warp_base[idx] : S(0);
+  }
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    const int idx = lane + k * kWarp;
+    const int item = idx / NC, c = idx - item * NC;
+    if (idx < total) stage[item * ST + c] = tmp[k];
   }
   __syncwarp();
 #pragma unroll
