@@ -507,6 +507,36 @@ __device__ __forceinline__ void warp_store_aos(S* stage, const S (&v)[NC], S* g_
   }
 }
 
+// Same, with eight shared-memory loads in flight before their eight stores.  Helps the
+// trajectory kernels (small NC, few live registers: Cartesian line + IK 1.56 -> 1.42 ms); it costs
+// K1's AOS kernel, which is already at its register limit, 19 %.
+template <typename S, int NC>
+__device__ __forceinline__ void warp_store_aos_ilp(S* stage, const S (&v)[NC], S* g_warp_base,
+                                                   int n_items, int lane) {
+  constexpr int ST = Stride<NC>::value;
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < NC; ++c) stage[lane * ST + c] = v[c];
+  __syncwarp();
+  const int total = n_items * NC;
+  constexpr int CH = NC < 8 ? NC : 8;
+#pragma unroll
+  for (int k0 = 0; k0 < NC; k0 += CH) {
+    S tmp[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int idx = lane + (k0 + k) * kWarp;
+      const int item = idx / NC, c = idx - item * NC;
+      tmp[k] = (k0 + k < NC && idx < total) ? stage[item * ST + c] : S(0);
+    }
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int idx = lane + (k0 + k) * kWarp;
+      if (k0 + k < NC && idx < total) g_warp_base[idx] = tmp[k];
+    }
+  }
+}
+
 template <typename S, int NC>
 __device__ __forceinline__ void warp_load_aos(S* stage, S (&v)[NC], const S* g_warp_base,
                                               int n_items, int lane) {

@@ -173,9 +173,9 @@ traj_kernel(const __grid_constant__ ArmP P, const double* __restrict__ q0, const
           trap_sample_joint(e.tt, seg, tk, e.q0[j], e.v[j], e.a[j], qv[j], dqv[j], ddqv[j]);
       }
       const int64_t s0 = tr * nsteps + base;  // first sample of this warp pass
-      if (q) warp_store_aos<double, NJ>(stage, qv, q + s0 * NJ, cnt, lane);
-      if (dq) warp_store_aos<double, NJ>(stage, dqv, dq + s0 * NJ, cnt, lane);
-      if (MODE != 2 && ddq) warp_store_aos<double, NJ>(stage, ddqv, ddq + s0 * NJ, cnt, lane);
+      if (q) warp_store_aos_ilp<double, NJ>(stage, qv, q + s0 * NJ, cnt, lane);
+      if (dq) warp_store_aos_ilp<double, NJ>(stage, dqv, dq + s0 * NJ, cnt, lane);
+      if (MODE != 2 && ddq) warp_store_aos_ilp<double, NJ>(stage, ddqv, ddq + s0 * NJ, cnt, lane);
       if (t && lane < cnt) t[s0 + lane] = tout;
       if constexpr (MODE == 1) {
         double Tv[16], Jv[18];
@@ -186,8 +186,8 @@ traj_kernel(const __grid_constant__ ArmP P, const double* __restrict__ q0, const
 #pragma unroll
           for (int k = 0; k < 18; ++k) Jv[k] = 0.0;
         }
-        if (o1) warp_store_aos<double, 16>(stage, Tv, o1 + s0 * 16, cnt, lane);
-        if (o2) warp_store_aos<double, 18>(stage, Jv, o2 + s0 * 18, cnt, lane);
+        if (o1) warp_store_aos_ilp<double, 16>(stage, Tv, o1 + s0 * 16, cnt, lane);
+        if (o2) warp_store_aos_ilp<double, 18>(stage, Jv, o2 + s0 * 18, cnt, lane);
       }
       if constexpr (MODE == 2) {
         // move_via_points: T_IK = [I | p] -> inverse_kinematics(m=1, k=1) (rrr_robot.py:263-270)
@@ -212,8 +212,8 @@ traj_kernel(const __grid_constant__ ArmP P, const double* __restrict__ q0, const
           jdq[1] = (B0 * dqv[0] + B1 * dqv[1] + B2 * dqv[2]) * inv;
           jdq[2] = (C0 * dqv[0] + C1 * dqv[1] + C2 * dqv[2]) * inv;
         }
-        if (o1) warp_store_aos<double, 3>(stage, jq, o1 + s0 * 3, cnt, lane);
-        if (o2) warp_store_aos<double, 3>(stage, jdq, o2 + s0 * 3, cnt, lane);
+        if (o1) warp_store_aos_ilp<double, 3>(stage, jq, o1 + s0 * 3, cnt, lane);
+        if (o2) warp_store_aos_ilp<double, 3>(stage, jdq, o2 + s0 * 3, cnt, lane);
         if (valid && lane < cnt) valid[s0 + lane] = ok ? 1 : 0;
       }
     }
