@@ -8,7 +8,7 @@ rk_fanuc_ik_f64 (all 8 Pieper branches + validity) on the poses K1 produced.  De
 15 steps x 2^26 poses = 1.0e9 poses (BASELINE config 2/3 sizes chunked for one GPU).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                  [--workload fk_jac_ik|fk_jac|ik|calib|traj] [--batch B] [--layout soa|aos]
+                  [--workload fk_jac_ik|fk_jac_ik_split|fk_jac|ik|calib|traj] [--batch B] [--layout soa|aos]
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 """
@@ -167,7 +167,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="fk_jac_ik",
-                    choices=["fk_jac_ik", "fk_jac", "ik", "calib", "traj"])
+                    choices=["fk_jac_ik", "fk_jac_ik_split", "fk_jac", "ik", "calib", "traj"])
     ap.add_argument("--batch", type=int, default=1 << 26, help="poses per GPU per step")
     ap.add_argument("--e2e-batch", type=int, default=1 << 20)
     ap.add_argument("--layout", default="soa", choices=["soa", "aos"])

@@ -24,7 +24,8 @@ def ncu_traffic_per_unit():
             for rec in json.load(open(path)):
                 if "traffic_bytes_per_unit" not in rec:
                     continue
-                for key, pat in (("fanuc_fk_jac", "fanuc_fk_jac"), ("fanuc_ik8", "fanuc_ik8"),
+                for key, pat in (("fanuc_fk_jac", "fanuc_fk_jac_tma"), ("fanuc_ik8", "fanuc_ik8"),
+                                 ("fanuc_fk_jac_ik8", "fanuc_fk_jac_ik8"),
                                  ("calib_normal_eq", "calib_normal_eq"), ("rrr_p2p_fk", "traj_kernel")):
                     if pat in rec["kernel"]:
                         out[key] = rec["traffic_bytes_per_unit"]
@@ -54,14 +55,16 @@ def fp64_probe():
 
 
 class FanucWorkload:
-    """K1 fk+jac+det then K2 ik8 over `batch` poses per step, SOA or AOS planes."""
+    """fk+jac+det and ik8 over `batch` poses per step, SOA or AOS planes.  `fk_jac_ik` is the single
+    call rk_fanuc_fk_jac_ik8 (one fused kernel for SOA); `fk_jac_ik_split` (and AOS) are the two calls
+    rk_fanuc_fk_jac then rk_fanuc_ik on the pose planes K1 wrote."""
     unit = "poses/s"
     metric = "FK+Jacobian+IK poses/s (Fanuc165F, fp64)"
     cpu = None
 
     def __init__(self, args, rank, world):
         self.args = args
-        self.mode = args.workload
+        self.mode = "fk_jac_ik" if args.workload == "fk_jac_ik_split" else args.workload
         self.n = n = args.batch
         self.units_per_step = n
         self.robot = Fanuc165F()
@@ -71,6 +74,7 @@ class FanucWorkload:
         self.flags = _lib.RK_SOA if self.soa else _lib.RK_AOS
         self.f32 = getattr(args, "dtype", "f64") == "f32"
         self.sfx = "f32" if self.f32 else "f64"
+        self.fused = args.workload == "fk_jac_ik" and self.soa
         dev = torch.device("cuda")
         # distinct input batches (so 15 steps really are 1e9 different poses), capped at 48 GB
         nbuf = max(1, min(args.steps, int(48e9 // (48 * n))))
@@ -101,12 +105,13 @@ class FanucWorkload:
             self._k1(self.q[0], with_j=False)
             torch.cuda.synchronize()
         self.events = []
-        self.alg_bytes = {"fanuc_fk_jac": 236, "fanuc_ik8": 264} if self.f32 else \
-            {"fanuc_fk_jac": 472, "fanuc_ik8": 520}
+        self.alg_bytes = {"fanuc_fk_jac": 236, "fanuc_ik8": 264, "fanuc_fk_jac_ik8": 432} if self.f32 else \
+            {"fanuc_fk_jac": 472, "fanuc_ik8": 520, "fanuc_fk_jac_ik8": 864}
         self.traffic = {} if self.f32 else {k: v * n for k, v in ncu_traffic_per_unit().items()}
-        self.launches_per_step = {"fk_jac_ik": 2, "fk_jac": 1, "ik": 1}[self.mode]
+        self.launches_per_step = 1 if self.fused else {"fk_jac_ik": 2, "fk_jac": 1, "ik": 1}[self.mode]
         self.config = {
-            "workload": {"fk_jac_ik": "fanuc165f_fk_jac_det_then_ik8",
+            "workload": "fanuc165f_fk_jac_det_ik8_one_kernel" if self.fused else
+                        {"fk_jac_ik": "fanuc165f_fk_jac_det_then_ik8",
                          "fk_jac": "fanuc165f_fk_jac_det", "ik": "fanuc165f_ik8"}[self.mode],
             "baseline_config": "configs[1] (+configs[2] IK on the same poses), chunked: "
                                f"{args.steps} steps x {n} poses per GPU",
@@ -129,12 +134,24 @@ class FanucWorkload:
             C.byref(self.st), _lib.ptr(self.T), self.n, self.ld, self.flags, None, 8,
             _lib.ptr(self.qik), _lib.ptr(self.valid), st))
 
+    def _k12(self, q):
+        st = _lib.stream_ptr()
+        _lib.check(getattr(self.lib, "rk_fanuc_fk_jac_ik8_" + self.sfx)(
+            C.byref(self.st), _lib.ptr(q), self.n, self.ld, self.flags, _lib.ptr(self.T),
+            _lib.ptr(self.J), _lib.ptr(self.det), _lib.ptr(self.qik), _lib.ptr(self.valid), st))
+
     def step(self, s):
         timed = s >= 0
         q = self.q[max(s, 0) % len(self.q)]
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if timed else None
         if timed:
             ev[0].record()
+        if self.fused:
+            self._k12(q)
+            if timed:
+                ev[2].record()
+                self.events.append(ev)
+            return
         if self.mode != "ik":
             self._k1(q)
         if timed:
@@ -147,6 +164,8 @@ class FanucWorkload:
 
     def kernel_times_ms(self):
         out = {}
+        if self.fused:
+            return {"fanuc_fk_jac_ik8": float(np.mean([e[0].elapsed_time(e[2]) for e in self.events]))}
         if self.mode != "ik":
             out["fanuc_fk_jac"] = float(np.mean([e[0].elapsed_time(e[1]) for e in self.events]))
         if self.mode != "fk_jac":
@@ -444,7 +463,7 @@ class TrajWorkload:
 
 
 def make(args, rank, world):
-    if args.workload in ("fk_jac_ik", "fk_jac", "ik"):
+    if args.workload in ("fk_jac_ik", "fk_jac_ik_split", "fk_jac", "ik"):
         return FanucWorkload(args, rank, world)
     if args.workload == "calib":
         return CalibWorkload(args, rank, world)

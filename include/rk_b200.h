@@ -111,6 +111,21 @@ int rk_fanuc_ik_f32(const RkFanuc* robot, const float* T, int64_t n, int64_t ld,
                     const int8_t* branches_mkw, int nb, float* q_out, uint8_t* valid,
                     void* stream);
 
+/* forward_kinematics + Jacobian + det followed by inverse_kinematics over the canonical 8
+ * branches of the pose just computed -- the FK -> IK round trip of fanuc_kinematics.py and
+ * tests/test_robots.py:33-52 (test_fanuc_ifk) -- as ONE call.  Arguments and results are
+ * exactly those of rk_fanuc_fk_jac_* followed by rk_fanuc_ik_*(T, branches = NULL, nb = 8);
+ * T, q_out and valid are required, J and det may be NULL.  With RK_SOA and all five
+ * outputs this is a single kernel in which the pose never returns from memory:
+ * algorithmic traffic (FP64) 48 B in + 128 + 288 + 8 + 384 + 8 B out = 864 B per pose
+ * (992 B for the two calls). */
+int rk_fanuc_fk_jac_ik8_f64(const RkFanuc* robot, const double* q, int64_t n, int64_t ld,
+                            int flags, double* T, double* J, double* det, double* q_out,
+                            uint8_t* valid, void* stream);
+int rk_fanuc_fk_jac_ik8_f32(const RkFanuc* robot, const float* q, int64_t n, int64_t ld,
+                            int flags, float* T, float* J, float* det, float* q_out,
+                            uint8_t* valid, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * RRRRobot / RRRobot  (reference: robots/rrr_robot.py, robots/rr_robot.py)
  * ---------------------------------------------------------------------------------- */

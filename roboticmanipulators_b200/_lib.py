@@ -70,6 +70,8 @@ _SIGNATURES = {
     "rk_last_cuda_error": (C.c_char_p, []),
     "rk_fanuc_fk_jac_f64": (_int, [C.POINTER(RkFanuc), _vp, _i64, _i64, _int, _vp, _vp, _vp, _vp]),
     "rk_fanuc_fk_jac_f32": (_int, [C.POINTER(RkFanuc), _vp, _i64, _i64, _int, _vp, _vp, _vp, _vp]),
+    "rk_fanuc_fk_jac_ik8_f64": (_int, [C.POINTER(RkFanuc), _vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rk_fanuc_fk_jac_ik8_f32": (_int, [C.POINTER(RkFanuc), _vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rk_fanuc_ik_f64": (_int, [C.POINTER(RkFanuc), _vp, _i64, _i64, _int, _vp, _int, _vp, _vp, _vp]),
     "rk_fanuc_ik_f32": (_int, [C.POINTER(RkFanuc), _vp, _i64, _i64, _int, _vp, _int, _vp, _vp, _vp]),
     "rk_rrr_fk_jac_f64": (_int, [C.POINTER(RkArm), _vp, _i64, _i64, _int, _vp, _vp, _vp]),

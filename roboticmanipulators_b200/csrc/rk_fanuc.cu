@@ -682,7 +682,7 @@ template <typename S, bool STD>
 __global__ void __launch_bounds__(kBlock, sizeof(S) == 4 ? 6 : 4)
 fanuc_ik8_pose_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant__ CUtensorMap tmT,
                       S* __restrict__ q_out, uint8_t* __restrict__ valid, int64_t n, int64_t ld,
-                      int64_t ntiles) {
+                      int64_t ntiles, int chunk) {
   using Tile = IkPoseTile<S>;
   constexpr int TP = Tile::kPoses;
   constexpr int WPB = kBlock / kWarp;
@@ -698,12 +698,17 @@ fanuc_ik8_pose_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant
     mbar_expect_tx(&sm.bar, 12 * TP * sizeof(S));
     tma_load_2d(&sm.in[0][0], &tmT, (int)(tile * TP), 0, &sm.bar);
   };
-  const int64_t stride = (int64_t)gridDim.x * WPB;
-  int64_t tile = (int64_t)blockIdx.x * WPB + warp;
-  if (lane == 0 && tile < ntiles) issue_load(tile);
+  // A CTA owns `chunk` consecutive groups of WPB tiles, so the CTAs resident at any moment write one
+  // compact window of every output plane.  (With a grid-strided tile loop a warp's successive tiles
+  // were gridDim.x * 128 poses apart and the chip was writing 16 separate regions of each of the
+  // 56 planes at once: 5.53 -> 5.31 ms per 2^26 poses.)
+  int64_t tile = (int64_t)blockIdx.x * WPB * chunk + warp;
+  const int64_t tlast = (int64_t)(blockIdx.x + 1) * WPB * chunk;
+  const int64_t tend = tlast < ntiles ? tlast : ntiles;
+  if (lane == 0 && tile < tend) issue_load(tile);
   int it = 0;
-  for (; tile < ntiles; tile += stride, ++it) {
-    const int64_t next = tile + stride;
+  for (; tile < tend; tile += WPB, ++it) {
+    const int64_t next = tile + WPB;
     mbar_wait(&sm.bar, it & 1);
     // every lane runs (fanuc_ik8_pose votes across the warp) and stores without a guard: lanes
     // past the end of a ragged last tile redo the last pose and write the same values again
@@ -713,13 +718,102 @@ fanuc_ik8_pose_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant
 #pragma unroll
     for (int c = 0; c < 12; ++c) Tin[c] = sm.in[c][src];
     __syncwarp();
-    if (lane == 0 && next < ntiles) issue_load(next);  // the buffer is free again
+    if (lane == 0 && next < tend) issue_load(next);  // the buffer is free again
     const int64_t i = tile * TP + src;
     S R0[9], p0[3];
     fanuc_ik_t0(P, Tin, R0, p0);
     IkPlaneSink<S> sink{q_out + i, valid + i, ld};
     if (fanuc_ik8_pose<S, STD>(P, R0, p0, sink)) {
       // measure-zero configurations: the branch-by-branch routine with all its special cases
+#pragma unroll 1
+      for (int mk = 0; mk < 4; ++mk) {
+        const int wl[2] = {0, 1};
+        S qo[2][6];
+        bool ok[2];
+        fanuc_ik_mk<S, 2>(P, R0, p0, (mk & 2) ? -1 : 1, (mk & 1) ? -1 : 1, wl, qo, ok);
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+#pragma unroll
+          for (int j = 0; j < 6; ++j) sink.q(mk * 2 + w, j, qo[w][j]);
+          sink.ok(mk * 2 + w, ok[w]);
+        }
+      }
+    }
+  }
+}
+
+// K1 + K2 on the same poses in one pass (the round trip of tests/test_robots.py::test_fanuc_ifk and
+// fanuc_kinematics.py: FK of q, then every IK branch of that pose): the pose never comes back from
+// HBM -- its 3x4 part stays in registers between the two halves -- so a pose costs
+// 48 B in + 128 + 288 + 8 + 384 + 8 B out = 864 B instead of 472 + 520 = 992 B.  Same per-warp
+// pipeline as fanuc_ik8_pose_kernel ([6][32] joint tile by TMA, next tile requested as soon as the
+// lanes hold their joints), every result stored to its plane the moment it exists, unguarded.
+template <typename S>
+struct FkIkSink {
+  S* Tp;
+  S* Jp;
+  S* dp;
+  int64_t ld;
+  S (&Tin)[12];
+  __device__ __forceinline__ void T(int k, S v) {
+    __stcs(Tp + k * ld, v);
+    if (k < 12) Tin[k] = v;
+  }
+  __device__ __forceinline__ void J(int k, S v) { __stcs(Jp + k * ld, v); }
+  __device__ __forceinline__ void det(S v) { __stcs(dp, v); }
+};
+
+template <typename S>
+struct alignas(128) FkIkTile {
+  static constexpr int kPoses = kWarp;
+  S q[6][kPoses];
+  uint64_t bar;
+};
+
+template <typename S, bool STD>
+__global__ void __launch_bounds__(kBlock, sizeof(S) == 4 ? 6 : 4)
+fanuc_fk_jac_ik8_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant__ CUtensorMap tmq,
+                        S* __restrict__ T, S* __restrict__ J, S* __restrict__ det,
+                        S* __restrict__ q_out, uint8_t* __restrict__ valid, int64_t n, int64_t ld,
+                        int64_t ntiles, int chunk) {
+  using Tile = FkIkTile<S>;
+  constexpr int TP = Tile::kPoses;
+  constexpr int WPB = kBlock / kWarp;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = uniform_warp_idx();
+  Tile& sm = reinterpret_cast<Tile*>(smem_raw)[warp];
+  if (lane == 0) {
+    mbar_init(&sm.bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  auto issue_load = [&](int64_t tile) {  // one lane
+    mbar_expect_tx(&sm.bar, 6 * TP * sizeof(S));
+    tma_load_2d(&sm.q[0][0], &tmq, (int)(tile * TP), 0, &sm.bar);
+  };
+  int64_t tile = (int64_t)blockIdx.x * WPB * chunk + warp;  // see fanuc_ik8_pose_kernel
+  const int64_t tlast = (int64_t)(blockIdx.x + 1) * WPB * chunk;
+  const int64_t tend = tlast < ntiles ? tlast : ntiles;
+  if (lane == 0 && tile < tend) issue_load(tile);
+  int it = 0;
+  for (; tile < tend; tile += WPB, ++it) {
+    const int64_t next = tile + WPB;
+    mbar_wait(&sm.bar, it & 1);
+    const int64_t rem = n - tile * TP;  // ragged last tile: the spare lanes redo the last pose
+    const int src = lane < rem ? lane : (int)rem - 1;
+    S qv[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) qv[c] = sm.q[c][src];
+    __syncwarp();
+    if (lane == 0 && next < tend) issue_load(next);
+    const int64_t i = tile * TP + src;
+    S Tin[12];
+    FkIkSink<S> fk{T + i, J + i, det + i, ld, Tin};
+    fanuc_fk_jac_emit(P, qv, fk);
+    S R0[9], p0[3];
+    fanuc_ik_t0(P, Tin, R0, p0);
+    IkPlaneSink<S> sink{q_out + i, valid + i, ld};
+    if (fanuc_ik8_pose<S, STD>(P, R0, p0, sink)) {
 #pragma unroll 1
       for (int mk = 0; mk < 4; ++mk) {
         const int wl[2] = {0, 1};
@@ -812,7 +906,8 @@ struct IkAosSink {
 template <typename S, bool STD>
 __global__ void __launch_bounds__(kBlock, sizeof(S) == 4 ? 6 : 4)
 fanuc_ik8_pose_aos_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant__ CUtensorMap tmT,
-                          S* __restrict__ q_out, uint8_t* __restrict__ valid, int64_t n, int64_t ntiles) {
+                          S* __restrict__ q_out, uint8_t* __restrict__ valid, int64_t n, int64_t ntiles,
+                          int chunk) {
   using Tile = IkPoseTileAos<S>;
   constexpr int TP = Tile::kPoses;
   constexpr int WPB = kBlock / kWarp;
@@ -832,12 +927,13 @@ fanuc_ik8_pose_aos_kernel(const __grid_constant__ FanucP<S> P, const __grid_cons
     mbar_expect_tx(&sm.bar[0], 16 * TP * sizeof(S));
     tma_load_2d(&sm.in[0][0][0], &tmT, 0, (int)(tile * TP), &sm.bar[0]);
   };
-  const int64_t stride = (int64_t)gridDim.x * WPB;
-  int64_t tile = (int64_t)blockIdx.x * WPB + warp;
-  if (lane == 0 && tile < ntiles) issue_load(tile);
+  int64_t tile = (int64_t)blockIdx.x * WPB * chunk + warp;  // see fanuc_ik8_pose_kernel
+  const int64_t tlast = (int64_t)(blockIdx.x + 1) * WPB * chunk;
+  const int64_t tend = tlast < ntiles ? tlast : ntiles;
+  if (lane == 0 && tile < tend) issue_load(tile);
   int it = 0;
-  for (; tile < ntiles; tile += stride, ++it) {
-    const int64_t next = tile + stride;
+  for (; tile < tend; tile += WPB, ++it) {
+    const int64_t next = tile + WPB;
     mbar_wait(&sm.bar[0], it & 1);
     // lane L owns row L; 16-byte piece c of the row sits at piece c ^ (swizzle bits of the address)
     S Tin[12];
@@ -853,7 +949,7 @@ fanuc_ik8_pose_aos_kernel(const __grid_constant__ FanucP<S> P, const __grid_cons
       for (int e = 0; e < kPer16; ++e) Tin[c * kPer16 + e] = tmp[e];
     }
     __syncwarp();
-    if (lane == 0 && next < ntiles) issue_load(next);  // the buffer is free again
+    if (lane == 0 && next < tend) issue_load(next);  // the buffer is free again
     // every lane runs (fanuc_ik8_pose votes across the warp); rows past the end were zero-filled
     const int64_t base = tile * TP;
     const int64_t i = base + lane;
@@ -981,6 +1077,22 @@ fanuc_ik_list_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant_
 // -----------------------------------------------------------------------------------
 // host launchers
 // -----------------------------------------------------------------------------------
+// Grid of the warp-per-tile kernels: a CTA owns `chunk` consecutive groups of (kBlock / kWarp) tiles.
+// Large batches: `want` groups per CTA and as many CTAs as that takes (the hardware block scheduler
+// balances the SMs); batches below 4 resident waves of such CTAs: one resident wave of equal chunks.
+struct TileGrid {
+  int grid, chunk;
+};
+template <typename K>
+static TileGrid tile_grid(K kernel, size_t smem, int64_t ntiles, int want) {
+  constexpr int WPB = kBlock / kWarp;
+  const int64_t groups = (ntiles + WPB - 1) / WPB;
+  const int64_t cap = persistent_grid(kernel, kBlock, smem, groups * kBlock);
+  int64_t chunk = want;
+  if (groups / chunk < 4 * cap) chunk = (groups + cap - 1) / cap;
+  const int64_t grid = (groups + chunk - 1) / chunk;
+  return {(int)grid, (int)chunk};
+}
 template <typename S>
 static int launch_fk_jac(const RkFanuc* robot, const S* q, int64_t n, int64_t ld, int flags, S* T,
                          S* J, S* det, void* stream) {
@@ -1069,8 +1181,9 @@ static int launch_ik(const RkFanuc* robot, const S* T, int64_t n, int64_t ld, in
         const int64_t ntiles = (n + TP - 1) / TP;
         const size_t smem = sizeof(IkPoseTile<S>) * (kBlock / kWarp);
         auto kern = P.std_limits ? fanuc_ik8_pose_kernel<S, true> : fanuc_ik8_pose_kernel<S, false>;
-        int grid = stream_grid(kern, kBlock, smem, ntiles * kWarp, 16);  // 4: 6.08, 16: 5.95, 32: 6.02 ms
-        kern<<<grid, kBlock, smem, st>>>(P, tmT, q_out, valid, n, ld, ntiles);
+        // groups per CTA, ms per 2^26 poses: 1: 5.72, 2: 5.42, 4: 5.31
+        const TileGrid tg = tile_grid(kern, smem, ntiles, 4);
+        kern<<<tg.grid, kBlock, smem, st>>>(P, tmT, q_out, valid, n, ld, ntiles, tg.chunk);
         return check_launch();
       }
     } else {
@@ -1084,8 +1197,8 @@ static int launch_ik(const RkFanuc* robot, const S* T, int64_t n, int64_t ld, in
         const size_t smem = sizeof(IkPoseTileAos<S>) * (kBlock / kWarp) + 1024;
         auto kern = P.std_limits ? fanuc_ik8_pose_aos_kernel<S, true> : fanuc_ik8_pose_aos_kernel<S, false>;
         if (!allow_dynamic_smem(kern, smem)) return RK_ERR_CUDA;
-        int grid = stream_grid(kern, kBlock, smem, ntiles * kWarp, 16);
-        kern<<<grid, kBlock, smem, st>>>(P, tmT, q_out, valid, n, ntiles);
+        const TileGrid tg = tile_grid(kern, smem, ntiles, 4);  // 1: 6.80, 4: 6.42 ms per 2^26 poses
+        kern<<<tg.grid, kBlock, smem, st>>>(P, tmT, q_out, valid, n, ntiles, tg.chunk);
         return check_launch();
       }
     }
@@ -1131,6 +1244,41 @@ static int launch_ik(const RkFanuc* robot, const S* T, int64_t n, int64_t ld, in
   return check_launch();
 }
 
+// K1 then K2 (canonical 8 branches) on the same poses.  One fused launch when the layout is SOA, every
+// output is requested and the planes satisfy the tensor-map alignment rules; otherwise the two
+// kernels back to back on `stream` (identical results: the fused kernel runs the same per-pose code
+// on the pose it has just written).
+template <typename S>
+static int launch_fk_jac_ik8(const RkFanuc* robot, const S* q, int64_t n, int64_t ld, int flags, S* T,
+                             S* J, S* det, S* q_out, uint8_t* valid, void* stream) {
+  if (!robot || n < 0) return RK_ERR_INVALID_ARG;
+  if (n == 0) return RK_OK;
+  if (!q || !T || !q_out || !valid) return RK_ERR_INVALID_ARG;
+  const bool soa = (flags & RK_SOA) != 0;
+  if (soa && ld < n) return RK_ERR_INVALID_ARG;
+  if (soa && J && det) {
+    constexpr int TP = FkIkTile<S>::kPoses;
+    CUtensorMap tmq;
+    if (make_tmap_2d(&tmq, TmapType<S>::value, sizeof(S), q, n, 6, ld * sizeof(S), TP, 6)) {
+      FanucP<S> P = make_params<S>(robot, flags);
+      const int64_t ntiles = (n + TP - 1) / TP;
+      const size_t smem = sizeof(FkIkTile<S>) * (kBlock / kWarp);
+      auto kern = P.std_limits ? fanuc_fk_jac_ik8_kernel<S, true> : fanuc_fk_jac_ik8_kernel<S, false>;
+      // One group per CTA: this kernel is 94 % writes (109 planes) and runs fastest with short-lived
+      // CTAs -- ms per 2^26 poses by groups per CTA: 1: 8.99, 2: 9.36, 4: 9.55, 8: 9.66 (the opposite
+      // of the read-heavier IK kernel above); 3 or 5 CTAs per SM instead of 4 and padded plane
+      // strides were also measured and are no better.
+      const TileGrid tg = tile_grid(kern, smem, ntiles, 1);
+      kern<<<tg.grid, kBlock, smem, (cudaStream_t)stream>>>(P, tmq, T, J, det, q_out, valid, n, ld, ntiles,
+                                                            tg.chunk);
+      return check_launch();
+    }
+  }
+  int rc = launch_fk_jac<S>(robot, q, n, ld, flags, T, J, det, stream);
+  if (rc != RK_OK) return rc;
+  return launch_ik<S>(robot, T, n, ld, flags & ~RK_JAC_USER_ANGLES, nullptr, 8, q_out, valid, stream);
+}
+
 }  // namespace rk
 
 extern "C" {
@@ -1152,6 +1300,17 @@ int rk_fanuc_ik_f32(const RkFanuc* robot, const float* T, int64_t n, int64_t ld,
                     const int8_t* branches_mkw, int nb, float* q_out, uint8_t* valid,
                     void* stream) {
   return rk::launch_ik<float>(robot, T, n, ld, flags, branches_mkw, nb, q_out, valid, stream);
+}
+
+int rk_fanuc_fk_jac_ik8_f64(const RkFanuc* robot, const double* q, int64_t n, int64_t ld, int flags,
+                            double* T, double* J, double* det, double* q_out, uint8_t* valid,
+                            void* stream) {
+  return rk::launch_fk_jac_ik8<double>(robot, q, n, ld, flags, T, J, det, q_out, valid, stream);
+}
+int rk_fanuc_fk_jac_ik8_f32(const RkFanuc* robot, const float* q, int64_t n, int64_t ld, int flags,
+                            float* T, float* J, float* det, float* q_out, uint8_t* valid,
+                            void* stream) {
+  return rk::launch_fk_jac_ik8<float>(robot, q, n, ld, flags, T, J, det, q_out, valid, stream);
 }
 
 }  // extern "C"

@@ -176,6 +176,38 @@ class Fanuc165F(Robot):
                           br, nb, _lib.ptr(qstore), _lib.ptr(vstore), _lib.stream_ptr(dev)))
         return qv, vv.bool()
 
+    def fk_jac_ik_batch(self, q, *, layout="auto", user_angles=False):
+        """forward_kinematics_batch(q, jacobian=True, measure=True) followed by
+        inverse_kinematics_batch(T) over the canonical 8 branches, as one call (one kernel for
+        SOA inputs: the pose does not travel through memory between the two halves; the FK -> IK
+        round trip of fanuc_kinematics.py / tests/test_robots.py:33-52).
+        Returns (T [N,4,4], J [N,6,6], det [N], q_ik [N,8,6], valid [N,8] bool)."""
+        _lib.require_cuda(q, "q")
+        if q.dtype not in _DTYPES:
+            raise TypeError("q must be float64 or float32")
+        if layout == "auto":
+            layout = _batch.detect_layout(q, 6)
+        qs, ld = _batch.prep_input(q, 6, layout, q.dtype)
+        n, dev = qs.shape[0], qs.device
+        T, Ts = _batch.alloc_out(n, (4, 4), layout, q.dtype, dev)
+        J, Js = _batch.alloc_out(n, (6, 6), layout, q.dtype, dev)
+        det = torch.empty(n, dtype=q.dtype, device=dev)
+        if layout == "soa":
+            qstore = torch.empty((48, n), dtype=q.dtype, device=dev)
+            vstore = torch.empty((8, n), dtype=torch.uint8, device=dev)
+            qv, vv = qstore.view(8, 6, n).permute(2, 0, 1), vstore.t()
+        else:
+            qstore = torch.empty((n, 8, 6), dtype=q.dtype, device=dev)
+            vstore = torch.empty((n, 8), dtype=torch.uint8, device=dev)
+            qv, vv = qstore, vstore
+        flags = _batch.flags_of(layout) | (_lib.RK_JAC_USER_ANGLES if user_angles else 0)
+        fn = getattr(_lib.load(), "rk_fanuc_fk_jac_ik8_" + _DTYPES[q.dtype])
+        with torch.cuda.device(dev):
+            _lib.check(fn(C.byref(self._struct()), _lib.ptr(qs), n, ld, flags, _lib.ptr(Ts),
+                          _lib.ptr(Js), _lib.ptr(det), _lib.ptr(qstore), _lib.ptr(vstore),
+                          _lib.stream_ptr(dev)))
+        return T, J, det, qv, vv.bool()
+
     # ------------------------------------------------------------- reference methods
     def forward_kinematics(self, q_values, plot=True):
         """robots/fanuc.py:151-179.  Returns a 4x4 np.ndarray.  `plot` is accepted and

@@ -390,3 +390,76 @@ def test_ik8_masks_large_sample():
         d[..., [3, 5]] = (d[..., [3, 5]] + np.pi) % (2 * np.pi) - np.pi
         assert np.nanmax(np.abs(d)) < 1e-8
         assert np.nanpercentile(np.abs(d), 99.9) < 1e-12
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("layout", ["aos", "soa"])
+def test_fk_jac_ik8_single_call(golden, layout, dtype):
+    """rk_fanuc_fk_jac_ik8 (one kernel for SOA): FK/J/det against the oracle, and the IK half
+    bit-identical to rk_fanuc_ik applied to the pose it wrote (same per-pose code, the pose just
+    stays in registers) -- ragged sizes included (spare lanes redo the last pose)."""
+    f64 = dtype == torch.float64
+    for n in (1, 31, 33, 1000, 10000):
+        q = rand_q(n, seed=100 + n)
+        for name, robot, c in robots(golden):
+            qt = torch.tensor(q, device="cuda", dtype=dtype)
+            if layout == "soa":
+                qt = qt.t().contiguous().t()
+            T, J, det, qik, val = robot.fk_jac_ik_batch(qt, layout=layout)
+            assert T.shape == (n, 4, 4) and J.shape == (n, 6, 6) and qik.shape == (n, 8, 6)
+            T2, J2, det2 = robot.forward_kinematics_batch(qt, jacobian=True, measure=True, layout=layout)
+            if f64:
+                check_fk_jac(T.cpu().numpy(), J.cpu().numpy(), det.cpu().numpy(), q, c, 1e-12)
+            assert (T - T2).abs().max().item() <= (1e-12 if f64 else 2e-3) * 4000
+            assert (J - J2).abs().max().item() <= (1e-12 if f64 else 2e-3) * 4000
+            q2, v2 = robot.inverse_kinematics_batch(T, layout=layout)
+            assert torch.equal(val, v2), name
+            assert torch.equal(qik, q2), name
+            if f64:
+                q_ref, v_ref = O.fanuc_ik_branches(T.cpu().numpy(), O.CANONICAL_8, c)
+                assert _cmp_ik(qik.cpu().numpy(), val.cpu().numpy(), q_ref, v_ref) < 1e-9
+
+
+def test_fk_jac_ik8_no_out_of_range_writes():
+    """The fused kernel stores without guards (ragged lanes redo the last pose): padding past n in
+    every plane must stay untouched."""
+    from roboticmanipulators_b200 import _lib
+    from roboticmanipulators_b200.robots.fanuc import Fanuc165F
+    import ctypes as C
+    robot, lib = Fanuc165F(), _lib.load()
+    for n, ld in ((1, 2), (33, 40), (1000, 1002), (4097, 4104)):
+        q = torch.zeros((6, ld), dtype=torch.float64, device="cuda")
+        q[:, :n] = torch.tensor(rand_q(n, seed=n).T, device="cuda")
+        outs = [torch.full((r, ld), -7.0, dtype=torch.float64, device="cuda") for r in (16, 36, 1, 48)]
+        valid = torch.full((8, ld), 9, dtype=torch.uint8, device="cuda")
+        _lib.check(lib.rk_fanuc_fk_jac_ik8_f64(C.byref(robot._struct()), _lib.ptr(q), n, ld, _lib.RK_SOA,
+                                               _lib.ptr(outs[0]), _lib.ptr(outs[1]), _lib.ptr(outs[2]),
+                                               _lib.ptr(outs[3]), _lib.ptr(valid), _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        for o in outs:
+            assert torch.all(o[:, n:] == -7.0)
+            assert not torch.any(o[:, :n] == -7.0)
+        assert torch.all(valid[:, n:] == 9) and torch.all(valid[:, :n] <= 1)
+
+
+def test_fk_jac_ik8_roundtrip_property_large():
+    """2^22 poses through the single call: the IK of FK(q) contains q itself (some branch
+    reproduces the joint vector) wherever a branch is valid, and masks match the two-call path."""
+    from roboticmanipulators_b200.robots.fanuc import Fanuc165F
+    robot = Fanuc165F()
+    n = (1 << 22) + 5
+    g = torch.Generator(device="cuda").manual_seed(3)
+    lim = torch.tensor(np.asarray(robot.qs_lim_rad), device="cuda")
+    store = torch.rand((6, n), generator=g, device="cuda", dtype=torch.float64)
+    store = lim[:, :1] + store * (lim[:, 1:] - lim[:, :1])
+    T, J, det, qik, val = robot.fk_jac_ik_batch(store.t())
+    q2, v2 = robot.inverse_kinematics_batch(T)
+    assert torch.equal(val, v2) and torch.equal(qik, q2)
+    d = (qik - store.t()[:, None, :]).abs()
+    d = torch.minimum(d, (d - 2 * np.pi).abs())           # q3/q5 are returned modulo 2 pi
+    best = torch.where(val, d.amax(dim=2), torch.full_like(d[..., 0], np.inf)).amin(dim=1)
+    found = best < 1e-6
+    # the oracle finds q in 63 % of uniform samples (the rest: q0 = atan2(y, x) +- pi 'over the back'
+    # configurations, which the reference's IK expresses through k = -1 with different q1, q2)
+    assert 0.60 < found.double().mean().item() < 0.66
+    assert best[found].median().item() < 1e-11
