@@ -59,6 +59,8 @@ inline int persistent_grid(K kernel, int block, size_t smem, int64_t work_items)
 // 14 % of K1 (ncu sm__cycles_active min / avg / max = 6.7 / 9.4 / 10.9 M cycles) waiting for the
 // slowest one.  Problems that would give fewer than 4 waves keep the resident grid: a partly
 // filled last wave costs more than the balancing gains (measured on 32 K trajectories: +25 %).
+// trips = 8 suits the thread-per-pose kernels (their software prefetch wants a few trips); the
+// write-only warp-per-trajectory samplers run 8-15 % faster with trips = 2 (rk_traj.cu).
 template <typename K>
 inline int stream_grid(K kernel, int block, size_t smem, int64_t work_items, int trips = 8) {
   const int64_t cap = persistent_grid(kernel, block, smem, work_items);
