@@ -110,9 +110,12 @@ class FanucWorkload:
         self.traffic = {} if self.f32 else {k: v * n for k, v in ncu_traffic_per_unit().items()}
         self.launches_per_step = 1 if self.fused else {"fk_jac_ik": 2, "fk_jac": 1, "ik": 1}[self.mode]
         self.config = {
-            "workload": "fanuc165f_fk_jac_det_ik8_one_kernel" if self.fused else
-                        {"fk_jac_ik": "fanuc165f_fk_jac_det_then_ik8",
+            # same workload name as the reference arm (bench.py run_reference)
+            "workload": {"fk_jac_ik": "fanuc165f_fk_jac_det_ik8",
                          "fk_jac": "fanuc165f_fk_jac_det", "ik": "fanuc165f_ik8"}[self.mode],
+            "calls_per_step": "rk_fanuc_fk_jac_ik8 (one fused kernel)" if self.fused else
+                              {"fk_jac_ik": "rk_fanuc_fk_jac then rk_fanuc_ik on the planes it wrote",
+                               "fk_jac": "rk_fanuc_fk_jac", "ik": "rk_fanuc_ik"}[self.mode],
             "baseline_config": "configs[1] (+configs[2] IK on the same poses), chunked: "
                                f"{args.steps} steps x {n} poses per GPU",
             "batch_per_gpu_per_step": n, "layout": args.layout, "dtype": self.sfx,
