@@ -64,6 +64,18 @@ def test_argument_validation_without_gpu():
     assert lib.rk_fanuc_fk_jac_f64(None, None, 4, 4, 0, None, None, None, None) == -1
     assert lib.rk_fanuc_fk_jac_f64(C.byref(st), None, 0, 0, 0, None, None, None, None) == 0
     assert lib.rk_fanuc_ik_f64(C.byref(st), None, 4, 4, 0, None, 5, None, None, None) == -1
+    # the single FK -> IK call: same rules, and T, q_out, valid are required
+    args = (None, None, None, None, None, None)
+    assert lib.rk_fanuc_fk_jac_ik8_f64(C.byref(st), None, -1, 0, 1, *args) == -1
+    assert lib.rk_fanuc_fk_jac_ik8_f64(None, None, 4, 4, 1, *args) == -1
+    assert lib.rk_fanuc_fk_jac_ik8_f64(C.byref(st), None, 0, 0, 1, *args) == 0
+    assert lib.rk_fanuc_fk_jac_ik8_f32(C.byref(st), C.c_void_p(16), 4, 4, 1, *args) == -1
+    assert lib.rk_fanuc_fk_jac_ik8_f64(C.byref(st), C.c_void_p(16), 8, 4, 1, C.c_void_p(16), None, None,
+                                       C.c_void_p(16), C.c_void_p(16), None) == -1      # ld < n
+    with pytest.raises(L.RkError):
+        import torch
+        from roboticmanipulators_b200.robots import Fanuc165F
+        Fanuc165F().fk_jac_ik_batch(torch.zeros(4, 6, dtype=torch.float64))
     ch = L.RkChain()
     ch.ntok = 40
     assert lib.rk_chain_fk_jac_f64(C.byref(ch), None, 0, 0, 0, 0, None, None, None) == -3
