@@ -92,6 +92,11 @@ def _fanuc(tag):
     if tag not in _ROBOTS:
         if tag == "default":
             _ROBOTS[tag] = Fanuc165F(save=False)
+        elif tag == "custom":
+            # non-stock link lengths, joint offsets and directions (fanuc.py:72-96)
+            _ROBOTS[tag] = Fanuc165F(save=False, lengths=CUSTOM_LENGTHS,
+                                     offsets=np.array(CUSTOM_OFFSETS),
+                                     directions=np.array(CUSTOM_DIRECTIONS))
         else:
             T_base = np.array([[1, 0, 0, 500], [0, 1, 0, 300],
                                [0, 0, 1, -100], [0, 0, 0, 1]], dtype=float)
@@ -165,6 +170,25 @@ def _rng_in_limits(rng, lim_deg, n):
 
 FANUC_LIM_DEG = ((-185.0, 185.0), (-60.0, 76.0), (-156.0, 156.0),
                  (-360.0, 360.0), (-125.0, 125.0), (-360.0, 360.0))
+
+
+CUSTOM_LENGTHS = (300.0, 350.0, 280.0, 900.0, 200.0, 1100.0, 180.0)
+CUSTOM_OFFSETS = (0.1, -1.2, 1.4, 0.0, 0.2, -0.3)
+CUSTOM_DIRECTIONS = (1, -1, 1, -1, 1, 1)
+
+
+def gen_fanuc_custom(pool, out_dir, n_rand):
+    """FK + 12-branch IK of a Fanuc165F built with custom lengths / offsets / directions."""
+    rng = np.random.default_rng(5)
+    q = np.vstack([np.zeros((1, 6)), rng.uniform(-1.0, 1.0, size=(n_rand, 6))])
+    r = pool.map(_w_fanuc_fk_ik, [("custom", qi) for qi in q], chunksize=2)
+    robot = _fanuc("custom")
+    res = {"q": q, "T": np.array([x[0] for x in r]), "ik12": np.array([x[1] for x in r]),
+           "branches12": np.array(ALL_12), "lengths": np.array(CUSTOM_LENGTHS),
+           "offsets": np.array(CUSTOM_OFFSETS), "directions": np.array(CUSTOM_DIRECTIONS, dtype=float),
+           "d": np.array(robot.d), "dq": np.array(robot.dq)}
+    print("fanuc custom", len(q), flush=True, file=sys.__stdout__)
+    np.savez_compressed(os.path.join(out_dir, "fanuc_custom.npz"), **res)
 
 
 def gen_fanuc(pool, out_dir, n_rand):
@@ -556,7 +580,7 @@ def gen_poly(out_dir):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="fanuc,jac,chain,rrr,traj,calib,poly")
+    ap.add_argument("--only", default="fanuc,custom,jac,chain,rrr,traj,calib,poly")
     ap.add_argument("--jobs", type=int, default=os.cpu_count())
     ap.add_argument("--n-rand", type=int, default=56)
     ap.add_argument("--calib-rows", type=int, default=240)
@@ -576,6 +600,8 @@ def main():
         gen_rrr_rr(pool, args.out, args.n_rand)
     if "fanuc" in only:
         gen_fanuc(pool, args.out, args.n_rand)
+    if "custom" in only:
+        gen_fanuc_custom(pool, args.out, args.n_rand // 2)
     if "jac" in only:
         gen_fanuc_jac(pool, args.out, args.n_rand // 2)
     pool.close()

@@ -200,3 +200,37 @@ def test_no_out_of_range_writes(dtype, layout):
         dq = (logical(Qv, 48).reshape(n, 8, 6) - q_ref).double().cpu().numpy()
         dq[..., [3, 5]] = (dq[..., [3, 5]] + np.pi) % (2 * np.pi) - np.pi
         assert np.nanmax(np.abs(dq)) < (1e-9 if dtype == torch.float64 else 2e-2)
+
+
+def test_custom_constants_against_reference_golden(golden):
+    """Custom lengths / offsets / directions against vectors from the real reference
+    (tests/golden/fanuc_custom.npz): FK, and all 12 IK branches with the same masks."""
+    from roboticmanipulators_b200.robots import Fanuc165F
+    g = golden("fanuc_custom.npz")
+    robot = Fanuc165F(lengths=tuple(g["lengths"]), offsets=g["offsets"], directions=g["directions"])
+    assert float(robot.d) == float(g["d"]) and float(robot.dq) == float(g["dq"])
+    Tg, ref = g["T"], g["ik12"]
+    br = [tuple(int(v) for v in b) for b in g["branches12"]]
+    for layout in ("aos", "soa"):
+        T = robot.forward_kinematics_batch(dev(g["q"]), layout=layout).cpu().numpy()
+        assert np.max(np.abs(T[:, :3, :3] - Tg[:, :3, :3])) < 1e-12
+        assert np.max(np.abs(T[:, :3, 3] - Tg[:, :3, 3]) / np.maximum(1, np.abs(Tg[:, :3, 3]))) < 1e-12
+        qg, vg = robot.inverse_kinematics_batch(dev(Tg), br, layout=layout)
+        qg = qg.cpu().numpy()
+        assert np.array_equal(np.isnan(qg), np.isnan(ref))
+        d = qg - ref
+        d[..., [3, 5]] = (d[..., [3, 5]] + np.pi) % (2 * np.pi) - np.pi
+        assert np.nanmax(np.abs(d)) < 2e-10
+        nz = lambda a: np.any(np.abs(np.nan_to_num(a, nan=1.0)) > 1e-12, axis=-1)  # noqa: E731
+        assert np.array_equal(vg.cpu().numpy() & nz(qg), nz(ref))
+        # the canonical 8 through the fused single call agree with the same vectors
+        _, _, _, q8, v8 = robot.fk_jac_ik_batch(dev(g["q"]), layout=layout)
+        q8 = q8.cpu().numpy()
+        idx8 = [br.index(b) for b in O.CANONICAL_8]
+        d8 = q8 - ref[:, idx8]
+        d8[..., [3, 5]] = (d8[..., [3, 5]] + np.pi) % (2 * np.pi) - np.pi
+        # IK of the pose the GPU computed (differs from the golden T by rounding): same masks except
+        # where a joint sits within rounding of a limit, values to 1e-9
+        same = v8.cpu().numpy() == nz(ref[:, idx8])
+        assert same.mean() > 0.99
+        assert np.nanmax(np.abs(d8[same & v8.cpu().numpy()])) < 1e-8

@@ -95,6 +95,18 @@ def test_fanuc_ik_all_branches(golden):
     assert not v.any() and not q.any()
 
 
+def test_fanuc_custom_constants(golden):
+    """Non-stock lengths / offsets / directions (fanuc.py:72-96), run through the real reference."""
+    g = golden("fanuc_custom.npz")
+    c = O.FanucConst(lengths=g["lengths"], offsets=g["offsets"], directions=g["directions"])
+    assert c.d == float(g["d"]) and c.dq == float(g["dq"])
+    T = O.fanuc_fk(g["q"], c)
+    assert scaled(T[:, :3, :3], g["T"][:, :3, :3], 1.0) < 1e-14
+    assert scaled(T[:, :3, 3], g["T"][:, :3, 3]) < 1e-14
+    _check_ik(g["T"], g["ik12"], g["branches12"], c)
+    assert np.any(g["ik12"] != 0, axis=-1).mean() > 0.2      # the set does exercise valid branches
+
+
 def test_fanuc_ik_roundtrip_k1():
     rng = np.random.default_rng(7)
     c = O.FanucConst()
