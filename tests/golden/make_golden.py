@@ -366,6 +366,58 @@ def gen_rrr_rr(pool, out_dir, n_rand):
     print("rrr/rr done", flush=True, file=sys.__stdout__)
 
 
+ARM_T_BASE_ARGS = ("TxTyTzRzRyRx", [0.5, 0.3, -0.1, 0.3, -0.2, 0.1])
+ARM_T_TOOL_ARGS = ("TxTzRxRz", [0.1, -0.3, 0.25, -0.4])
+
+
+def _arm_bt():
+    from utils.robo_math import Transformation as tf
+    return (np.array(tf(*ARM_T_BASE_ARGS).transformation, dtype=float),
+            np.array(tf(*ARM_T_TOOL_ARGS).transformation, dtype=float))
+
+
+def _w_rrr_bt(q):
+    from robots.rrr_robot import RRRRobot
+    if "rrr_bt" not in _ROBOTS:
+        Tb, Tt = _arm_bt()
+        _ROBOTS["rrr_bt"] = RRRRobot(T_base=Tb, T_tool=Tt)
+    r = _ROBOTS["rrr_bt"]
+    T = r.forward_kinematics(list(q), plot=False)
+    out = np.zeros((4, 3))
+    for b, (m, k) in enumerate([(1, 1), (1, -1), (-1, 1), (-1, -1)]):
+        out[b] = r.inverse_kinematics(T, m=m, k=k)
+    return T, out
+
+
+def _w_rr_bt(q):
+    from robots.rr_robot import RRRobot
+    if "rr_bt" not in _ROBOTS:
+        Tb, Tt = _arm_bt()
+        _ROBOTS["rr_bt"] = RRRobot(T_base=Tb, T_tool=Tt, lengths=(0.5, 1.25), save=False)
+    r = _ROBOTS["rr_bt"]
+    T = r.forward_kinematics(list(q), plot=False)
+    out = np.zeros((2, 2))
+    for b, m in enumerate((1, -1)):
+        out[b] = r.inverse_kinematics(T, m=m)
+    return T, out
+
+
+def gen_arms_base_tool(pool, out_dir, n_rand):
+    """RRR and RR (lengths 0.5, 1.25) with rotating T_base / T_tool (robot.py:39-57)."""
+    rng = np.random.default_rng(6)
+    Tb, Tt = _arm_bt()
+    q3 = np.vstack([[np.pi / 2, 0, 0.2], rng.uniform(-np.pi, np.pi, size=(n_rand, 3))])
+    q2 = np.vstack([[0.3, 0.4], rng.uniform(-np.pi, np.pi, size=(n_rand, 2))])
+    r3 = pool.map(_w_rrr_bt, list(q3), chunksize=4)
+    r2 = pool.map(_w_rr_bt, list(q2), chunksize=4)
+    res = {"T_base": Tb, "T_tool": Tt, "rr_lengths": np.array((0.5, 1.25)),
+           "rrr_q": q3, "rrr_T": np.array([x[0] for x in r3]), "rrr_ik4": np.array([x[1] for x in r3]),
+           "rrr_branches": np.array([(1, 1), (1, -1), (-1, 1), (-1, -1)]),
+           "rr_q": q2, "rr_T": np.array([x[0] for x in r2]), "rr_ik2": np.array([x[1] for x in r2])}
+    np.savez_compressed(os.path.join(out_dir, "arms_base_tool.npz"), **res)
+    print("arms base/tool done", flush=True, file=sys.__stdout__)
+
+
 def gen_trajectories(out_dir):
     from utils.trapezoidal_generator import TrapezoidalGenerator
     from utils.trajectory_generator import TrajectoryGenerator
@@ -580,7 +632,7 @@ def gen_poly(out_dir):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="fanuc,custom,jac,chain,rrr,traj,calib,poly")
+    ap.add_argument("--only", default="fanuc,custom,jac,chain,rrr,armsbt,traj,calib,poly")
     ap.add_argument("--jobs", type=int, default=os.cpu_count())
     ap.add_argument("--n-rand", type=int, default=56)
     ap.add_argument("--calib-rows", type=int, default=240)
@@ -598,6 +650,8 @@ def main():
         gen_trajectories(args.out)
     if "rrr" in only:
         gen_rrr_rr(pool, args.out, args.n_rand)
+    if "armsbt" in only:
+        gen_arms_base_tool(pool, args.out, args.n_rand)
     if "fanuc" in only:
         gen_fanuc(pool, args.out, args.n_rand)
     if "custom" in only:

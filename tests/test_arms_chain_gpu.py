@@ -171,3 +171,22 @@ def test_arm_ik_special_targets(layout):
             assert np.array_equal(vb[:, b].cpu().numpy(), v_ref), m
             folded = np.linalg.norm(T2[:, :2, 3], axis=1) < 1e-6                     # same corner
             assert np.nanmax(np.abs(qb[:, b].cpu().numpy() - q_ref)[~folded]) < 1e-6, m
+
+
+def test_arms_base_tool_against_reference_golden(golden):
+    """RRR / RR behind rotating T_base and T_tool against vectors from the real reference."""
+    from roboticmanipulators_b200.robots import RRRRobot, RRRobot
+    g = golden("arms_base_tool.npz")
+    Tb, Tt = g["T_base"], g["T_tool"]
+    rrr = RRRRobot(T_base=Tb, T_tool=Tt)
+    rr = RRRobot(T_base=Tb, T_tool=Tt, lengths=tuple(g["rr_lengths"]), save=False)
+    for layout in ("aos", "soa"):
+        T = rrr.forward_kinematics_batch(dev(g["rrr_q"]), layout=layout)
+        assert np.max(np.abs(T.cpu().numpy() - g["rrr_T"])) < 1e-13
+        qb, _ = rrr.inverse_kinematics_batch(dev(g["rrr_T"]), [tuple(b) for b in g["rrr_branches"]],
+                                             layout=layout)
+        assert np.max(np.abs(qb.cpu().numpy() - g["rrr_ik4"])) < 1e-9
+        T = rr.forward_kinematics_batch(dev(g["rr_q"]), layout=layout)
+        assert np.max(np.abs(T.cpu().numpy() - g["rr_T"])) < 1e-13
+        qb, _ = rr.inverse_kinematics_batch(dev(g["rr_T"]), layout=layout)
+        assert np.max(np.abs(qb.cpu().numpy() - g["rr_ik2"])) < 1e-9

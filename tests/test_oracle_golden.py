@@ -160,6 +160,21 @@ def test_rrr_rr(golden):
             assert np.max(np.abs(q - g[f"{nm}_ik2"][:, b])) < 1e-9
 
 
+def test_arms_with_base_and_tool(golden):
+    """RRR / RR behind rotating T_base and T_tool (robot.py:39-57), from the real reference."""
+    g = golden("arms_base_tool.npz")
+    Tb, Tt = g["T_base"], g["T_tool"]
+    assert scaled(O.rrr_fk(g["rrr_q"], Tb, Tt), g["rrr_T"]) < 1e-14
+    for b, (m, k) in enumerate(g["rrr_branches"]):
+        q, _ = O.rrr_ik(g["rrr_T"], int(m), int(k), Tb, Tt)
+        assert np.max(np.abs(q - g["rrr_ik4"][:, b])) < 1e-9
+    ls = tuple(g["rr_lengths"])
+    assert scaled(O.rr_fk(g["rr_q"], Tb, Tt, ls=ls), g["rr_T"]) < 1e-14
+    for b, m in enumerate((1, -1)):
+        q, _ = O.rr_ik(g["rr_T"], m, Tb, Tt, ls=ls)
+        assert np.max(np.abs(q - g["rr_ik2"][:, b])) < 1e-9
+
+
 def test_trapezoid_coefficients(golden):
     g = golden("trajectories.npz")
     for (v, a, f, q0, qf), ref in zip(g["coef_cases"], g["coef_out"]):
