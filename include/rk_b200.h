@@ -126,6 +126,27 @@ int rk_fanuc_fk_jac_ik8_f32(const RkFanuc* robot, const float* q, int64_t n, int
                             int flags, float* T, float* J, float* det, float* q_out,
                             uint8_t* valid, void* stream);
 
+/* The same round trip on HOST arrays (the reference's NumPy arrays: fanuc_kinematics.py:26-54 keeps q,
+ * T and the IK answers in host memory).  The batch is streamed through the GPU in chunks over three
+ * streams (upload / kernels / download) and a ring of device staging slots owned by an RkHostPipe,
+ * one cudaMemcpyAsync per array and chunk, so that both directions of the host link stay busy; the
+ * link is the roofline of this call (48 B up, up to 816 B down per pose in FP64).
+ *   q, T, J, det, q_out, valid: HOST pointers with the layouts of rk_fanuc_fk_jac_ik8_* (RK_AOS:
+ *   the reference's shapes; RK_SOA: planes of pitch ld); page-locked memory gives full link speed,
+ *   pageable memory works at the driver's staging speed.  A NULL output is neither computed nor
+ *   shipped (q_out and valid come together).  The call returns when the host arrays are complete.
+ * A pipe belongs to the device that was current at creation and to one host thread at a time. */
+typedef struct RkHostPipe RkHostPipe;
+int rk_host_pipe_create(RkHostPipe** pipe, int64_t chunk_poses, int nslots /* 2..8 */);
+int rk_host_pipe_destroy(RkHostPipe* pipe);
+float rk_host_pipe_last_ms(const RkHostPipe* pipe); /* device time of the last call (first upload -> last download) */
+int rk_fanuc_fk_jac_ik8_host_f64(RkHostPipe* pipe, const RkFanuc* robot, const double* q, int64_t n,
+                                 int64_t ld, int flags, double* T, double* J, double* det,
+                                 double* q_out, uint8_t* valid);
+int rk_fanuc_fk_jac_ik8_host_f32(RkHostPipe* pipe, const RkFanuc* robot, const float* q, int64_t n,
+                                 int64_t ld, int flags, float* T, float* J, float* det, float* q_out,
+                                 uint8_t* valid);
+
 /* ------------------------------------------------------------------------------------
  * RRRRobot / RRRobot  (reference: robots/rrr_robot.py, robots/rr_robot.py)
  * ---------------------------------------------------------------------------------- */

@@ -223,8 +223,12 @@ def fanuc_jacobian(q, c=None, model_angles=False):
                                 c.T_base, c.T_tool)
 
 
-def fanuc_ik(T, m=1, k=1, w=0, c=None):
+def fanuc_ik(T, m=1, k=1, w=0, c=None, details=None):
     """Fanuc165F.inverse_kinematics (fanuc.py:196-302), batched.
+
+    `details` (a dict, optional) receives the quantities the reference compares against its
+    thresholds -- psi_cos (:237), A (:253), r_11 (:272), r_13 (:279) and the user angles before
+    the limit test (:292-297) -- so that tests can tell how far a target is from every decision.
 
     Returns (qs [...,6], valid [...]) where invalid rows are the reference's
     all-zero failure sentinel (:239, :300).  Quirks reproduced: k=-1 keeps
@@ -281,6 +285,8 @@ def fanuc_ik(T, m=1, k=1, w=0, c=None):
         qs = (qs - c.offsets) * c.directions            # :290
         out = ((qs < c.lim[:, 0]) | (qs > c.lim[:, 1])).any(axis=-1)  # :292-297
     valid = ~unreachable & ~out
+    if details is not None:
+        details.update(psi_cos=psi_cos, A=A, r_11=r_11, r_13=r_13, qs_user=qs, unreachable=unreachable)
     qs = np.where(valid[..., None], qs, 0.0)
     return qs, valid
 

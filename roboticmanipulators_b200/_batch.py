@@ -13,7 +13,7 @@ from . import _lib
 
 
 def detect_layout(x, ncomp):
-    """'soa' if x ([N, ncomp] logical) is a transposed view of a contiguous [ncomp, ld]."""
+    """'soa' if x ([N, ncomp] logical) is a transposed view of component planes [ncomp, ld]."""
     if x.dim() == 2 and x.shape[1] == ncomp and x.stride(0) == 1 and x.shape[0] > 1 \
             and x.stride(1) >= x.shape[0]:
         return "soa"
@@ -27,8 +27,12 @@ def prep_input(x, ncomp, layout, dtype):
     x = x.to(dtype).reshape(x.shape[0], ncomp)
     n = x.shape[0]
     if layout == "soa":
-        if n > 1 and x.stride(0) == 1 and x.stride(1) >= n:
-            return x, x.stride(1)
+        # Zero-copy only for DENSE planes (pitch == n).  The C ABI has ONE leading dimension for the
+        # inputs and the outputs of a call and every caller allocates its outputs with pitch n, so a
+        # column slice of wider planes (Q[:, lo:hi].t(), pitch > n) is compacted first: 8 bytes per
+        # component and pose, against the >= 100 bytes per pose every kernel writes.
+        if n > 1 and x.stride(0) == 1 and x.stride(1) == n:
+            return x, n
         store = x.t().contiguous()          # [ncomp, N]
         return store.t(), n
     return x.contiguous(), n

@@ -1,8 +1,41 @@
 // Library-level entry points: version, error strings, FP64 peak probe.
 #include "rk_common.cuh"
 
+#include <map>
+#include <tuple>
+
 namespace rk {
 thread_local cudaError_t g_last_cuda = cudaSuccess;
+
+int sm_count() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+  return sms;
+}
+
+int64_t cached_resident_ctas(const void* kernel, int block, size_t smem) {
+  static std::mutex mu;
+  static std::map<std::tuple<const void*, int, size_t, int>, int64_t> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const auto key = std::make_tuple(kernel, block, smem, dev);
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+  }
+  int sms = 148, per_sm = 1;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 1;
+  }
+  const int64_t v = (int64_t)sms * per_sm;
+  std::lock_guard<std::mutex> lock(mu);
+  cache[key] = v;
+  return v;
+}
 
 // 8 independent FMA chains per thread; no memory traffic inside the loop.
 __global__ void __launch_bounds__(256) dfma_probe_kernel(int64_t iters, double* sink) {
@@ -119,7 +152,7 @@ int rk_probe_dmma(int64_t iters, double* sink, int64_t* total_fma, void* stream)
 int rk_probe_stream(const double* in, int nin, double* out, int nout, int64_t n, int64_t ld, int vec,
                     int cs, int blocks_per_sm, void* stream) {
   if (n <= 0 || !in || !out) return RK_ERR_INVALID_ARG;
-  const int grid = 148 * (blocks_per_sm > 0 ? blocks_per_sm : 4);
+  const int grid = rk::sm_count() * (blocks_per_sm > 0 ? blocks_per_sm : 4);
   cudaStream_t st = (cudaStream_t)stream;
   if (vec == 2 && cs) rk::stream_probe_kernel<2, true><<<grid, 128, 0, st>>>(in, nin, out, nout, n, ld);
   else if (vec == 2) rk::stream_probe_kernel<2, false><<<grid, 128, 0, st>>>(in, nin, out, nout, n, ld);

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "rk_b200.h"
 
 namespace rk {
@@ -38,16 +40,15 @@ inline bool allow_dynamic_smem(K kernel, size_t bytes) {
 // Grid for a kernel that must stay resident for the whole problem (per-CTA accumulators that are
 // reduced at the end): enough CTAs to fill every SM at the kernel's occupancy, never more than
 // the work needs ("a multiple of 148 x resident CTAs per SM").
+// Occupancy of (kernel, block, smem) on the current device, looked up once: the runtime query
+// costs ~2 us and used to be made on every launch (at 1e4 poses the kernel itself runs 1.5 us).
+// Returns resident CTAs on the whole device (SM count x CTAs per SM).  Defined in rk_api.cu.
+int64_t cached_resident_ctas(const void* kernel, int block, size_t smem);
+
 template <typename K>
 inline int persistent_grid(K kernel, int block, size_t smem, int64_t work_items) {
-  int dev = 0, sms = 148, per_sm = 1;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess ||
-      per_sm < 1)
-    per_sm = 1;
   int64_t need = (work_items + block - 1) / block;
-  int64_t cap = (int64_t)sms * per_sm;
+  const int64_t cap = cached_resident_ctas(reinterpret_cast<const void*>(kernel), block, smem);
   if (need < 1) need = 1;
   return (int)(need < cap ? need : cap);
 }
@@ -408,16 +409,15 @@ inline bool make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_byte
                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   static EncodeFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static std::once_flag once;
+  std::call_once(once, [] {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
       fn = (EncodeFn)p;
     cudaGetLastError();
-  }
+  });
   if (!fn) return false;
   if (((uintptr_t)base & 15) || (pitch_bytes & 15) || ((uint64_t)box_cols * elem_bytes & 15)) return false;
   if (cols == 0 || cols > 0x7fffffffull || rows == 0) return false;

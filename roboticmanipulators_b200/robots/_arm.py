@@ -5,7 +5,7 @@ import numpy as np
 import torch
 
 from .. import _batch, _lib
-from .robot import Robot
+from .robot import Robot, launch
 
 
 class _SerialArm(Robot):
@@ -24,6 +24,9 @@ class _SerialArm(Robot):
     def _generate_value_pairs(self):
         ls = self._lengths()
         self._value_pairs = [(f"l_{i}", ls[i]) for i in range(len(ls))]
+
+    def _fingerprint(self):
+        return np.asarray(self._lengths(), dtype=np.float64).tobytes()
 
     def _struct(self):
         st = _lib.RkArm()
@@ -49,10 +52,8 @@ class _SerialArm(Robot):
         J = Js = None
         if jacobian:
             J, Js = _batch.alloc_out(n, (6, nq), layout, torch.float64, dev)
-        with torch.cuda.device(dev):
-            _lib.check(getattr(_lib.load(), self._fk_fn)(
-                C.byref(self._struct()), _lib.ptr(qs), n, ld, _batch.flags_of(layout),
-                _lib.ptr(Ts), _lib.ptr(Js), _lib.stream_ptr(dev)))
+        launch(getattr(_lib.load(), self._fk_fn), dev, self._cached_struct(), _lib.ptr(qs), n, ld,
+               _batch.flags_of(layout), _lib.ptr(Ts), _lib.ptr(Js))
         return (T, J) if jacobian else T
 
     def inverse_kinematics_batch(self, T, branches=None, *, layout="auto"):
@@ -78,11 +79,9 @@ class _SerialArm(Robot):
             qstore = torch.empty((n, nb, nq), dtype=torch.float64, device=dev)
             vstore = torch.empty((n, nb), dtype=torch.uint8, device=dev)
             qv, vv = qstore, vstore
-        with torch.cuda.device(dev):
-            _lib.check(getattr(_lib.load(), self._ik_fn)(
-                C.byref(self._struct()), _lib.ptr(Ts), n, ld, _batch.flags_of(layout), br, nb,
-                _lib.ptr(qstore), _lib.ptr(vstore), _lib.stream_ptr(dev)))
-        return qv, vv.bool()
+        launch(getattr(_lib.load(), self._ik_fn), dev, self._cached_struct(), _lib.ptr(Ts), n, ld,
+               _batch.flags_of(layout), br, nb, _lib.ptr(qstore), _lib.ptr(vstore))
+        return qv, vv.view(torch.bool)
 
     def forward_kinematics(self, q_values, plot=True):
         """Single pose -> 4x4 np.ndarray (1-element GPU batch; `plot` is ignored)."""

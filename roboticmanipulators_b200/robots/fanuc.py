@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from .. import _batch, _lib
-from .robot import Robot
+from .robot import Robot, launch
 
 #: the canonical 8 branches, in the order every batched IK call returns them
 CANONICAL_8 = tuple((m, k, w) for m in (1, -1) for k in (1, -1) for w in (0, 1))
@@ -19,6 +19,7 @@ CANONICAL_8 = tuple((m, k, w) for m in (1, -1) for k in (1, -1) for w in (0, 1))
 ALL_12 = tuple((m, k, w) for m in (1, -1) for k in (1, -1) for w in (0, 1, -1))
 
 _DTYPES = {torch.float64: "f64", torch.float32: "f32"}
+_HOST_PIPES = {}      # (device index, chunk, slots) -> RkHostPipe* (device staging ring + 3 streams)
 
 
 class Fanuc165F(Robot):
@@ -79,6 +80,11 @@ class Fanuc165F(Robot):
             (np.deg2rad(x[0]), np.deg2rad(x[1])) for x in self.qs_lim_deg)   # fanuc.py:110-111
 
     # ------------------------------------------------------------------ C-ABI struct
+    def _fingerprint(self):
+        return (np.asarray(self.qs_offsets, dtype=np.float64).tobytes()
+                + np.asarray(self.qs_directions, dtype=np.float64).tobytes()
+                + np.asarray(self._ls, dtype=np.float64).tobytes())
+
     def _struct(self):
         st = _lib.RkFanuc()
         _lib.fill(st.l, self._ls)
@@ -118,9 +124,8 @@ class Fanuc165F(Robot):
             det = torch.empty(n, dtype=q.dtype, device=dev)
         flags = _batch.flags_of(layout) | (_lib.RK_JAC_USER_ANGLES if user_angles else 0)
         fn = getattr(_lib.load(), "rk_fanuc_fk_jac_" + _DTYPES[q.dtype])
-        with torch.cuda.device(dev):
-            _lib.check(fn(C.byref(self._struct()), _lib.ptr(qs), n, ld, flags, _lib.ptr(Ts),
-                          _lib.ptr(Js), _lib.ptr(det), _lib.stream_ptr(dev)))
+        launch(fn, dev, self._cached_struct(), _lib.ptr(qs), n, ld, flags, _lib.ptr(Ts), _lib.ptr(Js),
+               _lib.ptr(det))
         out = (T,)
         if jacobian:
             out += (J,)
@@ -131,6 +136,8 @@ class Fanuc165F(Robot):
     def jacobian_batch(self, q, *, layout="auto", user_angles=False):
         """6x6 Jacobian and det J only (no pose traffic)."""
         _lib.require_cuda(q, "q")
+        if q.dtype not in _DTYPES:
+            raise TypeError("q must be float64 or float32")
         if layout == "auto":
             layout = _batch.detect_layout(q, 6)
         qs, ld = _batch.prep_input(q, 6, layout, q.dtype)
@@ -139,9 +146,8 @@ class Fanuc165F(Robot):
         det = torch.empty(n, dtype=q.dtype, device=dev)
         flags = _batch.flags_of(layout) | (_lib.RK_JAC_USER_ANGLES if user_angles else 0)
         fn = getattr(_lib.load(), "rk_fanuc_fk_jac_" + _DTYPES[q.dtype])
-        with torch.cuda.device(dev):
-            _lib.check(fn(C.byref(self._struct()), _lib.ptr(qs), n, ld, flags, None,
-                          _lib.ptr(Js), _lib.ptr(det), _lib.stream_ptr(dev)))
+        launch(fn, dev, self._cached_struct(), _lib.ptr(qs), n, ld, flags, None, _lib.ptr(Js),
+               _lib.ptr(det))
         return J, det
 
     def inverse_kinematics_batch(self, T, branches=CANONICAL_8, *, layout="auto"):
@@ -171,10 +177,9 @@ class Fanuc165F(Robot):
             vstore = torch.empty((n, nb), dtype=torch.uint8, device=dev)
             qv, vv = qstore, vstore
         fn = getattr(_lib.load(), "rk_fanuc_ik_" + _DTYPES[T.dtype])
-        with torch.cuda.device(dev):
-            _lib.check(fn(C.byref(self._struct()), _lib.ptr(Ts), n, ld, _batch.flags_of(layout),
-                          br, nb, _lib.ptr(qstore), _lib.ptr(vstore), _lib.stream_ptr(dev)))
-        return qv, vv.bool()
+        launch(fn, dev, self._cached_struct(), _lib.ptr(Ts), n, ld, _batch.flags_of(layout), br, nb,
+               _lib.ptr(qstore), _lib.ptr(vstore))
+        return qv, vv.view(torch.bool)
 
     def fk_jac_ik_batch(self, q, *, layout="auto", user_angles=False):
         """forward_kinematics_batch(q, jacobian=True, measure=True) followed by
@@ -202,11 +207,96 @@ class Fanuc165F(Robot):
             qv, vv = qstore, vstore
         flags = _batch.flags_of(layout) | (_lib.RK_JAC_USER_ANGLES if user_angles else 0)
         fn = getattr(_lib.load(), "rk_fanuc_fk_jac_ik8_" + _DTYPES[q.dtype])
+        launch(fn, dev, self._cached_struct(), _lib.ptr(qs), n, ld, flags, _lib.ptr(Ts), _lib.ptr(Js),
+               _lib.ptr(det), _lib.ptr(qstore), _lib.ptr(vstore))
+        return T, J, det, qv, vv.view(torch.bool)
+
+    _STREAM_OUT = {"T": (4, 4), "J": (6, 6), "det": (), "q_ik": (8, 6), "valid": (8,)}
+
+    def fk_jac_ik_stream(self, q, *, want=("T", "J", "det", "q_ik", "valid"), out=None,
+                         chunk=1 << 16, slots=3, layout="aos", user_angles=False, device=None):
+        """The round trip of fk_jac_ik_batch on HOST arrays (NumPy arrays or CPU torch tensors, as
+        the reference keeps them), streamed through the GPU: the batch is cut in chunks that are
+        uploaded, computed and downloaded on three streams, so both directions of the host link
+        are busy all the time -- the link, not the GPU, is the roofline of this call (48 B up and
+        up to 816 B down per pose in float64).
+
+        q: [N, 6] float64 / float32 on the host (page-locked memory -- `torch.empty(...,
+        pin_memory=True)` -- gives full link speed).  `want` selects what is computed AND shipped
+        (e.g. ("q_ik", "valid") moves 392 B per pose instead of 816).  `out` may hold preallocated
+        (pinned) result tensors by name; missing ones are allocated page-locked.  layout="soa":
+        q is a [N, 6] view of [6, N] planes and results are such views too.
+        Returns a dict name -> host tensor with the reference's shapes (T [N,4,4], J [N,6,6],
+        det [N], q_ik [N,8,6], valid [N,8] bool); complete when the call returns."""
+        if isinstance(q, np.ndarray):
+            q = torch.from_numpy(q)
+        if not isinstance(q, torch.Tensor) or q.is_cuda:
+            raise _lib.RkError("fk_jac_ik_stream takes HOST arrays; use fk_jac_ik_batch for CUDA tensors")
+        if q.dtype not in _DTYPES:
+            raise TypeError("q must be float64 or float32")
+        unknown = set(want) - set(self._STREAM_OUT)
+        if unknown or not want:
+            raise ValueError(f"want must name some of {sorted(self._STREAM_OUT)}")
+        n = q.shape[0]
+        soa = layout == "soa"
+        if layout not in ("aos", "soa"):
+            raise ValueError("layout must be 'aos' or 'soa'")
+        q = q.reshape(n, 6)
+        if soa:
+            if not (q.stride(0) == 1 and (n == 1 or q.stride(1) >= n)):
+                q = q.t().contiguous().t()
+            ld = q.stride(1) if n > 1 else 1
+        else:
+            q, ld = q.contiguous(), n
+        names = set(want)
+        if names & {"q_ik", "valid"}:
+            names |= {"q_ik", "valid"}
+        res, ptrs = {}, {}
+        for name, shape in self._STREAM_OUT.items():
+            if name not in names:
+                ptrs[name] = None
+                continue
+            dt = torch.uint8 if name == "valid" else q.dtype
+            t = None if out is None else out.get(name)
+            ncomp = int(np.prod(shape)) if shape else 1
+            if t is not None:
+                if t.dtype == torch.bool:
+                    t = t.view(torch.uint8)
+                ok = (t.dtype == dt and not t.is_cuda and t.numel() == n * ncomp and
+                      (t.is_contiguous() if not soa else True))
+                if not ok or soa:
+                    raise ValueError(f"out[{name!r}] must be a contiguous host tensor of {n}x{shape} {dt} (AOS)")
+                store = t
+            elif soa:
+                store = torch.empty((ncomp, ld), dtype=dt, pin_memory=True)
+            else:
+                store = torch.empty((n, *shape), dtype=dt, pin_memory=True)
+            ptrs[name] = C.c_void_p(store.data_ptr())
+            if soa:
+                view = store[:, :n].view(*shape, n) if shape else store[0, :n]
+                view = view.permute(len(shape), *range(len(shape))) if shape else view
+            else:
+                view = store.view(n, *shape) if shape else store.view(n)
+            res[name] = view.view(torch.bool) if name == "valid" else view
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        pipe = self._host_pipe(dev, int(chunk), int(slots))
+        flags = (_lib.RK_SOA if soa else _lib.RK_AOS) | (_lib.RK_JAC_USER_ANGLES if user_angles else 0)
+        fn = getattr(_lib.load(), "rk_fanuc_fk_jac_ik8_host_" + _DTYPES[q.dtype])
         with torch.cuda.device(dev):
-            _lib.check(fn(C.byref(self._struct()), _lib.ptr(qs), n, ld, flags, _lib.ptr(Ts),
-                          _lib.ptr(Js), _lib.ptr(det), _lib.ptr(qstore), _lib.ptr(vstore),
-                          _lib.stream_ptr(dev)))
-        return T, J, det, qv, vv.bool()
+            _lib.check(fn(pipe, self._cached_struct(), C.c_void_p(q.data_ptr()), n, ld, flags,
+                          ptrs["T"], ptrs["J"], ptrs["det"], ptrs["q_ik"], ptrs["valid"]))
+        return {k: res[k] for k in want}
+
+    def _host_pipe(self, dev, chunk, slots):
+        """The (device, chunk, slots) staging pipe of this process, created on first use."""
+        key = (dev.index, chunk, slots)
+        pipe = _HOST_PIPES.get(key)
+        if pipe is None:
+            pipe = C.c_void_p()
+            with torch.cuda.device(dev):
+                _lib.check(_lib.load().rk_host_pipe_create(C.byref(pipe), chunk, slots))
+            _HOST_PIPES[key] = pipe
+        return pipe
 
     # ------------------------------------------------------------- reference methods
     def forward_kinematics(self, q_values, plot=True):

@@ -3,12 +3,20 @@ from abc import ABC, abstractmethod
 
 import numpy as np
 import sympy as sp
+import torch
 
 from .. import _lib
 
 
 class Robot(ABC):
-    """Abstract robot.  `epsilon` is the float-equality threshold (robot.py:17)."""
+    """Abstract robot.  `epsilon` is the float-equality threshold (robot.py:17).
+
+    The batched entry points hand the kernels a small constant block (RkFanuc / RkArm, include/
+    rk_b200.h).  Building it means converting SymPy matrices to NumPy and inverting them (~80 us),
+    so it is built once and kept: assigning ANY attribute of the robot drops it, and a cheap
+    fingerprint of the array-valued attributes catches in-place edits (`robot.qs_offsets[0] = ..`).
+    T_base / T_tool are immutable SymPy matrices for the same reason: replace them (set_transforms
+    or plain assignment), do not edit their entries."""
 
     epsilon = 1e-5
 
@@ -20,11 +28,16 @@ class Robot(ABC):
     def inverse_kinematics(self, T):
         """Joint values from pose T."""
 
+    def __setattr__(self, name, value):
+        object.__setattr__(self, name, value)
+        if name != "_c_struct":
+            object.__setattr__(self, "_c_struct", None)
+
     def set_transforms(self, T_base=None, T_tool=None):
         """World->base and flange->tool transforms; identity when None
         (robot.py:39-57).  Kept as sympy matrices like the reference."""
-        self.T_base = sp.eye(4) if T_base is None else sp.Matrix(T_base)
-        self.T_tool = sp.eye(4) if T_tool is None else sp.Matrix(T_tool)
+        self.T_base = sp.ImmutableMatrix(sp.eye(4) if T_base is None else sp.Matrix(T_base))
+        self.T_tool = sp.ImmutableMatrix(sp.eye(4) if T_tool is None else sp.Matrix(T_tool))
 
     def set_lengths(self, lengths):
         self._ls = (0.8, 0.8) if lengths is None else lengths   # robot.py:59-63
@@ -40,3 +53,32 @@ class Robot(ABC):
         _lib.fill(st.T_tool_inv, _lib.xf12(np.linalg.inv(Tt)))
         st.has_base = 0 if _lib.is_identity(Tb) else 1
         st.has_tool = 0 if _lib.is_identity(Tt) else 1
+
+    def _fingerprint(self):
+        """Bytes of the array-valued constants a caller may edit in place."""
+        return b""
+
+    def _struct(self):
+        """Build the C-ABI constant block from the current attributes (no caching)."""
+        raise NotImplementedError
+
+    def _cached_struct(self):
+        """(ctypes.byref of) the constant block, rebuilt only when an attribute changed."""
+        c = self.__dict__.get("_c_struct")
+        key = (self.epsilon, self._fingerprint())
+        if c is None or c[0] != key or c[1] is not self.T_base or c[2] is not self.T_tool:
+            st = self._struct()
+            import ctypes as C
+            c = (key, self.T_base, self.T_tool, st, C.byref(st))
+            object.__setattr__(self, "_c_struct", c)
+        return c[4]
+
+
+def launch(fn, dev, *args):
+    """Call a C-ABI entry point with `dev` current (kernels launch on the current device) and the
+    current torch stream of that device appended as the last argument."""
+    if dev.index is None or dev.index == torch.cuda.current_device():
+        _lib.check(fn(*args, torch.cuda.current_stream().cuda_stream))
+    else:
+        with torch.cuda.device(dev):
+            _lib.check(fn(*args, torch.cuda.current_stream(dev).cuda_stream))

@@ -255,7 +255,9 @@ class ModelCalibrator(object):
         return q.contiguous(), p
 
     def _workspace(self, device):
-        key = str(device)
+        """Reduction workspace (CTA partials + ticket counter).  One per (device, stream): two
+        streams of one device must not share the counter."""
+        key = (str(device), torch.cuda.current_stream(device).cuda_stream)
         if key not in self._ws:
             nbytes = int(_lib.load().rk_calib_workspace_bytes())
             self._ws[key] = torch.zeros(nbytes, dtype=torch.uint8, device=device)
@@ -366,34 +368,36 @@ class ModelCalibrator(object):
         return T_base, T_tools
 
     def residual_sums(self, qs, pts, T_base, T_tools, parameters=None, process_group=None):
-        """[sum dist^2, sum dx^2, sum dy^2, sum dz^2, max dist, max|dx|, max|dy|, max|dz|]
-        (CUDA tensor) over this rank's measurements, all-reduced when distributed."""
+        """[sum dist^2, sum dx^2, sum dy^2, sum dz^2, max dist, max|dx|, max|dy|, max|dz|,
+        number of measured points] (CUDA tensor) over this rank's measurements; with
+        torch.distributed initialised the sums and the point count are all-reduced with SUM and the
+        maxima with MAX, so every rank holds the statistics of the whole data set."""
         q, p = self._device_data(qs, pts)
         model = self._compile(parameters, T_base, T_tools)
-        out = torch.empty(8, dtype=torch.float64, device=q.device)
+        out = torch.empty(9, dtype=torch.float64, device=q.device)
         ws = self._workspace(q.device)
         with torch.cuda.device(q.device):
             _lib.check(_lib.load().rk_calib_eval_f64(
                 C.byref(model), _lib.ptr(q), _lib.ptr(p), q.shape[0], _lib.ptr(out), _lib.ptr(ws),
                 ws.numel(), _lib.stream_ptr(q.device)))
+        out[8] = float(q.shape[0] * (p.shape[1] // 3))
+        return self._reduce_residual_sums(out, process_group)
+
+    def _reduce_residual_sums(self, out, process_group=None):
+        """Cross-rank step of `residual_sums`: entries 0-3 and 8 (the sums and the point count)
+        reduce with SUM, entries 4-7 (the maxima) with MAX."""
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and process_group is not False:
-            sums, maxs = out[:4].clone(), out[4:].clone()
+            sums, maxs = torch.cat([out[:4], out[8:]]), out[4:8].clone()
             self._allreduce(sums, dist.ReduceOp.SUM, process_group)
             self._allreduce(maxs, dist.ReduceOp.MAX, process_group)
-            out = torch.cat([sums, maxs])
+            out = torch.cat([sums[:4], maxs, sums[4:]])
         return out
 
-    def evaluate(self, qs, pts, T_base, T_tools, process_group=None, count=None):
-        """RMS and maximum residuals (model_calibration.py:456-539).  `count` overrides
-        the number of measured points (needed when the measurements are sharded)."""
-        if self._parameters is None:
-            print(self._no_model_msg)
-            return [], []
-        o = self.residual_sums(qs, pts, T_base, T_tools, process_group=process_group).cpu().numpy()
-        shape = tuple(pts.shape)
-        n = count if count is not None else shape[0] * (int(np.prod(shape[1:])) // 3)
-        result = {
+    @staticmethod
+    def _metrics(o, n):
+        """The eight numbers of evaluate (model_calibration.py:507-521) from the reduced sums."""
+        return {
             "distance_rms": float(np.sqrt(o[0] / n)),
             "x_rms": float(np.sqrt(o[1] / n)),
             "y_rms": float(np.sqrt(o[2] / n)),
@@ -403,6 +407,17 @@ class ModelCalibrator(object):
             "max_diff_y": float(o[6]),
             "max_diff_z": float(o[7]),
         }
+
+    def evaluate(self, qs, pts, T_base, T_tools, process_group=None, count=None):
+        """RMS and maximum residuals (model_calibration.py:456-539).  When the measurements are
+        sharded over the ranks of torch.distributed the residual sums AND the number of measured
+        points are all-reduced, so the RMS values are those of the whole data set on every rank
+        (`count` overrides the divisor, e.g. for replicated data with process_group=False)."""
+        if self._parameters is None:
+            print(self._no_model_msg)
+            return [], []
+        o = self.residual_sums(qs, pts, T_base, T_tools, process_group=process_group).cpu().numpy()
+        result = self._metrics(o, count if count is not None else o[8])
         if self.verbose:
             print()
             print(f"Distance RMS (mm): {result['distance_rms']}")

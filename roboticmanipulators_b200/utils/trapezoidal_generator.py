@@ -102,8 +102,21 @@ class TrapezoidalGenerator():
             raise ValueError("Not enough points. Please, increase n")
         return (x[0, :L].cpu().numpy() for x in (q, dq, ddq, t))
 
+    @staticmethod
+    def _flat_only(t_1, tau, n):
+        """Number of constant-velocity samples when the acceleration segment is EMPTY
+        (int(step * t_1) == 0, trapezoidal_generator.py:222-226), else None.  get_q / get_dq raise in
+        that case (:142, :180) but get_t / get_ddq do not: they return the flat segment alone."""
+        step = n / (tau + t_1)
+        if int(step * t_1) != 0:
+            return None
+        return int(step * (tau - t_1))
+
     def get_t(self, t_1, tau, n):
         """Time samples (trapezoidal_generator.py:110-123)."""
+        Lf = self._flat_only(t_1, tau, n)
+        if Lf is not None:
+            return np.linspace(t_1, tau, Lf)
         return list(self._sample(t_1, tau, n))[3]
 
     def get_q(self, t_1, tau, n):
@@ -116,4 +129,7 @@ class TrapezoidalGenerator():
 
     def get_ddq(self, t_1, tau, n):
         """Acceleration samples (:188-206)."""
+        Lf = self._flat_only(t_1, tau, n)
+        if Lf is not None:
+            return np.zeros(Lf)
         return list(self._sample(t_1, tau, n))[2]

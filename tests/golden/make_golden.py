@@ -13,7 +13,8 @@ this repo) with three non-arithmetic shims:
   2. stub matplotlib / matplotlib.pyplot       (plotting side-car only)
   3. delete robots/data/*.pkl, data/*.pkl      (unpickle to zero matrices)
 
-Usage:  python tests/golden/make_golden.py [--only fk,ik,...] [--jobs 8]
+Usage:  python tests/golden/make_golden.py [--only fanuc,jac,...] [--jobs 8]
+        python tests/golden/make_golden.py --only config1 [--config1-n 10000]   (config-1 set, ~10 min)
 """
 import argparse
 import os
@@ -166,6 +167,38 @@ def _w_fanuc_jac(args):
 def _rng_in_limits(rng, lim_deg, n):
     lim = np.deg2rad(np.array(lim_deg))
     return rng.uniform(lim[:, 0], lim[:, 1], size=(n, lim.shape[0]))
+
+
+def _w_config1(args):
+    """One config-1 pose through the real reference: FK, all 12 (m, k, w) IK branches of that
+    pose, and calculate_numerically's 6x6 Jacobian at the model angles q' = q*dir + off."""
+    q = args
+    T, ik = _w_fanuc_fk_ik(("default", q))
+    off = np.array([0.0, -np.pi / 2, np.pi / 2, 0.0, 0.0, 0.0])
+    dirs = np.array([1.0, 1.0, -1.0, -1.0, -1.0, -1.0])
+    J = _w_fanuc_jac(("default", q * dirs + off))
+    return T, ik, J
+
+
+def gen_config1(pool, out_dir, n):
+    """BASELINE.json configs[0]: FK -> IK round trip + Jacobian on n (1e4) uniform-in-limits joint
+    vectors, seed 0, through the REAL reference.  Stored: q, T[:, :3, :] (the 4th row is 0 0 0 1),
+    the 12-branch IK answers (zeros = the reference's failure sentinel) and J."""
+    rng = np.random.default_rng(0)
+    q = _rng_in_limits(rng, FANUC_LIM_DEG, n)
+    T = np.zeros((n, 3, 4))
+    ik = np.zeros((n, 12, 6))
+    J = np.zeros((n, 6, 6))
+    done = 0
+    for i, (Ti, iki, Ji) in enumerate(pool.imap(_w_config1, list(q), chunksize=8)):
+        assert np.array_equal(Ti[3], [0, 0, 0, 1])
+        T[i], ik[i], J[i] = Ti[:3], iki, Ji
+        done += 1
+        if done % 500 == 0:
+            print("config1", done, "/", n, flush=True, file=sys.__stdout__)
+    np.savez_compressed(os.path.join(out_dir, "fanuc_config1.npz"), q=q, T34=T, ik12=ik, J=J,
+                        branches12=np.array(ALL_12), seed=np.array(0))
+    print("config1 done", n, flush=True, file=sys.__stdout__)
 
 
 FANUC_LIM_DEG = ((-185.0, 185.0), (-60.0, 76.0), (-156.0, 156.0),
@@ -637,6 +670,8 @@ def main():
     ap.add_argument("--n-rand", type=int, default=56)
     ap.add_argument("--calib-rows", type=int, default=240)
     ap.add_argument("--out", default=HERE)
+    ap.add_argument("--config1-n", type=int, default=10000,
+                    help="poses of the config-1 set (only with --only config1; ~10 min on 8 cores)")
     args = ap.parse_args()
     only = set(args.only.split(","))
     dst = prepare_reference()
@@ -658,6 +693,8 @@ def main():
         gen_fanuc_custom(pool, args.out, args.n_rand // 2)
     if "jac" in only:
         gen_fanuc_jac(pool, args.out, args.n_rand // 2)
+    if "config1" in only:
+        gen_config1(pool, args.out, args.config1_n)
     pool.close()
     if "calib" in only:
         gen_calibration(args.out, args.calib_rows)

@@ -54,7 +54,19 @@ def _worker(rank, world, port, q):
     # the max-type metrics of evaluate() reduce with MAX
     mx = torch.tensor([float(rank + 1)])
     mc._allreduce(mx, dist.ReduceOp.MAX, None)
-    q.put((rank, params, float(np.abs(Hs - g["J_sum"]).max() / np.abs(g["J_sum"]).max()), float(mx)))
+    # evaluate() on sharded measurements: the residual sums AND the point count are summed over the
+    # ranks, the maxima are MAX-reduced; every rank then reports the whole data set's RMS values
+    diffs = []
+    for j, Tt in enumerate(g["T_tools"]):
+        T = O.calib_pose(model, g["qs"][lo:hi], g["params"], g["T_base"], Tt)
+        diffs.append(g["pts"][lo:hi, 3 * j:3 * j + 3] - T[:, :3, 3])
+    d = np.abs(np.concatenate(diffs))
+    nrm = np.linalg.norm(d, axis=1)
+    local = torch.tensor([(nrm * nrm).sum(), (d[:, 0]**2).sum(), (d[:, 1]**2).sum(), (d[:, 2]**2).sum(),
+                          nrm.max(), d[:, 0].max(), d[:, 1].max(), d[:, 2].max(), float(len(d))])
+    red = mc._reduce_residual_sums(local).numpy()
+    metrics = mc._metrics(red, red[8])
+    q.put((rank, params, float(np.abs(Hs - g["J_sum"]).max() / np.abs(g["J_sum"]).max()), float(mx), metrics))
     dist.destroy_process_group()
 
 
@@ -70,8 +82,11 @@ def test_two_rank_normal_equation_allreduce():
         p.join(timeout=60)
         assert p.exitcode == 0
     g = np.load(os.path.join(ROOT, "tests", "golden", "calibration.npz"))
-    for rank, params, herr, mx in results:
+    want = dict(zip([str(k) for k in g["eval_keys"]], g["eval_after_params"]))
+    for rank, params, herr, mx, metrics in results:
         assert herr < 1e-12
         assert np.max(np.abs(params - g["params"])) < 1e-9     # every rank solves the same system
         assert mx == 2.0
+        for k, v in want.items():                               # the reference's evaluate() on all 240 rows
+            assert abs(metrics[k] - v) < 1e-9, (k, metrics[k], v)
     assert np.array_equal(results[0][1], results[1][1])        # bit-identical across ranks

@@ -127,20 +127,14 @@ def test_tool_base_other_tool_counts(golden):
 
 def test_ik_f32_with_base_and_tool(golden):
     from roboticmanipulators_b200.robots import Fanuc165F
+    from test_fanuc_gpu import _check_ik_f32
     g = golden("fanuc_fk_ik.npz")
     robot = Fanuc165F(T_base=g["rotated_T_base"], T_tool=g["rotated_T_tool"])
     c = O.FanucConst(g["rotated_T_base"], g["rotated_T_tool"])
     rng = np.random.default_rng(5)
-    q = rng.uniform(c.lim[:, 0], c.lim[:, 1], size=(4096, 6))
-    T32 = torch.tensor(O.fanuc_fk(q, c), device="cuda", dtype=torch.float32)
+    q = rng.uniform(c.lim[:, 0], c.lim[:, 1], size=(8192, 6))
     for layout in ("aos", "soa"):
-        qb, vb = robot.inverse_kinematics_batch(T32, layout=layout)
-        q_ref, v_ref = O.fanuc_ik_branches(T32.cpu().numpy().astype(np.float64), O.CANONICAL_8, c)
-        assert (vb.cpu().numpy() == v_ref).mean() > 0.99
-        both = vb.cpu().numpy() & v_ref
-        d = qb.cpu().numpy().astype(np.float64) - q_ref
-        d[..., [3, 5]] = (d[..., [3, 5]] + np.pi) % (2 * np.pi) - np.pi
-        assert np.nanpercentile(np.abs(d[both]), 99) < 5e-3
+        _check_ik_f32(robot, c, O.fanuc_fk(q, c), layout)
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
@@ -208,6 +202,7 @@ def test_custom_constants_against_reference_golden(golden):
     from roboticmanipulators_b200.robots import Fanuc165F
     g = golden("fanuc_custom.npz")
     robot = Fanuc165F(lengths=tuple(g["lengths"]), offsets=g["offsets"], directions=g["directions"])
+    c_custom = O.FanucConst(lengths=tuple(g["lengths"]), offsets=g["offsets"], directions=g["directions"])
     assert float(robot.d) == float(g["d"]) and float(robot.dq) == float(g["dq"])
     Tg, ref = g["T"], g["ik12"]
     br = [tuple(int(v) for v in b) for b in g["branches12"]]
@@ -218,9 +213,13 @@ def test_custom_constants_against_reference_golden(golden):
         qg, vg = robot.inverse_kinematics_batch(dev(Tg), br, layout=layout)
         qg = qg.cpu().numpy()
         assert np.array_equal(np.isnan(qg), np.isnan(ref))
-        d = qg - ref
-        d[..., [3, 5]] = (d[..., [3, 5]] + np.pi) % (2 * np.pi) - np.pi
-        assert np.nanmax(np.abs(d)) < 2e-10
+        import ikcond
+        with np.errstate(all="ignore"):
+            _, _, det = ikcond.ik_details(Tg, br, c_custom)
+        tol, _ = ikcond.ik_tolerance(ref, det, base=2e-12)
+        err = ikcond.ik_diff(qg, ref.copy())
+        live = vg.cpu().numpy()[..., None] & ~np.isnan(ref)
+        assert not np.any(live & (err > tol)), float(np.nanmax(np.where(live, err / tol, 0)))
         nz = lambda a: np.any(np.abs(np.nan_to_num(a, nan=1.0)) > 1e-12, axis=-1)  # noqa: E731
         assert np.array_equal(vg.cpu().numpy() & nz(qg), nz(ref))
         # the canonical 8 through the fused single call agree with the same vectors
@@ -234,3 +233,79 @@ def test_custom_constants_against_reference_golden(golden):
         same = v8.cpu().numpy() == nz(ref[:, idx8])
         assert same.mean() > 0.99
         assert np.nanmax(np.abs(d8[same & v8.cpu().numpy()])) < 1e-8
+
+
+def test_soa_column_slice_of_wider_planes_is_safe():
+    """Q[:, lo:hi].t() -- the per-rank shard of wider SOA planes -- has a plane
+    pitch larger than its length.  The outputs are allocated dense, so the wrappers must not hand
+    the input's pitch to the kernel as the output pitch: results equal those of a dense copy and
+    nothing is written outside the result tensors (the caching allocator would place such writes in
+    neighbouring live tensors, hence the sentinels around the calls)."""
+    from roboticmanipulators_b200.robots import Fanuc165F, RRRRobot
+    from roboticmanipulators_b200.utils.robo_math import Transformation
+    robot, c = Fanuc165F(), O.FanucConst()
+    rng = np.random.default_rng(11)
+    N, lo, hi = 5000, 1237, 3290
+    Q = dev(rng.uniform(c.lim[:, 0], c.lim[:, 1], size=(N, 6)).T.copy())      # [6, N] planes
+    view = Q[:, lo:hi].t()                                                      # [n, 6], pitch N > n
+    dense = view.contiguous()
+    sentinels = [torch.full((1 << 16,), 3.25, dtype=torch.float64, device="cuda") for _ in range(4)]
+    T, J, det, qik, val = robot.fk_jac_ik_batch(view)
+    T2, J2, det2 = robot.forward_kinematics_batch(view, jacobian=True, measure=True)
+    q3, v3 = robot.inverse_kinematics_batch(T2)
+    more = [torch.full((1 << 16,), 3.25, dtype=torch.float64, device="cuda") for _ in range(4)]
+    Td, Jd, detd, qikd, vald = robot.fk_jac_ik_batch(dense, layout="aos")
+    torch.cuda.synchronize()
+    for a, b in ((T, Td), (J, Jd), (det, detd), (T2, Td), (J2, Jd), (det2, detd)):
+        assert a.shape == b.shape and (a - b).abs().max().item() < 1e-9
+    assert torch.equal(val, vald) and torch.equal(v3, vald)
+    assert all(bool((s == 3.25).all()) for s in sentinels + more)
+    # the same pattern through the arms and the generic chain
+    rrr = RRRRobot()
+    Q3 = dev(rng.uniform(-3, 3, size=(3, N)))
+    Ta, Ja = rrr.forward_kinematics_batch(Q3[:, lo:hi].t(), jacobian=True)
+    Tb, Jb = rrr.forward_kinematics_batch(Q3[:, lo:hi].t().contiguous(), jacobian=True, layout="aos")
+    assert (Ta - Tb).abs().max().item() < 1e-12 and (Ja - Jb).abs().max().item() < 1e-12
+    V = dev(rng.uniform(-2, 2, size=(4, N)))
+    Tc = Transformation.batch("RzTxRzTx", V[:, lo:hi].t())
+    Tdn = Transformation.batch("RzTxRzTx", V[:, lo:hi].t().contiguous(), layout="aos")
+    torch.cuda.synchronize()
+    assert (Tc - Tdn).abs().max().item() < 1e-12
+    assert all(bool((s == 3.25).all()) for s in sentinels + more)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_host_stream_matches_device_batch(dtype):
+    """Fanuc165F.fk_jac_ik_stream (rk_fanuc_fk_jac_ik8_host_*): host arrays streamed in chunks over
+    three streams give bit-identical results to the device-resident call, for ragged sizes, chunk
+    sizes that do and do not divide n, pinned and pageable inputs, output selection and SOA planes."""
+    from roboticmanipulators_b200.robots import Fanuc165F
+    robot, c = Fanuc165F(), O.FanucConst()
+    rng = np.random.default_rng(21)
+    for n, chunk in ((1, 64), (33, 32), (1000, 256), (5000, 4096), (70001, 1 << 14)):
+        q = torch.tensor(rng.uniform(c.lim[:, 0], c.lim[:, 1], size=(n, 6))).to(dtype)
+        ref = robot.fk_jac_ik_batch(q.cuda(), layout="aos")
+        names = ("T", "J", "det", "q_ik", "valid")
+        for pinned in (True, False):
+            hq = q.pin_memory() if pinned else q.numpy()
+            res = robot.fk_jac_ik_stream(hq, chunk=chunk)
+            for name, r in zip(names, ref):
+                assert not res[name].is_cuda
+                assert torch.equal(res[name], r.cpu()), (n, chunk, name)
+        # output selection: only the IK answers travel; preallocated result buffers are filled in place
+        outs = {"q_ik": torch.full((n, 8, 6), -5.0, dtype=dtype).pin_memory(),
+                "valid": torch.zeros((n, 8), dtype=torch.bool).pin_memory()}
+        res = robot.fk_jac_ik_stream(q.pin_memory(), want=("q_ik", "valid"), out=outs, chunk=chunk)
+        assert set(res) == {"q_ik", "valid"} and res["q_ik"].data_ptr() == outs["q_ik"].data_ptr()
+        assert torch.equal(res["q_ik"], ref[3].cpu()) and torch.equal(res["valid"], ref[4].cpu())
+        res = robot.fk_jac_ik_stream(q.pin_memory(), want=("J", "det"), chunk=chunk)
+        assert torch.equal(res["J"], ref[1].cpu()) and torch.equal(res["det"], ref[2].cpu())
+        # component-major host planes
+        planes = q.t().contiguous()
+        ref_soa = robot.fk_jac_ik_batch(planes.cuda().t(), layout="soa")
+        res = robot.fk_jac_ik_stream(planes.t(), layout="soa", chunk=chunk)
+        for name, r in zip(names, ref_soa):
+            assert res[name].shape == r.shape
+            assert torch.equal(res[name], r.cpu()), (n, chunk, name, "soa")
+    with pytest.raises(Exception):
+        robot.fk_jac_ik_stream(q.cuda())

@@ -279,3 +279,31 @@ def test_polynomial_profiles(golden):
         assert np.array_equal(O.poly_sample(c, 0, g["t0"][i], g["tf"][i], 64), g["q"][i])
         assert np.array_equal(O.poly_sample(c, 1, g["t0"][i], g["tf"][i], 64), g["dq"][i])
         assert np.array_equal(O.poly_sample(c, 2, g["t0"][i], g["tf"][i], 64), g["ddq"][i])
+
+
+def test_config1_oracle_against_the_real_reference(golden):
+    """BASELINE config 1 at full size (1e4 uniform-in-limits poses, seed 0) from the REAL reference:
+    the oracle reproduces its FK and Jacobian to 1e-12 scaled, all 1.2e5 IK validity decisions of
+    the 12 (m, k, w) combinations exactly, and every IK value within the conditioned 1e-12 bound
+    of tests/ikcond.py (the gate the CUDA kernels are then held to against this same file)."""
+    import ikcond
+    g = golden("fanuc_config1.npz")
+    q, T34, ik12, Jg = g["q"], g["T34"], g["ik12"], g["J"]
+    assert q.shape == (10000, 6)
+    c = O.FanucConst()
+    rng = np.random.default_rng(0)                      # the recipe of make_golden.gen_config1
+    assert np.array_equal(q, rng.uniform(c.lim[:, 0], c.lim[:, 1], size=(10000, 6)))
+    T = O.fanuc_fk(q, c)
+    assert np.max(np.abs(T[:, :3, :3] - T34[:, :, :3])) < 1e-12
+    assert np.max(np.abs(T[:, :3, 3] - T34[:, :, 3]) / np.maximum(1, np.abs(T34[:, :, 3]).max(1, keepdims=True))) < 1e-12
+    J = O.fanuc_jacobian(q, c)
+    assert np.max(np.abs(J[:, :3] - Jg[:, :3])) / np.abs(Jg[:, :3]).max() < 1e-12
+    assert np.max(np.abs(J[:, 3:] - Jg[:, 3:])) < 1e-12
+    Tg = np.zeros((10000, 4, 4))
+    Tg[:, :3], Tg[:, 3, 3] = T34, 1.0
+    br = [tuple(int(v) for v in b) for b in g["branches12"]]
+    q_o, v_o, det = ikcond.ik_details(Tg, br, c)
+    v_ref = np.any(ik12 != 0.0, axis=2)
+    assert 0.3 < v_ref.mean() < 0.5
+    frac = ikcond.assert_ik_close(ik12, v_ref, q_o, v_o, det)
+    assert frac > 0.99

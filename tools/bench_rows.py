@@ -25,6 +25,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--scale", type=float, default=1.0, help="scale every batch size")
+    ap.add_argument("--warmup", type=int, default=2, help="0 with --reps 1 under ncu: one launch per row")
     args = ap.parse_args()
     import torch
     from roboticmanipulators_b200 import _lib
@@ -49,7 +50,7 @@ def main():
     out = {}
 
     def timed(name, units, nbytes, fn):
-        for _ in range(2):
+        for _ in range(args.warmup):
             fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
