@@ -9,6 +9,8 @@
 //    rk_calib_eval_f64: residual sums and maxima.
 // Every reduction ends the same way: CTA partials go to the workspace and the last CTA to finish
 // (atomic ticket) adds them in index order, so results are deterministic.
+#include <cstdlib>
+
 #include "rk_common.cuh"
 
 namespace rk {
@@ -548,6 +550,327 @@ calib_normal_eq6_kernel(const __grid_constant__ CalibP P, const __grid_constant_
 }
 
 // -------------------------------------------------------------------------------------------
+// K5 with the model STRUCTURE fixed at compile time (values stay runtime).
+//
+// The generic kernel above interprets the model: the joint walk is a rolled loop over runtime
+// tables (parameter lists per joint, parameter kinds, joint axes), so every constant it touches
+// costs an LDC, every parameter a kind branch, every joint an axis switch -- three quarters of its
+// instructions were phase 1 and only a third of those FP64 (ncu, round 1).  Here a Shape type
+// carries the structure as constant expressions: after full unrolling every table index is
+// static, the constants become constant-bank operands of the DFMAs themselves, and a joint is ONE
+// straight-line variant instead of a switch over three.  The Shape below is the Fanuc165F reduced
+// model of fanuc_calibration.py (the reference's one real calibration model: six revolute joints
+// z y y x y x, 18 parameters); any other model takes the generic kernel.
+//
+// Columns are also reordered in the slab: the 8 translation parameters first, then the 10 rotation
+// parameters, the residual and one zero column.  The three "angular" rows of a measurement
+// (y[3..5] = R22 a') are identically zero in the translation columns, so their Gram update needs
+// only the 3 tiles of the rotation blocks, not 6: 6.75 DMMA per measurement instead of 9.
+// -------------------------------------------------------------------------------------------
+struct FanucReducedShape {
+  static constexpr int NJ = 6, NP = 18;
+  static constexpr int SPLIT = 1;  // role A: joints >= SPLIT (make_calibn's cost model picks 1 for this model)
+  static __host__ __device__ constexpr int jaxis(int j) {
+    constexpr int a[NJ] = {2, 1, 1, 0, 1, 0};
+    return a[j];
+  }
+  static __host__ __device__ constexpr int pstart(int j) {
+    constexpr int a[NJ + 1] = {0, 3, 7, 11, 15, 18, 18};
+    return a[j];
+  }
+  static __host__ __device__ constexpr int pkind(int p) {  // 1 rotation, 0 translation
+    constexpr int a[NP] = {0, 0, 1, 1, 0, 1, 1, 1, 0, 0, 1, 1, 0, 0, 1, 1, 0, 1};
+    return a[p];
+  }
+  // slab column of parameter p: translations 0..7 in parameter order, then rotations 8..17
+  // (checked against pkind by shape_matches)
+  static __host__ __device__ constexpr int pcol(int p) {
+    constexpr int a[NP] = {0, 1, 8, 9, 2, 10, 11, 12, 3, 4, 13, 14, 5, 6, 15, 16, 7, 17};
+    return a[p];
+  }
+  static constexpr int NTRANS = 8;  // == number of translation parameters (one 8-column block)
+};
+
+template <class Shape>
+static bool shape_matches(const CalibP& P) {
+  if (P.nj != Shape::NJ || P.np != Shape::NP) return false;
+  int ntr = 0;
+  for (int j = 0; j < Shape::NJ; ++j)
+    if (P.jkind[j] != 1 || P.jaxis[j] != Shape::jaxis(j) || P.pstart[j] != Shape::pstart(j)) return false;
+  if (P.pstart[Shape::NJ] != Shape::pstart(Shape::NJ)) return false;
+  int nrot = 0;
+  for (int p = 0; p < Shape::NP; ++p) {
+    if (P.pkind[p] != Shape::pkind(p)) return false;
+    if (Shape::pcol(p) != (P.pkind[p] ? Shape::NTRANS + nrot : ntr)) return false;  // the table above
+    (P.pkind[p] ? nrot : ntr) += 1;
+  }
+  return ntr == Shape::NTRANS;
+}
+
+// parameter index of every slab column (the residual column maps to NP); host side
+struct ColMap {
+  int param_of_col[kW];
+};
+template <class Shape>
+static ColMap make_colmap() {
+  ColMap m;
+  for (int c = 0; c < kW; ++c) m.param_of_col[c] = Shape::NP;
+  for (int p = 0; p < Shape::NP; ++p) m.param_of_col[Shape::pcol(p)] = p;
+  return m;
+}
+
+// Phase 1 for one (measurement, role), every index static: joints and parameters are expanded by
+// template recursion (a `#pragma unroll` over bounds that come out of constexpr functions stayed a
+// rolled loop with table look-ups in local memory).  Column layout: see Shape::pcol; the residual is
+// column NP, column NP + 1 is zero.
+template <class Shape, int PI>
+__device__ __forceinline__ void static_param(const CalibP& P, const CalibN& N, const Sfx& S,
+                                             double* __restrict__ rows) {
+  constexpr int kRowStep = (kMeas / 2) * kRS6;
+  const double ax = P.pax[PI][0], ay = P.pax[PI][1], az = P.pax[PI][2];
+  const double a0 = S.Q[0] * ax + S.Q[3] * ay + S.Q[6] * az;  // a' = Q^T a
+  const double a1 = S.Q[1] * ax + S.Q[4] * ay + S.Q[7] * az;
+  const double a2 = S.Q[2] * ax + S.Q[5] * ay + S.Q[8] * az;
+  double* col = rows + Shape::pcol(PI);
+  if constexpr (Shape::pkind(PI) == 1) {
+    const double dx = S.s[0] - P.porg[PI][0], dy = S.s[1] - P.porg[PI][1], dz = S.s[2] - P.porg[PI][2];
+    const double b0 = S.Q[0] * dx + S.Q[3] * dy + S.Q[6] * dz + N.tbar[0];  // b'' = Q^T (s - o) + tbar
+    const double b1 = S.Q[1] * dx + S.Q[4] * dy + S.Q[7] * dz + N.tbar[1];
+    const double b2 = S.Q[2] * dx + S.Q[5] * dy + S.Q[8] * dz + N.tbar[2];
+    col[0 * kRowStep] = N.R[0][0] * (a1 * b2 - a2 * b1);
+    col[1 * kRowStep] = N.R[1][1] * (a2 * b0 - a0 * b2);
+    col[2 * kRowStep] = N.R[2][2] * (a0 * b1 - a1 * b0);
+    col[3 * kRowStep] = N.R[3][3] * a0 + N.R[3][4] * a1 + N.R[3][5] * a2;
+    col[4 * kRowStep] = N.R[4][4] * a1 + N.R[4][5] * a2;
+    col[5 * kRowStep] = N.R[5][5] * a2;
+  } else {
+    // translation column: the angular rows are zero and, by the column order, never read
+    col[0 * kRowStep] = N.R[0][0] * a0;
+    col[1 * kRowStep] = N.R[1][1] * a1;
+    col[2 * kRowStep] = N.R[2][2] * a2;
+  }
+}
+template <class Shape, int P0, int P1>
+__device__ __forceinline__ void static_params(const CalibP& P, const CalibN& N, const Sfx& S,
+                                              double* __restrict__ rows) {
+  if constexpr (P0 < P1) {
+    static_param<Shape, P0>(P, N, S, rows);
+    static_params<Shape, P0 + 1, P1>(P, N, S, rows);
+  }
+}
+// joints J, J - 1, ..., 0 of the backward walk
+template <class Shape, bool ROLE_A, int J>
+__device__ __forceinline__ void static_joints(const CalibP& P, const CalibN& N, Sfx& S,
+                                              const double (&qv)[RK_CALIB_MAX_JOINTS],
+                                              double* __restrict__ rows) {
+  constexpr int SPLIT = Shape::SPLIT;
+  if constexpr (!(ROLE_A && J < SPLIT)) {
+    if (P.seg_trans[J]) {  // S_j = X_j Rot_{j+1} S_{j+1}; a pure translation at the nominal model
+      S.s[0] += P.seg[J][3], S.s[1] += P.seg[J][7], S.s[2] += P.seg[J][11];
+    } else {
+      sfx_premul(S, P.seg[J]);
+    }
+    if constexpr (ROLE_A ? (J >= SPLIT) : (J < SPLIT))
+      static_params<Shape, Shape::pstart(J), Shape::pstart(J + 1)>(P, N, S, rows);
+    if constexpr (!(ROLE_A && J == SPLIT)) {  // S <- Rot_j(q_j) S_j  (role A never needs Rot_SPLIT)
+      const double v = __dadd_rn(__dmul_rn(qv[J], P.jdir[J]), P.joff[J]);  // model_calibration.py:557
+      double sn, cs;
+      fast_sincos(v, &sn, &cs);
+      sfx_rot<Shape::jaxis(J)>(S, sn, cs);
+    }
+    if constexpr (J > 0) static_joints<Shape, ROLE_A, J - 1>(P, N, S, qv, rows);
+  }
+}
+template <class Shape, bool ROLE_A, int PI>
+__device__ __forceinline__ void static_zero_cols(double* __restrict__ rows) {
+  constexpr int kRowStep = (kMeas / 2) * kRS6;
+  if constexpr (PI < Shape::NP) {
+    if constexpr (ROLE_A ? (PI >= Shape::pstart(Shape::SPLIT)) : (PI < Shape::pstart(Shape::SPLIT))) {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) rows[r * kRowStep + Shape::pcol(PI)] = 0.0;
+    }
+    static_zero_cols<Shape, ROLE_A, PI + 1>(rows);
+  }
+}
+
+template <class Shape, bool ROLE_A>
+__device__ __forceinline__ double fill_rows6_static(const CalibP& P, const CalibN& N,
+                                                    const double (&qv)[RK_CALIB_MAX_JOINTS],
+                                                    const double (&pv)[3 * RK_CALIB_MAX_TOOLS], bool live,
+                                                    double* __restrict__ rows) {
+  constexpr int kRowStep = (kMeas / 2) * kRS6;
+  constexpr int NJ = Shape::NJ, NP = Shape::NP;
+  if (!live) {  // past the end of the data: this role's columns are zero
+    static_zero_cols<Shape, ROLE_A, 0>(rows);
+    if (!ROLE_A) {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) rows[r * kRowStep + NP] = 0.0, rows[r * kRowStep + NP + 1] = 0.0;
+    }
+    return 0.0;
+  }
+  Sfx S;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) S.Q[k] = (k % 4 == 0) ? 1.0 : 0.0;
+  S.s[0] = S.s[1] = S.s[2] = 0.0;
+  static_joints<Shape, ROLE_A, NJ - 1>(P, N, S, qv, rows);
+  if (ROLE_A) return 0.0;
+  // role B: S = Rot_0 S_0; T_end = T_base S.  Residual of tool t in the end frame:
+  // rho_t = R_end^T (p_meas - p_end) - tool_t   (r = p_meas - T[:3,3], model_calibration.py:420)
+  sfx_premul(S, P.Tb);
+  double rho[3 * RK_CALIB_MAX_TOOLS];
+  double rr = 0.0;
+#pragma unroll
+  for (int t = 0; t < RK_CALIB_MAX_TOOLS; ++t) {
+    if (t < P.nt) {
+      const double dx = pv[3 * t] - S.s[0], dy = pv[3 * t + 1] - S.s[1], dz = pv[3 * t + 2] - S.s[2];
+      rho[3 * t + 0] = S.Q[0] * dx + S.Q[3] * dy + S.Q[6] * dz - P.tool[t][0];
+      rho[3 * t + 1] = S.Q[1] * dx + S.Q[4] * dy + S.Q[7] * dz - P.tool[t][1];
+      rho[3 * t + 2] = S.Q[2] * dx + S.Q[5] * dy + S.Q[8] * dz - P.tool[t][2];
+      rr += rho[3 * t] * rho[3 * t] + rho[3 * t + 1] * rho[3 * t + 1] + rho[3 * t + 2] * rho[3 * t + 2];
+    } else {
+      rho[3 * t] = rho[3 * t + 1] = rho[3 * t + 2] = 0.0;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3 * RK_CALIB_MAX_TOOLS; ++k) acc = fma(N.Qt[r][k], rho[k], acc);
+    rows[r * kRowStep + NP] = acc;
+    rows[r * kRowStep + NP + 1] = 0.0;
+  }
+  return rr;
+}
+
+// Phase 2 for the reordered columns: block 0 = translations (zero in the angular rows), block 1 =
+// rotations 0..7, block 2 = rotations 8, 9, residual, zero (+ 4 columns that exist only as the
+// zero fill of the fragment).  Row groups [0, kGroups / 2) hold the linear rows y[0..2] of the
+// pass's measurements (6 tiles), the other half the angular rows y[3..5] (3 tiles).
+struct GramDmmaSplit {
+  double acc[kTiles6][2];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int t = 0; t < kTiles6; ++t) acc[t][0] = acc[t][1] = 0.0;
+  }
+  __device__ __forceinline__ void accumulate(const double* __restrict__ slab, int warp, int lane) {
+    const int k = lane & 3, c = lane >> 2;
+    constexpr int kGroups = kMeas * 3 / 4;
+#pragma unroll 2
+    for (int g = warp; g < kGroups / 2; g += kMeas / kWarp) {
+      const int row = (g >> 3) * 32 + (g & 7) + 8 * k;
+      const double* rp = slab + row * kRS6 + c;
+      const double v0 = rp[0], v1 = rp[8];
+      const double v2 = c < 4 ? rp[16] : 0.0;
+      GramDmma::mma(acc[0], v0, v0), GramDmma::mma(acc[1], v0, v1), GramDmma::mma(acc[2], v0, v2);
+      GramDmma::mma(acc[3], v1, v1), GramDmma::mma(acc[4], v1, v2), GramDmma::mma(acc[5], v2, v2);
+    }
+#pragma unroll 2
+    for (int g = kGroups / 2 + warp; g < kGroups; g += kMeas / kWarp) {
+      const int row = (g >> 3) * 32 + (g & 7) + 8 * k;
+      const double* rp = slab + row * kRS6 + c;
+      const double v1 = rp[8];
+      const double v2 = c < 4 ? rp[16] : 0.0;
+      GramDmma::mma(acc[3], v1, v1), GramDmma::mma(acc[4], v1, v2), GramDmma::mma(acc[5], v2, v2);
+    }
+  }
+};
+
+template <class Shape>
+__global__ void __launch_bounds__(kMeas, 3)
+calib_normal_eq6_static_kernel(const __grid_constant__ CalibP P, const __grid_constant__ CalibN N,
+                               const __grid_constant__ ColMap CM, const double* __restrict__ q,
+                               const double* __restrict__ pts, int64_t m,
+                               double* __restrict__ partial, unsigned int* __restrict__ counter,
+                               double* __restrict__ out) {
+  extern __shared__ __align__(16) double slab[];  // [(kMeas/2)*6 rows][kRS6]
+  __shared__ int s_last;
+  __shared__ double s_rr[kMeas / kWarp];
+  constexpr int kHalf = kMeas / 2;
+  constexpr int NP = Shape::NP;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool role_a = tid >= kHalf;  // warp-uniform
+  const int ms = tid & (kHalf - 1);
+  GramDmmaSplit G;
+  G.init();
+  double rr = 0.0;
+  double qn[RK_CALIB_MAX_JOINTS], pn[3 * RK_CALIB_MAX_TOOLS];
+  auto prefetch = [&](int64_t i) {
+    const bool live = i < m;
+#pragma unroll
+    for (int j = 0; j < RK_CALIB_MAX_JOINTS; ++j) qn[j] = (live && j < Shape::NJ) ? __ldcs(q + i * Shape::NJ + j) : 0.0;
+#pragma unroll
+    for (int k = 0; k < 3 * RK_CALIB_MAX_TOOLS; ++k)
+      pn[k] = (live && !role_a && k < 3 * P.nt) ? __ldcs(pts + i * 3 * P.nt + k) : 0.0;
+  };
+  const int64_t stride = (int64_t)gridDim.x * kHalf;
+  int64_t base = (int64_t)blockIdx.x * kHalf;
+  prefetch(base + ms);
+  for (; base < m; base += stride) {
+    double qv[RK_CALIB_MAX_JOINTS], pv[3 * RK_CALIB_MAX_TOOLS];
+#pragma unroll
+    for (int j = 0; j < RK_CALIB_MAX_JOINTS; ++j) qv[j] = qn[j];
+#pragma unroll
+    for (int k = 0; k < 3 * RK_CALIB_MAX_TOOLS; ++k) pv[k] = pn[k];
+    __syncthreads();  // previous phase 2 is done with the slab
+    if (role_a)
+      fill_rows6_static<Shape, true>(P, N, qv, pv, base + ms < m, slab + ms * kRS6);
+    else
+      rr += fill_rows6_static<Shape, false>(P, N, qv, pv, base + ms < m, slab + ms * kRS6);
+    prefetch(base + stride + ms);
+    __syncthreads();
+    G.accumulate(slab, warp, lane);
+  }
+
+  // warps -> CTA partial (reuse the slab): lane l holds C[l/4][2(l%4) + e] of every tile
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < kTiles6; ++t)
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+      slab[(warp * kTiles6 + t) * 64 + (lane >> 2) * 8 + 2 * (lane & 3) + e] = G.acc[t][e];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rr += __shfl_xor_sync(0xffffffffu, rr, o);
+  if (lane == 0) s_rr[warp] = rr;
+  __syncthreads();
+  double* mine = partial + (int64_t)blockIdx.x * kPartStride;
+  for (int e = tid; e < kPart6; e += kMeas) {
+    double sum = 0.0;
+#pragma unroll
+    for (int w = 0; w < kMeas / kWarp; ++w) sum += slab[w * kPart6 + e];
+    mine[e] = sum;
+  }
+  if (tid == 0) mine[kPart6] = (s_rr[0] + s_rr[1]) + (s_rr[2] + s_rr[3]);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // last CTA: deterministic sum over CTAs (index order), then scatter into the packed format,
+  // undoing the column order (slab column -> parameter)
+  for (int e = tid; e <= kPart6; e += kMeas) {
+    double sum = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) sum += __ldcg(partial + (int64_t)b * kPartStride + e);
+    if (e == kPart6) {
+      out[NP * (NP + 1) / 2 + NP] = sum;  // r^T r
+      continue;
+    }
+    const int t = e >> 6, r = (e >> 3) & 7, c = e & 7;
+    const int I = t < 3 ? 0 : (t < 5 ? 1 : 2), J = t < 3 ? t : (t < 5 ? t - 2 : 2);
+    const int gi = 8 * I + r, gj = 8 * J + c;  // slab columns
+    if (gi > gj || gj > NP || gi >= NP) continue;
+    const int pi = CM.param_of_col[gi], pj = CM.param_of_col[gj];  // NP = the residual column
+    if (gj == NP) {
+      out[NP * (NP + 1) / 2 + pi] = sum;  // g
+    } else {
+      const int a = pi < pj ? pi : pj, b2 = pi < pj ? pj : pi;
+      out[a * NP - a * (a - 1) / 2 + (b2 - a)] = sum;  // packed upper H
+    }
+  }
+  if (tid == 0) *counter = 0;
+}
+
+// -------------------------------------------------------------------------------------------
 // estimate_tool_base (model_calibration.py:296-332) without forming the rows.  The reference sums
 // A^T A and A^T dp over (measurement i, tool t) with A = [I | skew(p_i)^T | R_i in block t],
 // dp = p_meas(i,t) - p_i, where (R_i, p_i) is the flange pose.  Every block of those sums is a
@@ -741,6 +1064,12 @@ calib_eval_kernel(const __grid_constant__ CalibP P, const double* __restrict__ q
 
 constexpr size_t kWsCounterOffset = (size_t)kMaxGrid * kPartStride * sizeof(double);
 constexpr size_t kWsBytes = kWsCounterOffset + 256;
+// RK_CALIB_GENERIC=1 in the environment sends every model through the generic (interpreting)
+// kernel: lets the tests and tools/bench compare the two on the same model
+static const bool g_calib_force_generic = [] {
+  const char* e = getenv("RK_CALIB_GENERIC");
+  return e && e[0] == '1';
+}();
 
 }  // namespace rk
 
@@ -764,11 +1093,20 @@ int rk_calib_normal_eq_f64(const RkCalibModel* model, const double* q, const dou
   make_calibn(P, N);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)kMeas * 3 * kRS6 * sizeof(double);
+  unsigned int* counter = reinterpret_cast<unsigned int*>((char*)workspace + kWsCounterOffset);
+  if (cudaMemsetAsync(counter, 0, sizeof(unsigned int), st) != cudaSuccess) return check_launch();
+  if (shape_matches<FanucReducedShape>(P) && !g_calib_force_generic) {
+    auto kern = calib_normal_eq6_static_kernel<FanucReducedShape>;
+    if (!allow_dynamic_smem(kern, smem)) return RK_ERR_CUDA;
+    int grid = persistent_grid(kern, kMeas, smem, m > 0 ? 2 * m : 1);
+    if (grid > kMaxGrid) grid = kMaxGrid;
+    kern<<<grid, kMeas, smem, st>>>(P, N, make_colmap<FanucReducedShape>(), q, pts, m, (double*)workspace,
+                                    counter, out);
+    return check_launch();
+  }
   if (!allow_dynamic_smem(calib_normal_eq6_kernel, smem)) return RK_ERR_CUDA;
   int grid = persistent_grid(calib_normal_eq6_kernel, kMeas, smem, m > 0 ? 2 * m : 1);
   if (grid > kMaxGrid) grid = kMaxGrid;
-  unsigned int* counter = reinterpret_cast<unsigned int*>((char*)workspace + kWsCounterOffset);
-  if (cudaMemsetAsync(counter, 0, sizeof(unsigned int), st) != cudaSuccess) return check_launch();
   calib_normal_eq6_kernel<<<grid, kMeas, smem, st>>>(P, N, q, pts, m, ncols, (double*)workspace, counter, out);
   return check_launch();
 }

