@@ -111,6 +111,15 @@ int rk_fanuc_ik_f32(const RkFanuc* robot, const float* T, int64_t n, int64_t ld,
                     const int8_t* branches_mkw, int nb, float* q_out, uint8_t* valid,
                     void* stream);
 
+/* TrajectoryGenerator.get_dq_from_dx (utils/trajectory_generator.py:161-188) for the Fanuc165F:
+ * dq = J(q)^-1 dx with the 6x6 Jacobian of rk_fanuc_fk_jac_* (dx = [v; omega] per pose; columns
+ * w.r.t. the model angles unless RK_JAC_USER_ANGLES), solved in registers with partial pivoting.
+ * q, dx, dq: AOS [n][6] / SOA [6][ld]; ok [n]: 0 where J is exactly singular; may be NULL. */
+int rk_fanuc_dq_from_dx_f64(const RkFanuc* robot, const double* q, const double* dx, int64_t n,
+                            int64_t ld, int flags, double* dq, uint8_t* ok, void* stream);
+int rk_fanuc_dq_from_dx_f32(const RkFanuc* robot, const float* q, const float* dx, int64_t n,
+                            int64_t ld, int flags, float* dq, uint8_t* ok, void* stream);
+
 /* forward_kinematics + Jacobian + det followed by inverse_kinematics over the canonical 8
  * branches of the pose just computed -- the FK -> IK round trip of fanuc_kinematics.py and
  * tests/test_robots.py:33-52 (test_fanuc_ifk) -- as ONE call.  Arguments and results are
@@ -175,6 +184,16 @@ int rk_rr_fk_jac_f64(const RkArm* robot, const double* q, int64_t n, int64_t ld,
 int rk_rr_ik_f64(const RkArm* robot, const double* T, int64_t n, int64_t ld, int flags,
                  const int8_t* branches_m, int nb, double* q_out, uint8_t* valid,
                  void* stream);
+/* FP32 variants of the four entry points above (same arguments; the reachability and limit
+ * tests of the IK are evaluated in FP32 on the FP32 inputs). */
+int rk_rrr_fk_jac_f32(const RkArm* robot, const float* q, int64_t n, int64_t ld, int flags,
+                      float* T, float* J, void* stream);
+int rk_rrr_ik_f32(const RkArm* robot, const float* T, int64_t n, int64_t ld, int flags,
+                  const int8_t* branches_mk, int nb, float* q_out, uint8_t* valid, void* stream);
+int rk_rr_fk_jac_f32(const RkArm* robot, const float* q, int64_t n, int64_t ld, int flags,
+                     float* T, float* J, void* stream);
+int rk_rr_ik_f32(const RkArm* robot, const float* T, int64_t n, int64_t ld, int flags,
+                 const int8_t* branches_m, int nb, float* q_out, uint8_t* valid, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Generic token chains  (reference: utils/robo_math.py Transformation,
@@ -182,8 +201,10 @@ int rk_rr_ik_f64(const RkArm* robot, const double* T, int64_t n, int64_t ld, int
  * ---------------------------------------------------------------------------------- */
 #define RK_MAX_TOKENS 32
 
-/* Opcode = kind*3 + axis, kind: 0 T, 1 R, 2 T-inverse, 3 R-inverse; axis 0 x, 1 y, 2 z
- * (the 12 non-derivative tokens of utils/robo_math.py:368-380). */
+/* Opcode = kind*3 + axis, kind: 0 T, 1 R, 2 T-inverse, 3 R-inverse, 4 T-derivative, 5 R-derivative;
+ * axis 0 x, 1 y, 2 z -- the 18 tokens of utils/robo_math.py:368-387 (Tx .. Rz, Txi .. Rzi,
+ * Txd .. Rzd).  A derivative token is the matrix dM/dv with a ZERO corner (robo_math.py:556-608), so
+ * the [3][3] entry of a product that contains one is 0. */
 typedef struct RkChain {
   int32_t ntok;
   int32_t op[RK_MAX_TOKENS];
@@ -201,6 +222,21 @@ typedef struct RkChain {
  *   J      out: 6 x n_active per sample (AOS [n][6][na]; SOA [6*na][ld]); may be NULL */
 int rk_chain_fk_jac_f64(const RkChain* chain, const double* values, int nvals, int64_t n,
                         int64_t ld, int flags, double* T, double* J, void* stream);
+int rk_chain_fk_jac_f32(const RkChain* chain, const float* values, int nvals, int64_t n,
+                        int64_t ld, int flags, float* T, float* J, void* stream);
+
+/* TrajectoryGenerator.get_dq_from_dx (utils/trajectory_generator.py:161-188) for any chain: the
+ * reference evaluates a SYMBOLIC inverse of a square block of the Jacobian per sample
+ * (rrr_robot_jacobians.py:14-46 builds it as calculate_numeric()[:3, :3].inv()); here the na x na
+ * block J[rows, :] of the chain's Jacobian (na = number of active tokens <= 6) is formed in
+ * registers and  J[rows, :] dq = dx  is solved in place with partial pivoting.
+ *   rows in : HOST pointer to na distinct row indices in 0..5 (0-2 linear, 3-5 angular);
+ *             NULL = rows 0 .. na-1
+ *   dx   in : AOS [n][na]; SOA [na][ld];   dq out: same layout
+ *   ok   out: [n], 0 where a pivot was exactly zero (singular block); may be NULL */
+int rk_chain_dq_from_dx_f64(const RkChain* chain, const double* values, int nvals,
+                            const int32_t* rows, const double* dx, int64_t n, int64_t ld, int flags,
+                            double* dq, uint8_t* ok, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Trapezoidal trajectories (reference: utils/trapezoidal_generator.py,
@@ -255,6 +291,14 @@ int rk_trap_p2p_f64(const double* q0, const double* qf, int64_t ntraj, int nj, i
 int rk_rrr_p2p_fk_f64(const RkArm* robot, const double* q0, const double* qf, int64_t ntraj,
                       int nsteps, double v_max, double a_max, double control_freq, double* q,
                       double* dq, double* ddq, double* t, int32_t* len, double* T, double* J,
+                      void* stream);
+
+/* FP32 variant: the profile (coefficients, sample COUNTS, times, q / dq / ddq) is evaluated in
+ * FP64 exactly as above -- len[] is bit-identical to the FP64 call -- and rounded to FP32 on the
+ * way out; the per-sample forward kinematics and Jacobian are computed in FP32.  176 B per sample. */
+int rk_rrr_p2p_fk_f32(const RkArm* robot, const double* q0, const double* qf, int64_t ntraj,
+                      int nsteps, double v_max, double a_max, double control_freq, float* q,
+                      float* dq, float* ddq, float* t, int32_t* len, float* T, float* J,
                       void* stream);
 
 /* TrajectoryGenerator.generate_lin_trajectory (trajectory_generator.py:94-116) followed

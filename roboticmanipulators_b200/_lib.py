@@ -83,7 +83,18 @@ _SIGNATURES = {
     "rk_rrr_ik_f64": (_int, [C.POINTER(RkArm), _vp, _i64, _i64, _int, _vp, _int, _vp, _vp, _vp]),
     "rk_rr_fk_jac_f64": (_int, [C.POINTER(RkArm), _vp, _i64, _i64, _int, _vp, _vp, _vp]),
     "rk_rr_ik_f64": (_int, [C.POINTER(RkArm), _vp, _i64, _i64, _int, _vp, _int, _vp, _vp, _vp]),
+    "rk_rrr_fk_jac_f32": (_int, [C.POINTER(RkArm), _vp, _i64, _i64, _int, _vp, _vp, _vp]),
+    "rk_rrr_ik_f32": (_int, [C.POINTER(RkArm), _vp, _i64, _i64, _int, _vp, _int, _vp, _vp, _vp]),
+    "rk_rr_fk_jac_f32": (_int, [C.POINTER(RkArm), _vp, _i64, _i64, _int, _vp, _vp, _vp]),
+    "rk_rr_ik_f32": (_int, [C.POINTER(RkArm), _vp, _i64, _i64, _int, _vp, _int, _vp, _vp, _vp]),
+    "rk_rrr_p2p_fk_f32": (_int, [C.POINTER(RkArm), _vp, _vp, _i64, _int, C.c_double, C.c_double,
+                                 C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rk_chain_fk_jac_f64": (_int, [C.POINTER(RkChain), _vp, _int, _i64, _i64, _int, _vp, _vp, _vp]),
+    "rk_chain_fk_jac_f32": (_int, [C.POINTER(RkChain), _vp, _int, _i64, _i64, _int, _vp, _vp, _vp]),
+    "rk_chain_dq_from_dx_f64": (_int, [C.POINTER(RkChain), _vp, _int, C.POINTER(C.c_int32), _vp, _i64, _i64,
+                                       _int, _vp, _vp, _vp]),
+    "rk_fanuc_dq_from_dx_f64": (_int, [C.POINTER(RkFanuc), _vp, _vp, _i64, _i64, _int, _vp, _vp, _vp]),
+    "rk_fanuc_dq_from_dx_f32": (_int, [C.POINTER(RkFanuc), _vp, _vp, _i64, _i64, _int, _vp, _vp, _vp]),
     "rk_trap_coefficients_f64": (_int, [_vp, _vp, _i64, C.c_double, C.c_double, C.c_double,
                                         _vp, _vp, _vp]),
     "rk_trap_sample_f64": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp,

@@ -4,51 +4,30 @@
 
 namespace rk {
 
-static ArmP make_arm(const RkArm* r) {
-  ArmP p;
-  for (int i = 0; i < 3; ++i) {
-    p.l[i] = r->l[i];
-    p.lo[i] = r->lim_lo[i];
-    p.hi[i] = r->lim_hi[i];
-  }
-  p.eps = r->eps;
-  for (int i = 0; i < 12; ++i) {
-    p.Tb[i] = r->T_base[i];
-    p.Tt[i] = r->T_tool[i];
-    p.Tbi[i] = r->T_base_inv[i];
-    p.Tti[i] = r->T_tool_inv[i];
-  }
-  p.has_base = r->has_base;
-  p.has_tool = r->has_tool;
-  return p;
-}
-
-ArmP make_arm_params(const RkArm* r) { return make_arm(r); }
-
 // One thread per pose; AOS goes through the warp-private staging tile.
-template <int NQ, bool SOA>
+template <typename S, int NQ, bool SOA>
 __global__ void __launch_bounds__(kBlock, 4)
-arm_fk_jac_kernel(const __grid_constant__ ArmP P, const double* __restrict__ q, int64_t n,
-                  int64_t ld, double* __restrict__ T, double* __restrict__ J) {
+arm_fk_jac_kernel(const __grid_constant__ ArmPT<S> P, const S* __restrict__ q, int64_t n,
+                  int64_t ld, S* __restrict__ T, S* __restrict__ J) {
   constexpr int NJ = 6 * NQ;
   constexpr int NST = Stride<NJ>::value > Stride<16>::value ? Stride<NJ>::value : Stride<16>::value;
-  __shared__ double stage_all[SOA ? 1 : (kBlock / kWarp) * kWarp * NST];
+  __shared__ S stage_all[SOA ? 1 : (kBlock / kWarp) * kWarp * NST];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t base = (int64_t)blockIdx.x * blockDim.x + warp * kWarp; base < n; base += stride) {
     const int64_t i = base + lane;
     const int64_t rem = n - base;
     const int cnt = rem < kWarp ? (int)rem : kWarp;
-    double qv[NQ], Tv[16], Jv[NJ];
-    double* stage = stage_all + (SOA ? 0 : warp * kWarp * NST);
+    S qv[NQ], Tv[16], Jv[NJ];
+    S* stage = stage_all + (SOA ? 0 : warp * kWarp * NST);
     if (SOA) {
 #pragma unroll
-      for (int k = 0; k < NQ; ++k) qv[k] = (lane < cnt) ? __ldcs(q + k * ld + i) : 0.0;
+      for (int k = 0; k < NQ; ++k) qv[k] = (lane < cnt) ? __ldcs(q + k * ld + i) : S(0);
     } else {
-      warp_load_aos<double, NQ>(stage, qv, q + base * NQ, cnt, lane);
+      warp_load_aos<S, NQ>(stage, qv, q + base * NQ, cnt, lane);
       if (lane >= cnt) {
 #pragma unroll
-        for (int k = 0; k < NQ; ++k) qv[k] = 0.0;
+        for (int k = 0; k < NQ; ++k) qv[k] = S(0);
       }
     }
     if constexpr (NQ == 3)
@@ -67,8 +46,8 @@ arm_fk_jac_kernel(const __grid_constant__ ArmP P, const double* __restrict__ q, 
         }
       }
     } else {
-      if (T) warp_store_aos<double, 16>(stage, Tv, T + base * 16, cnt, lane);
-      if (J) warp_store_aos<double, NJ>(stage, Jv, J + base * NJ, cnt, lane);
+      if (T) warp_store_aos<S, 16>(stage, Tv, T + base * 16, cnt, lane);
+      if (J) warp_store_aos<S, NJ>(stage, Jv, J + base * NJ, cnt, lane);
     }
   }
 }
@@ -79,10 +58,10 @@ struct ArmBranches {
 };
 
 // One thread per (pose, branch).
-template <int NQ, bool SOA>
+template <typename S, int NQ, bool SOA>
 __global__ void __launch_bounds__(kBlock)
-arm_ik_kernel(const __grid_constant__ ArmP P, const __grid_constant__ ArmBranches BL,
-              const double* __restrict__ T, int64_t n, int64_t ld, double* __restrict__ q_out,
+arm_ik_kernel(const __grid_constant__ ArmPT<S> P, const __grid_constant__ ArmBranches BL,
+              const S* __restrict__ T, int64_t n, int64_t ld, S* __restrict__ q_out,
               uint8_t* __restrict__ valid) {
   const int nb = BL.nb;
   const int64_t total = n * nb;
@@ -90,12 +69,12 @@ arm_ik_kernel(const __grid_constant__ ArmP P, const __grid_constant__ ArmBranche
   for (int64_t tix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tix < total; tix += stride) {
     const int64_t i = tix / nb;
     const int b = (int)(tix - i * nb);
-    double Tin[12];
+    S Tin[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) Tin[k] = SOA ? T[k * ld + i] : T[i * 16 + k];
-    double p0[3];
+    S p0[3];
     arm_ik_p0(P, Tin, p0);
-    double qo[NQ];
+    S qo[NQ];
     bool ok;
     if constexpr (NQ == 3)
       ok = rrr_ik_branch(P, p0, BL.mk[b * 2], BL.mk[b * 2 + 1], qo);
@@ -118,17 +97,17 @@ arm_ik_kernel(const __grid_constant__ ArmP P, const __grid_constant__ ArmBranche
 // Canonical branch set (RRR: 4 = m outer, k inner; RR: 2), one thread per target: the work shared
 // by the branches is done once (rrr_ik4_pose / rr_ik2_pose).  The arms' IK is position-only, so
 // without a base / tool transform only the translation column of T is read (24 of 128 bytes).
-template <int NQ, bool SOA>
+template <typename S, int NQ, bool SOA>
 __global__ void __launch_bounds__(kBlock)
-arm_ik_pose_kernel(const __grid_constant__ ArmP P, const double* __restrict__ T, int64_t n, int64_t ld,
-                   double* __restrict__ q_out, uint8_t* __restrict__ valid) {
+arm_ik_pose_kernel(const __grid_constant__ ArmPT<S> P, const S* __restrict__ T, int64_t n, int64_t ld,
+                   S* __restrict__ q_out, uint8_t* __restrict__ valid) {
   constexpr int NB = (NQ == 3) ? 4 : 2;
   const bool full = P.has_base || P.has_tool;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    double p0[3];
+    S p0[3];
     if (full) {
-      double Tin[12];
+      S Tin[12];
 #pragma unroll
       for (int k = 0; k < 12; ++k) Tin[k] = SOA ? __ldcs(T + k * ld + i) : T[i * 16 + k];
       arm_ik_p0(P, Tin, p0);
@@ -136,7 +115,7 @@ arm_ik_pose_kernel(const __grid_constant__ ArmP P, const double* __restrict__ T,
 #pragma unroll
       for (int k = 0; k < 3; ++k) p0[k] = SOA ? __ldcs(T + (4 * k + 3) * ld + i) : T[i * 16 + 4 * k + 3];
     }
-    double qo[NB][NQ];
+    S qo[NB][NQ];
     bool ok[NB];
     if constexpr (NQ == 3)
       rrr_ik4_pose(P, p0, qo, ok);
@@ -150,8 +129,8 @@ arm_ik_pose_kernel(const __grid_constant__ ArmP P, const double* __restrict__ T,
         valid[(int64_t)b * ld + i] = ok[b] ? 1 : 0;
       }
     } else {
-      // [n][NB][NQ]: a thread's NB*NQ values are contiguous (96 / 32 bytes)
-      double* qp = q_out + i * (NB * NQ);
+      // [n][NB][NQ]: a thread's NB*NQ values are contiguous (96 / 32 bytes in FP64)
+      S* qp = q_out + i * (NB * NQ);
 #pragma unroll
       for (int b = 0; b < NB; ++b)
 #pragma unroll
@@ -162,29 +141,29 @@ arm_ik_pose_kernel(const __grid_constant__ ArmP P, const double* __restrict__ T,
   }
 }
 
-template <int NQ>
-static int launch_arm_fk(const RkArm* robot, const double* q, int64_t n, int64_t ld, int flags,
-                         double* T, double* J, void* stream) {
+template <typename S, int NQ>
+static int launch_arm_fk(const RkArm* robot, const S* q, int64_t n, int64_t ld, int flags,
+                         S* T, S* J, void* stream) {
   if (!robot || n < 0) return RK_ERR_INVALID_ARG;
   if (n == 0) return RK_OK;
   if (!q) return RK_ERR_INVALID_ARG;
   const bool soa = (flags & RK_SOA) != 0;
   if (soa && ld < n) return RK_ERR_INVALID_ARG;
-  ArmP P = make_arm(robot);
+  ArmPT<S> P = make_arm_params_t<S>(robot);
   cudaStream_t st = (cudaStream_t)stream;
   if (soa) {
-    int grid = stream_grid(arm_fk_jac_kernel<NQ, true>, kBlock, 0, n);
-    arm_fk_jac_kernel<NQ, true><<<grid, kBlock, 0, st>>>(P, q, n, ld, T, J);
+    int grid = stream_grid(arm_fk_jac_kernel<S, NQ, true>, kBlock, 0, n);
+    arm_fk_jac_kernel<S, NQ, true><<<grid, kBlock, 0, st>>>(P, q, n, ld, T, J);
   } else {
-    int grid = stream_grid(arm_fk_jac_kernel<NQ, false>, kBlock, 0, n);
-    arm_fk_jac_kernel<NQ, false><<<grid, kBlock, 0, st>>>(P, q, n, ld, T, J);
+    int grid = stream_grid(arm_fk_jac_kernel<S, NQ, false>, kBlock, 0, n);
+    arm_fk_jac_kernel<S, NQ, false><<<grid, kBlock, 0, st>>>(P, q, n, ld, T, J);
   }
   return check_launch();
 }
 
-template <int NQ>
-static int launch_arm_ik(const RkArm* robot, const double* T, int64_t n, int64_t ld, int flags,
-                         const int8_t* branches, int nb, double* q_out, uint8_t* valid,
+template <typename S, int NQ>
+static int launch_arm_ik(const RkArm* robot, const S* T, int64_t n, int64_t ld, int flags,
+                         const int8_t* branches, int nb, S* q_out, uint8_t* valid,
                          void* stream) {
   constexpr int canon = (NQ == 3) ? 4 : 2;
   if (!robot || n < 0 || nb < 1 || nb > 8) return RK_ERR_INVALID_ARG;
@@ -193,7 +172,7 @@ static int launch_arm_ik(const RkArm* robot, const double* T, int64_t n, int64_t
   if (!T || !q_out || !valid) return RK_ERR_INVALID_ARG;
   const bool soa = (flags & RK_SOA) != 0;
   if (soa && ld < n) return RK_ERR_INVALID_ARG;
-  ArmP P = make_arm(robot);
+  ArmPT<S> P = make_arm_params_t<S>(robot);
   ArmBranches BL;
   BL.nb = nb;
   for (int b = 0; b < nb; ++b) {
@@ -217,20 +196,20 @@ static int launch_arm_ik(const RkArm* robot, const double* T, int64_t n, int64_t
   }
   if (canonical) {
     if (soa) {
-      int grid = stream_grid(arm_ik_pose_kernel<NQ, true>, kBlock, 0, n);
-      arm_ik_pose_kernel<NQ, true><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
+      int grid = stream_grid(arm_ik_pose_kernel<S, NQ, true>, kBlock, 0, n);
+      arm_ik_pose_kernel<S, NQ, true><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
     } else {
-      int grid = stream_grid(arm_ik_pose_kernel<NQ, false>, kBlock, 0, n);
-      arm_ik_pose_kernel<NQ, false><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
+      int grid = stream_grid(arm_ik_pose_kernel<S, NQ, false>, kBlock, 0, n);
+      arm_ik_pose_kernel<S, NQ, false><<<grid, kBlock, 0, st>>>(P, T, n, ld, q_out, valid);
     }
     return check_launch();
   }
   if (soa) {
-    int grid = stream_grid(arm_ik_kernel<NQ, true>, kBlock, 0, n * nb);
-    arm_ik_kernel<NQ, true><<<grid, kBlock, 0, st>>>(P, BL, T, n, ld, q_out, valid);
+    int grid = stream_grid(arm_ik_kernel<S, NQ, true>, kBlock, 0, n * nb);
+    arm_ik_kernel<S, NQ, true><<<grid, kBlock, 0, st>>>(P, BL, T, n, ld, q_out, valid);
   } else {
-    int grid = stream_grid(arm_ik_kernel<NQ, false>, kBlock, 0, n * nb);
-    arm_ik_kernel<NQ, false><<<grid, kBlock, 0, st>>>(P, BL, T, n, ld, q_out, valid);
+    int grid = stream_grid(arm_ik_kernel<S, NQ, false>, kBlock, 0, n * nb);
+    arm_ik_kernel<S, NQ, false><<<grid, kBlock, 0, st>>>(P, BL, T, n, ld, q_out, valid);
   }
   return check_launch();
 }
@@ -238,20 +217,24 @@ static int launch_arm_ik(const RkArm* robot, const double* T, int64_t n, int64_t
 }  // namespace rk
 
 extern "C" {
-int rk_rrr_fk_jac_f64(const RkArm* robot, const double* q, int64_t n, int64_t ld, int flags,
-                      double* T, double* J, void* stream) {
-  return rk::launch_arm_fk<3>(robot, q, n, ld, flags, T, J, stream);
-}
-int rk_rr_fk_jac_f64(const RkArm* robot, const double* q, int64_t n, int64_t ld, int flags,
-                     double* T, double* J, void* stream) {
-  return rk::launch_arm_fk<2>(robot, q, n, ld, flags, T, J, stream);
-}
-int rk_rrr_ik_f64(const RkArm* robot, const double* T, int64_t n, int64_t ld, int flags,
-                  const int8_t* branches_mk, int nb, double* q_out, uint8_t* valid, void* stream) {
-  return rk::launch_arm_ik<3>(robot, T, n, ld, flags, branches_mk, nb, q_out, valid, stream);
-}
-int rk_rr_ik_f64(const RkArm* robot, const double* T, int64_t n, int64_t ld, int flags,
-                 const int8_t* branches_m, int nb, double* q_out, uint8_t* valid, void* stream) {
-  return rk::launch_arm_ik<2>(robot, T, n, ld, flags, branches_m, nb, q_out, valid, stream);
-}
+#define RK_ARM_ENTRY(SFX, S)                                                                                \
+  int rk_rrr_fk_jac_##SFX(const RkArm* robot, const S* q, int64_t n, int64_t ld, int flags, S* T, S* J,     \
+                          void* stream) {                                                                   \
+    return rk::launch_arm_fk<S, 3>(robot, q, n, ld, flags, T, J, stream);                                   \
+  }                                                                                                         \
+  int rk_rr_fk_jac_##SFX(const RkArm* robot, const S* q, int64_t n, int64_t ld, int flags, S* T, S* J,      \
+                         void* stream) {                                                                    \
+    return rk::launch_arm_fk<S, 2>(robot, q, n, ld, flags, T, J, stream);                                   \
+  }                                                                                                         \
+  int rk_rrr_ik_##SFX(const RkArm* robot, const S* T, int64_t n, int64_t ld, int flags,                     \
+                      const int8_t* branches_mk, int nb, S* q_out, uint8_t* valid, void* stream) {          \
+    return rk::launch_arm_ik<S, 3>(robot, T, n, ld, flags, branches_mk, nb, q_out, valid, stream);          \
+  }                                                                                                         \
+  int rk_rr_ik_##SFX(const RkArm* robot, const S* T, int64_t n, int64_t ld, int flags,                      \
+                     const int8_t* branches_m, int nb, S* q_out, uint8_t* valid, void* stream) {            \
+    return rk::launch_arm_ik<S, 2>(robot, T, n, ld, flags, branches_m, nb, q_out, valid, stream);           \
+  }
+RK_ARM_ENTRY(f64, double)
+RK_ARM_ENTRY(f32, float)
+#undef RK_ARM_ENTRY
 }

@@ -5,26 +5,46 @@
 
 namespace rk {
 
-struct ArmP {
-  double l[3], lo[3], hi[3], eps;
-  double Tb[12], Tt[12], Tbi[12], Tti[12];
+template <typename S>
+struct ArmPT {
+  S l[3], lo[3], hi[3], eps;
+  S Tb[12], Tt[12], Tbi[12], Tti[12];
   int has_base, has_tool;
 };
+using ArmP = ArmPT<double>;
 
-ArmP make_arm_params(const RkArm* r);
+template <typename S>
+inline ArmPT<S> make_arm_params_t(const RkArm* r) {
+  ArmPT<S> p;
+  for (int i = 0; i < 3; ++i) {
+    p.l[i] = (S)r->l[i];
+    p.lo[i] = (S)r->lim_lo[i];
+    p.hi[i] = (S)r->lim_hi[i];
+  }
+  p.eps = (S)r->eps;
+  for (int i = 0; i < 12; ++i) {
+    p.Tb[i] = (S)r->T_base[i];
+    p.Tt[i] = (S)r->T_tool[i];
+    p.Tbi[i] = (S)r->T_base_inv[i];
+    p.Tti[i] = (S)r->T_tool_inv[i];
+  }
+  p.has_base = r->has_base;
+  p.has_tool = r->has_tool;
+  return p;
+}
+inline ArmP make_arm_params(const RkArm* r) { return make_arm_params_t<double>(r); }
 
 // Apply T_tool on the right and T_base on the left of a local pose (R columns-major
 // 3x3 row-major array, origin On) and of NC Jacobian columns; write T (16) and J (6 x NC).
-template <int NC>
-__device__ __forceinline__ void arm_finish(const ArmP& P, double (&R)[9], V3<double> On,
-                                           V3<double> (&jv)[NC], V3<double> (&jw)[NC],
-                                           const V3<double> (&Ok)[NC], double (&T)[16],
-                                           double (&J)[6 * NC]) {
+template <typename S, int NC>
+__device__ __forceinline__ void arm_finish(const ArmPT<S>& P, S (&R)[9], V3<S> On, V3<S> (&jv)[NC],
+                                           V3<S> (&jw)[NC], const V3<S> (&Ok)[NC], S (&T)[16],
+                                           S (&J)[6 * NC]) {
   if (P.has_tool) {
-    V3<double> pt = {P.Tt[3], P.Tt[7], P.Tt[11]};
-    V3<double> dv = rot(R, pt);
+    V3<S> pt = {P.Tt[3], P.Tt[7], P.Tt[11]};
+    V3<S> dv = rot(R, pt);
     On = {On.x + dv.x, On.y + dv.y, On.z + dv.z};
-    double Rn[9];
+    S Rn[9];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -36,15 +56,15 @@ __device__ __forceinline__ void arm_finish(const ArmP& P, double (&R)[9], V3<dou
 #pragma unroll
   for (int k = 0; k < NC; ++k) jv[k] = cross(jw[k], sub(On, Ok[k]));  // u x (O_n - O_k)
   if (P.has_base) {
-    const double Rb[9] = {P.Tb[0], P.Tb[1], P.Tb[2], P.Tb[4], P.Tb[5], P.Tb[6], P.Tb[8], P.Tb[9], P.Tb[10]};
+    const S Rb[9] = {P.Tb[0], P.Tb[1], P.Tb[2], P.Tb[4], P.Tb[5], P.Tb[6], P.Tb[8], P.Tb[9], P.Tb[10]};
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
       jv[k] = rot(Rb, jv[k]);
       jw[k] = rot(Rb, jw[k]);
     }
-    V3<double> p = rot(Rb, On);
+    V3<S> p = rot(Rb, On);
     On = {p.x + P.Tb[3], p.y + P.Tb[7], p.z + P.Tb[11]};
-    double Rn[9];
+    S Rn[9];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -56,7 +76,7 @@ __device__ __forceinline__ void arm_finish(const ArmP& P, double (&R)[9], V3<dou
   T[0] = R[0], T[1] = R[1], T[2] = R[2], T[3] = On.x;
   T[4] = R[3], T[5] = R[4], T[6] = R[5], T[7] = On.y;
   T[8] = R[6], T[9] = R[7], T[10] = R[8], T[11] = On.z;
-  T[12] = 0.0, T[13] = 0.0, T[14] = 0.0, T[15] = 1.0;
+  T[12] = S(0), T[13] = S(0), T[14] = S(0), T[15] = S(1);
 #pragma unroll
   for (int k = 0; k < NC; ++k) {
     J[0 * NC + k] = jv[k].x, J[1 * NC + k] = jv[k].y, J[2 * NC + k] = jv[k].z;
@@ -65,44 +85,47 @@ __device__ __forceinline__ void arm_finish(const ArmP& P, double (&R)[9], V3<dou
 }
 
 // RRRRobot.forward_kinematics (rrr_robot.py:96-120): Rz(q0) Tz(l0) Ry(q1) Tx(l1) Ry(q2) Tx(l2)
-__device__ __forceinline__ void rrr_fk_jac_pose(const ArmP& P, const double (&q)[3], double (&T)[16],
-                                                double (&J)[18]) {
-  double s0, c0, s1, c1, s2, c2;
-  fast_sincos(q[0], &s0, &c0);
-  fast_sincos(q[1], &s1, &c1);
-  fast_sincos(q[2], &s2, &c2);
-  const double c12 = c1 * c2 - s1 * s2, s12 = s1 * c2 + c1 * s2;
-  const double l0 = P.l[0], l1 = P.l[1], l2 = P.l[2];
-  const V3<double> y1 = {-s0, c0, 0.0};
-  const V3<double> x3 = {c12 * c0, c12 * s0, -s12};
-  const V3<double> z3 = {s12 * c0, s12 * s0, c12};
-  const double rho2 = l1 * c1, h2 = l0 - l1 * s1;
-  const double rho3 = rho2 + l2 * c12, h3 = h2 - l2 * s12;
-  V3<double> On = {rho3 * c0, rho3 * s0, h3};
-  double R[9] = {x3.x, y1.x, z3.x, x3.y, y1.y, z3.y, x3.z, y1.z, z3.z};
-  V3<double> jv[3], jw[3] = {{0.0, 0.0, 1.0}, y1, y1};
-  const V3<double> Ok[3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, l0}, {rho2 * c0, rho2 * s0, h2}};
-  arm_finish<3>(P, R, On, jv, jw, Ok, T, J);
+template <typename S>
+__device__ __forceinline__ void rrr_fk_jac_pose(const ArmPT<S>& P, const S (&q)[3], S (&T)[16], S (&J)[18]) {
+  using M = Sc<S>;
+  S s0, c0, s1, c1, s2, c2;
+  M::sincos(q[0], &s0, &c0);
+  M::sincos(q[1], &s1, &c1);
+  M::sincos(q[2], &s2, &c2);
+  const S c12 = c1 * c2 - s1 * s2, s12 = s1 * c2 + c1 * s2;
+  const S l0 = P.l[0], l1 = P.l[1], l2 = P.l[2];
+  const V3<S> y1 = {-s0, c0, S(0)};
+  const V3<S> x3 = {c12 * c0, c12 * s0, -s12};
+  const V3<S> z3 = {s12 * c0, s12 * s0, c12};
+  const S rho2 = l1 * c1, h2 = l0 - l1 * s1;
+  const S rho3 = rho2 + l2 * c12, h3 = h2 - l2 * s12;
+  V3<S> On = {rho3 * c0, rho3 * s0, h3};
+  S R[9] = {x3.x, y1.x, z3.x, x3.y, y1.y, z3.y, x3.z, y1.z, z3.z};
+  V3<S> jv[3], jw[3] = {{S(0), S(0), S(1)}, y1, y1};
+  const V3<S> Ok[3] = {{S(0), S(0), S(0)}, {S(0), S(0), l0}, {rho2 * c0, rho2 * s0, h2}};
+  arm_finish<S, 3>(P, R, On, jv, jw, Ok, T, J);
 }
 
 // RRRobot.forward_kinematics (rr_robot.py:102-126): Rz(q0) Tx(l0) Rz(q1) Tx(l1)
-__device__ __forceinline__ void rr_fk_jac_pose(const ArmP& P, const double (&q)[2], double (&T)[16],
-                                               double (&J)[12]) {
-  double s0, c0, s1, c1;
-  fast_sincos(q[0], &s0, &c0);
-  fast_sincos(q[1], &s1, &c1);
-  const double c01 = c0 * c1 - s0 * s1, s01 = s0 * c1 + c0 * s1;
-  const double l0 = P.l[0], l1 = P.l[1];
-  V3<double> On = {l0 * c0 + l1 * c01, l0 * s0 + l1 * s01, 0.0};
-  double R[9] = {c01, -s01, 0.0, s01, c01, 0.0, 0.0, 0.0, 1.0};
-  V3<double> jv[2], jw[2] = {{0.0, 0.0, 1.0}, {0.0, 0.0, 1.0}};
-  const V3<double> Ok[2] = {{0.0, 0.0, 0.0}, {l0 * c0, l0 * s0, 0.0}};
-  arm_finish<2>(P, R, On, jv, jw, Ok, T, J);
+template <typename S>
+__device__ __forceinline__ void rr_fk_jac_pose(const ArmPT<S>& P, const S (&q)[2], S (&T)[16], S (&J)[12]) {
+  using M = Sc<S>;
+  S s0, c0, s1, c1;
+  M::sincos(q[0], &s0, &c0);
+  M::sincos(q[1], &s1, &c1);
+  const S c01 = c0 * c1 - s0 * s1, s01 = s0 * c1 + c0 * s1;
+  const S l0 = P.l[0], l1 = P.l[1];
+  V3<S> On = {l0 * c0 + l1 * c01, l0 * s0 + l1 * s01, S(0)};
+  S R[9] = {c01, -s01, S(0), s01, c01, S(0), S(0), S(0), S(1)};
+  V3<S> jv[2], jw[2] = {{S(0), S(0), S(1)}, {S(0), S(0), S(1)}};
+  const V3<S> Ok[2] = {{S(0), S(0), S(0)}, {l0 * c0, l0 * s0, S(0)}};
+  arm_finish<S, 2>(P, R, On, jv, jw, Ok, T, J);
 }
 
 // translation of T_0 = T_base^-1 T T_tool^-1 (rrr_robot.py:159, rr_robot.py:162)
-__device__ __forceinline__ void arm_ik_p0(const ArmP& P, const double (&Tin)[12], double (&p0)[3]) {
-  double A[12], B[12];
+template <typename S>
+__device__ __forceinline__ void arm_ik_p0(const ArmPT<S>& P, const S (&Tin)[12], S (&p0)[3]) {
+  S A[12], B[12];
   if (P.has_base) {
     xf_mul(P.Tbi, Tin, A);
   } else {
@@ -123,65 +146,69 @@ __device__ __forceinline__ void arm_ik_p0(const ArmP& P, const double (&Tin)[12]
 // has just produced with acos/atan2, so those are formed from the operands (as in the Fanuc IK):
 // sin(q2) = m sqrt(1 - cc^2); A = l1 cos q1 + l2 cos(q1 + q2) (:181) is the radial coordinate of the
 // target, i.e. x' itself up to rounding.  acos(cc) = atan2(sqrt((1-cc)(1+cc)), cc).
+template <typename S>
 struct RrrK {          // what depends on the target and on k only
-  double xp, zp, cc, sabs, acosc, beta, gamma;
+  S xp, zp, cc, sabs, acosc, beta, gamma;
   bool reach;
 };
 
-__device__ __forceinline__ RrrK rrr_ik_k(const ArmP& P, const double (&p0)[3], double rxy, int k) {
-  using M = Sc<double>;
-  const double l0 = P.l[0], l1 = P.l[1], l2 = P.l[2];
-  RrrK r;
+template <typename S>
+__device__ __forceinline__ RrrK<S> rrr_ik_k(const ArmPT<S>& P, const S (&p0)[3], S rxy, int k) {
+  using M = Sc<S>;
+  const S l0 = P.l[0], l1 = P.l[1], l2 = P.l[2];
+  RrrK<S> r;
   r.xp = k > 0 ? rxy : -rxy;                                                     // :162
   r.zp = M::sub(l0, p0[2]);                                                      // :163
-  const double num = M::sub(M::sub(M::add(M::mul(r.xp, r.xp), M::mul(r.zp, r.zp)), M::mul(l1, l1)),
-                            M::mul(l2, l2));                                     // :165-166
-  r.cc = M::div(num, M::mul(M::mul(2.0, l1), l2));                               // :167-168
-  r.reach = !(fabs(r.cc) > 1.0);                                                 // :171
-  const double c = r.reach ? r.cc : 0.5;   // unreachable: computed on harmless operands, discarded
-  r.sabs = fast_sqrt((1.0 - c) * (1.0 + c));
-  r.acosc = fast_atan2(r.sabs, c);                                               // :175 (|q2|)
-  r.beta = fast_atan2(l2 * r.sabs, l1 + l2 * c);                                 // :177-178, m = +1
-  r.gamma = fast_atan2(r.zp, r.xp);                                              // :179
+  const S num = M::sub(M::sub(M::add(M::mul(r.xp, r.xp), M::mul(r.zp, r.zp)), M::mul(l1, l1)),
+                       M::mul(l2, l2));                                          // :165-166
+  r.cc = M::div(num, M::mul(M::mul(S(2), l1), l2));                              // :167-168
+  r.reach = !(M::abs(r.cc) > S(1));                                              // :171
+  const S c = r.reach ? r.cc : S(0.5);   // unreachable: computed on harmless operands, discarded
+  r.sabs = M::sqrt_fast((S(1) - c) * (S(1) + c));
+  r.acosc = M::atan2_fast(r.sabs, c);                                            // :175 (|q2|)
+  r.beta = M::atan2_fast(l2 * r.sabs, l1 + l2 * c);                              // :177-178, m = +1
+  r.gamma = M::atan2_fast(r.zp, r.xp);                                           // :179
   return r;
 }
 
 // finishes branch (m, k): limits (:191-196) and the zeros-on-failure convention
-__device__ __forceinline__ bool rrr_ik_finish(const ArmP& P, const RrrK& r, double q0atan, int m,
-                                              double (&qo)[3]) {
-  using M = Sc<double>;
-  const double q2 = m > 0 ? r.acosc : -r.acosc;                                  // :175
-  const double q1 = m > 0 ? M::sub(r.gamma, r.beta) : M::add(r.gamma, r.beta);   // :179
-  const double q0 = (fabs(r.xp) < P.eps) ? 0.0 : q0atan;                         // :181-187
-  const double qs[3] = {q0, q1, q2};
+template <typename S>
+__device__ __forceinline__ bool rrr_ik_finish(const ArmPT<S>& P, const RrrK<S>& r, S q0atan, int m,
+                                              S (&qo)[3]) {
+  using M = Sc<S>;
+  const S q2 = m > 0 ? r.acosc : -r.acosc;                                       // :175
+  const S q1 = m > 0 ? M::sub(r.gamma, r.beta) : M::add(r.gamma, r.beta);        // :179
+  const S q0 = (M::abs(r.xp) < P.eps) ? S(0) : q0atan;                           // :181-187
+  const S qs[3] = {q0, q1, q2};
   bool out = !r.reach;
 #pragma unroll
   for (int j = 0; j < 3; ++j) out = out || (qs[j] < P.lo[j]) || (qs[j] > P.hi[j]);
 #pragma unroll
-  for (int j = 0; j < 3; ++j) qo[j] = out ? 0.0 : qs[j];
+  for (int j = 0; j < 3; ++j) qo[j] = out ? S(0) : qs[j];
   return !out;
 }
 
-__device__ __forceinline__ bool rrr_ik_branch(const ArmP& P, const double (&p0)[3], int m, int k,
-                                              double (&qo)[3]) {
-  using M = Sc<double>;
-  const double x = p0[0], y = p0[1];
-  const double rxy = M::sqrt(M::add(M::mul(x, x), M::mul(y, y)));                // :162
-  const RrrK r = rrr_ik_k(P, p0, rxy, k);
-  return rrr_ik_finish(P, r, fast_atan2(y, x), m, qo);
+template <typename S>
+__device__ __forceinline__ bool rrr_ik_branch(const ArmPT<S>& P, const S (&p0)[3], int m, int k, S (&qo)[3]) {
+  using M = Sc<S>;
+  const S x = p0[0], y = p0[1];
+  const S rxy = M::sqrt(M::add(M::mul(x, x), M::mul(y, y)));                     // :162
+  const RrrK<S> r = rrr_ik_k(P, p0, rxy, k);
+  return rrr_ik_finish(P, r, M::atan2_fast(y, x), m, qo);
 }
 
 // The canonical 4 branches (m outer, k inner) of one target in one thread: atan2(y, x) once,
 // acos / beta / gamma once per k (beta is odd in m) -- 7 atan2 instead of 16.
-__device__ __forceinline__ void rrr_ik4_pose(const ArmP& P, const double (&p0)[3], double (&qo)[4][3],
+template <typename S>
+__device__ __forceinline__ void rrr_ik4_pose(const ArmPT<S>& P, const S (&p0)[3], S (&qo)[4][3],
                                              bool (&ok)[4]) {
-  using M = Sc<double>;
-  const double x = p0[0], y = p0[1];
-  const double rxy = M::sqrt(M::add(M::mul(x, x), M::mul(y, y)));
-  const double q0 = fast_atan2(y, x);
+  using M = Sc<S>;
+  const S x = p0[0], y = p0[1];
+  const S rxy = M::sqrt(M::add(M::mul(x, x), M::mul(y, y)));
+  const S q0 = M::atan2_fast(y, x);
 #pragma unroll
   for (int ki = 0; ki < 2; ++ki) {
-    const RrrK r = rrr_ik_k(P, p0, rxy, ki ? -1 : 1);
+    const RrrK<S> r = rrr_ik_k(P, p0, rxy, ki ? -1 : 1);
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi) ok[mi * 2 + ki] = rrr_ik_finish(P, r, q0, mi ? -1 : 1, qo[mi * 2 + ki]);
   }
@@ -189,36 +216,37 @@ __device__ __forceinline__ void rrr_ik4_pose(const ArmP& P, const double (&p0)[3
 
 // RRRobot.inverse_kinematics (rr_robot.py:147-195): both elbow signs share acos, beta (odd in m)
 // and atan2(y, x).
-__device__ __forceinline__ void rr_ik2_pose(const ArmP& P, const double (&p0)[3], double (&qo)[2][2],
+template <typename S>
+__device__ __forceinline__ void rr_ik2_pose(const ArmPT<S>& P, const S (&p0)[3], S (&qo)[2][2],
                                             bool (&ok)[2]) {
-  using M = Sc<double>;
-  const double l0 = P.l[0], l1 = P.l[1];
-  const double x = p0[0], y = p0[1];
-  const double num = M::sub(M::sub(M::add(M::mul(x, x), M::mul(y, y)), M::mul(l0, l0)),
-                            M::mul(l1, l1));                                     // :167
-  const double cc = M::div(num, M::mul(M::mul(2.0, l0), l1));                    // :168-169
-  const bool reach = !(fabs(cc) > 1.0);                                          // :172
-  const double c = reach ? cc : 0.5;
-  const double sabs = fast_sqrt((1.0 - c) * (1.0 + c));
-  const double acosc = fast_atan2(sabs, c);                                      // :176
-  const double beta = fast_atan2(l1 * sabs, l0 + l1 * c);                        // :177-178, m = +1
-  const double th = fast_atan2(y, x);
+  using M = Sc<S>;
+  const S l0 = P.l[0], l1 = P.l[1];
+  const S x = p0[0], y = p0[1];
+  const S num = M::sub(M::sub(M::add(M::mul(x, x), M::mul(y, y)), M::mul(l0, l0)),
+                       M::mul(l1, l1));                                          // :167
+  const S cc = M::div(num, M::mul(M::mul(S(2), l0), l1));                        // :168-169
+  const bool reach = !(M::abs(cc) > S(1));                                       // :172
+  const S c = reach ? cc : S(0.5);
+  const S sabs = M::sqrt_fast((S(1) - c) * (S(1) + c));
+  const S acosc = M::atan2_fast(sabs, c);                                        // :176
+  const S beta = M::atan2_fast(l1 * sabs, l0 + l1 * c);                          // :177-178, m = +1
+  const S th = M::atan2_fast(y, x);
 #pragma unroll
   for (int mi = 0; mi < 2; ++mi) {
-    const double q1 = mi ? -acosc : acosc;
-    const double q0 = mi ? M::add(th, beta) : M::sub(th, beta);                  // :179
-    const double qs[2] = {q0, q1};
+    const S q1 = mi ? -acosc : acosc;
+    const S q0 = mi ? M::add(th, beta) : M::sub(th, beta);                       // :179
+    const S qs[2] = {q0, q1};
     bool out = !reach;
 #pragma unroll
     for (int j = 0; j < 2; ++j) out = out || (qs[j] < P.lo[j]) || (qs[j] > P.hi[j]);
-    qo[mi][0] = out ? 0.0 : q0, qo[mi][1] = out ? 0.0 : q1;
+    qo[mi][0] = out ? S(0) : q0, qo[mi][1] = out ? S(0) : q1;
     ok[mi] = !out;
   }
 }
 
-__device__ __forceinline__ bool rr_ik_branch(const ArmP& P, const double (&p0)[3], int m,
-                                             double (&qo)[2]) {
-  double q2[2][2];
+template <typename S>
+__device__ __forceinline__ bool rr_ik_branch(const ArmPT<S>& P, const S (&p0)[3], int m, S (&qo)[2]) {
+  S q2[2][2];
   bool ok[2];
   rr_ik2_pose(P, p0, q2, ok);
   const int mi = m > 0 ? 0 : 1;

@@ -118,7 +118,7 @@ struct Sc<float> {
   static __device__ __forceinline__ float cos(float x) { return ::cosf(x); }
   static __device__ __forceinline__ float acos(float x) { return ::acosf(x); }
   static __device__ __forceinline__ float atan2(float y, float x) { return ::atan2f(y, x); }
-  static __device__ __forceinline__ float atan2_fast(float y, float x) { return ::atan2f(y, x); }
+  static __device__ __forceinline__ float atan2_fast(float y, float x);
   static __device__ __forceinline__ float atan2_core(float y, float x, bool& rare);
   static __device__ __forceinline__ float rcp_fast(float x) {  // normal finite x, <= 1 ulp
     float r;
@@ -329,6 +329,12 @@ __device__ __forceinline__ float fast_atan2f_core(float y, float x, bool& rare) 
 __device__ __forceinline__ float Sc<float>::atan2_core(float y, float x, bool& rare) {
   return fast_atan2f_core(y, x, rare);
 }
+__device__ __forceinline__ float Sc<float>::atan2_fast(float y, float x) {
+  bool rare = false;
+  float a = fast_atan2f_core(y, x, rare);
+  if (rare) a = ::atan2f(y, x);
+  return a;
+}
 
 __device__ __forceinline__ double Sc<double>::atan2_fast(double y, double x) { return fast_atan2(y, x); }
 __device__ __forceinline__ double Sc<double>::atan2_core(double y, double x, bool& rare) {
@@ -494,6 +500,48 @@ __device__ __forceinline__ void xf_mul(const S* A, const S* B, S* C) {
       C[i * 4 + j] = acc;
     }
   }
+}
+
+// Solve A x = b for a small dense system held in registers (N <= 6): Gaussian elimination with
+// partial pivoting.  Every index is static -- the pivot row is brought up by conditional swaps, not
+// by an indexed access -- so A and b never leave the register file.  x overwrites b; returns false
+// when a pivot is exactly zero (the result then holds inf / nan, like a failed np.linalg.inv).
+template <typename S, int N>
+__device__ __forceinline__ bool gauss_solve(S (&A)[N][N], S (&b)[N]) {
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+#pragma unroll
+    for (int r = k + 1; r < N; ++r) {
+      const bool sw = Sc<S>::abs(A[r][k]) > Sc<S>::abs(A[k][k]);
+#pragma unroll
+      for (int c = k; c < N; ++c) {
+        const S t = A[k][c];
+        A[k][c] = sw ? A[r][c] : t;
+        A[r][c] = sw ? t : A[r][c];
+      }
+      const S t = b[k];
+      b[k] = sw ? b[r] : t;
+      b[r] = sw ? t : b[r];
+    }
+    ok = ok && (A[k][k] != S(0));
+    const S inv = S(1) / A[k][k];
+#pragma unroll
+    for (int r = k + 1; r < N; ++r) {
+      const S f = A[r][k] * inv;
+#pragma unroll
+      for (int c = k + 1; c < N; ++c) A[r][c] -= f * A[k][c];
+      b[r] -= f * b[k];
+    }
+  }
+#pragma unroll
+  for (int k = N - 1; k >= 0; --k) {
+    S acc = b[k];
+#pragma unroll
+    for (int c = k + 1; c < N; ++c) acc -= A[k][c] * b[c];
+    b[k] = acc / A[k][k];
+  }
+  return ok;
 }
 
 // ---------------------------------------------------------------------------------

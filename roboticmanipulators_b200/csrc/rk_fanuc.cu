@@ -1084,6 +1084,58 @@ fanuc_ik_list_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant_
   }
 }
 
+// TrajectoryGenerator.get_dq_from_dx (utils/trajectory_generator.py:161-188) for the Fanuc165F:
+// dq = J(q)^-1 dx with the 6x6 Jacobian of K1 (the twist dx = [v; omega]); the Jacobian never
+// leaves the registers, the system is solved in place with partial pivoting.
+template <typename S, bool SOA>
+__global__ void __launch_bounds__(kBlock)
+fanuc_dq_from_dx_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict__ q, const S* __restrict__ dx,
+                        int64_t n, int64_t ld, S* __restrict__ dq, uint8_t* __restrict__ ok) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    S qv[6], b[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      qv[k] = SOA ? __ldcs(q + k * ld + i) : q[i * 6 + k];
+      b[k] = SOA ? __ldcs(dx + k * ld + i) : dx[i * 6 + k];
+    }
+    S Tv[16], Jv[36], dv;
+    fanuc_fk_jac_pose(P, qv, Tv, Jv, dv);
+    S A[6][6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) A[r][c] = Jv[r * 6 + c];
+    const bool good = gauss_solve<S, 6>(A, b);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      if (SOA) __stcs(dq + k * ld + i, b[k]);
+      else dq[i * 6 + k] = b[k];
+    }
+    if (ok) ok[i] = good ? 1 : 0;
+  }
+}
+
+template <typename S>
+static int launch_dq_from_dx(const RkFanuc* robot, const S* q, const S* dx, int64_t n, int64_t ld, int flags,
+                             S* dq, uint8_t* ok, void* stream) {
+  if (!robot || n < 0) return RK_ERR_INVALID_ARG;
+  if (n == 0) return RK_OK;
+  if (!q || !dx || !dq) return RK_ERR_INVALID_ARG;
+  const bool soa = (flags & RK_SOA) != 0;
+  if (soa && ld < n) return RK_ERR_INVALID_ARG;
+  FanucP<S> P = make_params<S>(robot, flags);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (soa) {
+    int grid = stream_grid(fanuc_dq_from_dx_kernel<S, true>, kBlock, 0, n);
+    fanuc_dq_from_dx_kernel<S, true><<<grid, kBlock, 0, st>>>(P, q, dx, n, ld, dq, ok);
+  } else {
+    int grid = stream_grid(fanuc_dq_from_dx_kernel<S, false>, kBlock, 0, n);
+    fanuc_dq_from_dx_kernel<S, false><<<grid, kBlock, 0, st>>>(P, q, dx, n, ld, dq, ok);
+  }
+  return check_launch();
+}
+
 // -----------------------------------------------------------------------------------
 // host launchers
 // -----------------------------------------------------------------------------------
@@ -1310,6 +1362,15 @@ int rk_fanuc_ik_f32(const RkFanuc* robot, const float* T, int64_t n, int64_t ld,
                     const int8_t* branches_mkw, int nb, float* q_out, uint8_t* valid,
                     void* stream) {
   return rk::launch_ik<float>(robot, T, n, ld, flags, branches_mkw, nb, q_out, valid, stream);
+}
+
+int rk_fanuc_dq_from_dx_f64(const RkFanuc* robot, const double* q, const double* dx, int64_t n, int64_t ld,
+                            int flags, double* dq, uint8_t* ok, void* stream) {
+  return rk::launch_dq_from_dx<double>(robot, q, dx, n, ld, flags, dq, ok, stream);
+}
+int rk_fanuc_dq_from_dx_f32(const RkFanuc* robot, const float* q, const float* dx, int64_t n, int64_t ld,
+                            int flags, float* dq, uint8_t* ok, void* stream) {
+  return rk::launch_dq_from_dx<float>(robot, q, dx, n, ld, flags, dq, ok, stream);
 }
 
 int rk_fanuc_fk_jac_ik8_f64(const RkFanuc* robot, const double* q, int64_t n, int64_t ld, int flags,

@@ -139,20 +139,23 @@ __device__ __forceinline__ Equalized<NJ> equalize(const double* __restrict__ q0,
   return e;
 }
 
-// mode 0: joint-space sampler; 1: + RRR FK/Jacobian per sample; 2: Cartesian + RRR IK + dq
-template <int NJ, int MODE>
+// mode 0: joint-space sampler; 1: + RRR FK/Jacobian per sample; 2: Cartesian + RRR IK + dq.
+// SO = type of the OUTPUTS and of the per-sample FK / Jacobian (mode 1).  The profile itself --
+// coefficients, sample counts, sample times, q / dq / ddq -- is always evaluated in FP64 in the
+// reference's operation order (counts must be bit-exact), and rounded to SO on the way out.
+template <int NJ, int MODE, typename SO>
 __global__ void __launch_bounds__(kBlock, MODE == 2 ? 4 : (MODE == 1 ? 2 : 3))
-traj_kernel(const __grid_constant__ ArmP P, const double* __restrict__ q0, const double* __restrict__ qf,
-            int64_t ntraj, int nsteps, double vmax, double amax, double freq, double* __restrict__ q,
-            double* __restrict__ dq, double* __restrict__ ddq, double* __restrict__ t,
-            int32_t* __restrict__ len, double* __restrict__ o1, double* __restrict__ o2,
+traj_kernel(const __grid_constant__ ArmPT<SO> P, const double* __restrict__ q0, const double* __restrict__ qf,
+            int64_t ntraj, int nsteps, double vmax, double amax, double freq, SO* __restrict__ q,
+            SO* __restrict__ dq, SO* __restrict__ ddq, SO* __restrict__ t,
+            int32_t* __restrict__ len, SO* __restrict__ o1, SO* __restrict__ o2,
             uint8_t* __restrict__ valid) {
   constexpr int NST = (MODE == 1) ? Stride<18>::value : Stride<NJ>::value;
-  __shared__ double stage_all[(kBlock / kWarp) * kWarp * NST];
+  __shared__ SO stage_all[(kBlock / kWarp) * kWarp * NST];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* stage = stage_all + warp * kWarp * NST;
+  SO* stage = stage_all + warp * kWarp * NST;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  ArmP bare = P;  // get_symbolic_jacobian_inverse uses identity base/tool (rrr_robot_jacobians.py:19-20)
+  ArmPT<SO> bare = P;  // get_symbolic_jacobian_inverse uses identity base/tool (rrr_robot_jacobians.py:19-20)
   bare.has_base = bare.has_tool = 0;
   for (int64_t tr = (((int64_t)blockIdx.x * blockDim.x) >> 5) + warp; tr < ntraj; tr += warps) {
     const Equalized<NJ> e = equalize<NJ>(q0 + tr * NJ, qf + tr * NJ, vmax, amax, freq, nsteps);
@@ -173,21 +176,24 @@ traj_kernel(const __grid_constant__ ArmP P, const double* __restrict__ q0, const
           trap_sample_joint(e.tt, seg, tk, e.q0[j], e.v[j], e.a[j], qv[j], dqv[j], ddqv[j]);
       }
       const int64_t s0 = tr * nsteps + base;  // first sample of this warp pass
-      if (q) warp_store_aos_ilp<double, NJ>(stage, qv, q + s0 * NJ, cnt, lane);
-      if (dq) warp_store_aos_ilp<double, NJ>(stage, dqv, dq + s0 * NJ, cnt, lane);
-      if (MODE != 2 && ddq) warp_store_aos_ilp<double, NJ>(stage, ddqv, ddq + s0 * NJ, cnt, lane);
-      if (t && lane < cnt) t[s0 + lane] = tout;
+      SO qo[NJ], dqo[NJ], ddqo[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) qo[j] = (SO)qv[j], dqo[j] = (SO)dqv[j], ddqo[j] = (SO)ddqv[j];
+      if (q) warp_store_aos_ilp<SO, NJ>(stage, qo, q + s0 * NJ, cnt, lane);
+      if (dq) warp_store_aos_ilp<SO, NJ>(stage, dqo, dq + s0 * NJ, cnt, lane);
+      if (MODE != 2 && ddq) warp_store_aos_ilp<SO, NJ>(stage, ddqo, ddq + s0 * NJ, cnt, lane);
+      if (t && lane < cnt) t[s0 + lane] = (SO)tout;
       if constexpr (MODE == 1) {
-        double Tv[16], Jv[18];
-        rrr_fk_jac_pose(P, reinterpret_cast<const double(&)[3]>(qv), Tv, Jv);
+        SO Tv[16], Jv[18];
+        rrr_fk_jac_pose(P, reinterpret_cast<const SO(&)[3]>(qo), Tv, Jv);
         if (!live) {
 #pragma unroll
-          for (int k = 0; k < 16; ++k) Tv[k] = 0.0;
+          for (int k = 0; k < 16; ++k) Tv[k] = SO(0);
 #pragma unroll
-          for (int k = 0; k < 18; ++k) Jv[k] = 0.0;
+          for (int k = 0; k < 18; ++k) Jv[k] = SO(0);
         }
-        if (o1) warp_store_aos_ilp<double, 16>(stage, Tv, o1 + s0 * 16, cnt, lane);
-        if (o2) warp_store_aos_ilp<double, 18>(stage, Jv, o2 + s0 * 18, cnt, lane);
+        if (o1) warp_store_aos_ilp<SO, 16>(stage, Tv, o1 + s0 * 16, cnt, lane);
+        if (o2) warp_store_aos_ilp<SO, 18>(stage, Jv, o2 + s0 * 18, cnt, lane);
       }
       if constexpr (MODE == 2) {
         // move_via_points: T_IK = [I | p] -> inverse_kinematics(m=1, k=1) (rrr_robot.py:263-270)
@@ -319,15 +325,14 @@ poly5_kernel(const double* __restrict__ b0, const double* __restrict__ bf, const
   }
 }
 
-template <int NJ, int MODE>
-static int launch_traj(const ArmP& P, const double* q0, const double* qf, int64_t ntraj, int nsteps,
-                       double vmax, double amax, double freq, double* q, double* dq, double* ddq,
-                       double* t, int32_t* len, double* o1, double* o2, uint8_t* valid,
-                       cudaStream_t st) {
+template <int NJ, int MODE, typename SO = double>
+static int launch_traj(const ArmPT<SO>& P, const double* q0, const double* qf, int64_t ntraj, int nsteps,
+                       double vmax, double amax, double freq, SO* q, SO* dq, SO* ddq, SO* t, int32_t* len,
+                       SO* o1, SO* o2, uint8_t* valid, cudaStream_t st) {
   // 2 trajectories per warp (ms per 2^15 x 1000 samples, 6 joints: 8 per warp 0.85, 2: 0.79, 1: 0.79)
-  int grid = stream_grid(traj_kernel<NJ, MODE>, kBlock, 0, ntraj * kWarp, 2);
-  traj_kernel<NJ, MODE><<<grid, kBlock, 0, st>>>(P, q0, qf, ntraj, nsteps, vmax, amax, freq, q, dq,
-                                                 ddq, t, len, o1, o2, valid);
+  int grid = stream_grid(traj_kernel<NJ, MODE, SO>, kBlock, 0, ntraj * kWarp, 2);
+  traj_kernel<NJ, MODE, SO><<<grid, kBlock, 0, st>>>(P, q0, qf, ntraj, nsteps, vmax, amax, freq, q, dq,
+                                                     ddq, t, len, o1, o2, valid);
   return check_launch();
 }
 
@@ -346,7 +351,7 @@ int rk_trap_p2p_f64(const double* q0, const double* qf, int64_t ntraj, int nj, i
   cudaStream_t st = (cudaStream_t)stream;
 #define RK_CASE(N)                                                                            \
   case N:                                                                                     \
-    return rk::launch_traj<N, 0>(P, q0, qf, ntraj, nsteps, v_max, a_max, control_freq, q, dq, \
+    return rk::launch_traj<N, 0, double>(P, q0, qf, ntraj, nsteps, v_max, a_max, control_freq, q, dq, \
                                  ddq, t, len, nullptr, nullptr, nullptr, st);
   switch (nj) {
     RK_CASE(1) RK_CASE(2) RK_CASE(3) RK_CASE(4) RK_CASE(5) RK_CASE(6) RK_CASE(7) RK_CASE(8)
@@ -398,8 +403,19 @@ int rk_rrr_p2p_fk_f64(const RkArm* robot, const double* q0, const double* qf, in
   if (ntraj == 0) return RK_OK;
   if (!q0 || !qf) return RK_ERR_INVALID_ARG;
   rk::ArmP P = rk::make_arm_params(robot);
-  return rk::launch_traj<3, 1>(P, q0, qf, ntraj, nsteps, v_max, a_max, control_freq, q, dq, ddq, t,
+  return rk::launch_traj<3, 1, double>(P, q0, qf, ntraj, nsteps, v_max, a_max, control_freq, q, dq, ddq, t,
                                len, T, J, nullptr, (cudaStream_t)stream);
+}
+
+int rk_rrr_p2p_fk_f32(const RkArm* robot, const double* q0, const double* qf, int64_t ntraj, int nsteps,
+                      double v_max, double a_max, double control_freq, float* q, float* dq, float* ddq,
+                      float* t, int32_t* len, float* T, float* J, void* stream) {
+  if (!robot || ntraj < 0 || nsteps < 1 || !len) return RK_ERR_INVALID_ARG;
+  if (ntraj == 0) return RK_OK;
+  if (!q0 || !qf) return RK_ERR_INVALID_ARG;
+  rk::ArmPT<float> P = rk::make_arm_params_t<float>(robot);
+  return rk::launch_traj<3, 1, float>(P, q0, qf, ntraj, nsteps, v_max, a_max, control_freq, q, dq, ddq, t,
+                                      len, T, J, nullptr, (cudaStream_t)stream);
 }
 
 int rk_rrr_lin_ik_f64(const RkArm* robot, const double* p0, const double* pf, int64_t ntraj,
@@ -410,7 +426,7 @@ int rk_rrr_lin_ik_f64(const RkArm* robot, const double* p0, const double* pf, in
   if (ntraj == 0) return RK_OK;
   if (!p0 || !pf) return RK_ERR_INVALID_ARG;
   rk::ArmP P = rk::make_arm_params(robot);
-  return rk::launch_traj<3, 2>(P, p0, pf, ntraj, nsteps, dx_max, ddx_max, control_freq, x, dx,
+  return rk::launch_traj<3, 2, double>(P, p0, pf, ntraj, nsteps, dx_max, ddx_max, control_freq, x, dx,
                                nullptr, t, len, qj, dqj, valid, (cudaStream_t)stream);
 }
 

@@ -8,10 +8,18 @@ from .. import _batch, _lib
 from .robot import Robot, launch
 
 
+_SFX = {torch.float64: "f64", torch.float32: "f32"}
+
+
+def _dtype_of(x):
+    """float32 inputs run the FP32 kernels; everything else is computed in float64."""
+    return x.dtype if x.dtype in _SFX else torch.float64
+
+
 class _SerialArm(Robot):
     _nq = 3            # number of joints
-    _fk_fn = "rk_rrr_fk_jac_f64"
-    _ik_fn = "rk_rrr_ik_f64"
+    _fk_fn = "rk_rrr_fk_jac_"      # + "f64" / "f32"
+    _ik_fn = "rk_rrr_ik_"
     _canonical = ((1, 1), (1, -1), (-1, 1), (-1, -1))
 
     def _lengths(self):
@@ -41,18 +49,19 @@ class _SerialArm(Robot):
         return st
 
     def forward_kinematics_batch(self, q, *, jacobian=False, layout="auto"):
-        """q CUDA tensor [N, nq] (float64) -> T [N,4,4] (and J [N,6,nq])."""
+        """q CUDA tensor [N, nq] (float64, or float32 for the FP32 kernels) -> T [N,4,4] (and
+        J [N,6,nq]) of the same dtype."""
         _lib.require_cuda(q, "q")
-        nq = self._nq
+        nq, dt = self._nq, _dtype_of(q)
         if layout == "auto":
             layout = _batch.detect_layout(q, nq)
-        qs, ld = _batch.prep_input(q, nq, layout, torch.float64)
+        qs, ld = _batch.prep_input(q, nq, layout, dt)
         n, dev = qs.shape[0], qs.device
-        T, Ts = _batch.alloc_out(n, (4, 4), layout, torch.float64, dev)
+        T, Ts = _batch.alloc_out(n, (4, 4), layout, dt, dev)
         J = Js = None
         if jacobian:
-            J, Js = _batch.alloc_out(n, (6, nq), layout, torch.float64, dev)
-        launch(getattr(_lib.load(), self._fk_fn), dev, self._cached_struct(), _lib.ptr(qs), n, ld,
+            J, Js = _batch.alloc_out(n, (6, nq), layout, dt, dev)
+        launch(getattr(_lib.load(), self._fk_fn + _SFX[dt]), dev, self._cached_struct(), _lib.ptr(qs), n, ld,
                _batch.flags_of(layout), _lib.ptr(Ts), _lib.ptr(Js))
         return (T, J) if jacobian else T
 
@@ -61,25 +70,25 @@ class _SerialArm(Robot):
         (default: the canonical order, m outer, k inner)."""
         _lib.require_cuda(T, "T")
         branches = self._canonical if branches is None else branches
-        n = T.shape[0]
+        n, dt = T.shape[0], _dtype_of(T)
         T2 = T.reshape(n, 16) if T.dim() == 3 else T
         if layout == "auto":
             layout = _batch.detect_layout(T2, 16)
-        Ts, ld = _batch.prep_input(T2, 16, layout, torch.float64)
+        Ts, ld = _batch.prep_input(T2, 16, layout, dt)
         dev, nb, nq = Ts.device, len(branches), self._nq
         flat = []
         for b in branches:
             flat.extend([int(v) for v in (b if isinstance(b, (tuple, list)) else (b,))])
         br = (C.c_int8 * len(flat))(*flat)
         if layout == "soa":
-            qstore = torch.empty((nb * nq, n), dtype=torch.float64, device=dev)
+            qstore = torch.empty((nb * nq, n), dtype=dt, device=dev)
             vstore = torch.empty((nb, n), dtype=torch.uint8, device=dev)
             qv, vv = qstore.view(nb, nq, n).permute(2, 0, 1), vstore.t()
         else:
-            qstore = torch.empty((n, nb, nq), dtype=torch.float64, device=dev)
+            qstore = torch.empty((n, nb, nq), dtype=dt, device=dev)
             vstore = torch.empty((n, nb), dtype=torch.uint8, device=dev)
             qv, vv = qstore, vstore
-        launch(getattr(_lib.load(), self._ik_fn), dev, self._cached_struct(), _lib.ptr(Ts), n, ld,
+        launch(getattr(_lib.load(), self._ik_fn + _SFX[dt]), dev, self._cached_struct(), _lib.ptr(Ts), n, ld,
                _batch.flags_of(layout), br, nb, _lib.ptr(qstore), _lib.ptr(vstore))
         return qv, vv.view(torch.bool)
 

@@ -211,6 +211,29 @@ class Fanuc165F(Robot):
                _lib.ptr(det), _lib.ptr(qstore), _lib.ptr(vstore))
         return T, J, det, qv, vv.view(torch.bool)
 
+    def dq_from_dx_batch(self, q, dx, *, layout="aos", user_angles=True):
+        """Joint rates from Cartesian twists: dq = J(q)^-1 dx for N poses, solved in the kernel that
+        computes the 6x6 Jacobian (TrajectoryGenerator.get_dq_from_dx, utils/trajectory_generator.py:
+        161-188, for this robot).  q, dx: CUDA [N, 6] (dx = [v; omega]); user_angles=True returns
+        rates of the USER joint angles (columns scaled by qs_directions).  Returns (dq [N, 6],
+        ok [N] bool -- False where J is exactly singular)."""
+        _lib.require_cuda(q, "q")
+        _lib.require_cuda(dx, "dx")
+        if q.dtype not in _DTYPES:
+            raise TypeError("q must be float64 or float32")
+        if layout not in ("aos", "soa"):
+            raise ValueError("layout must be 'aos' or 'soa'")
+        qs, ld = _batch.prep_input(q, 6, layout, q.dtype)
+        ds, _ = _batch.prep_input(dx.reshape(dx.shape[0], 6), 6, layout, q.dtype)
+        n, dev = qs.shape[0], qs.device
+        dq, dqs = _batch.alloc_out(n, (6,), layout, q.dtype, dev)
+        ok = torch.empty(n, dtype=torch.uint8, device=dev)
+        flags = _batch.flags_of(layout) | (_lib.RK_JAC_USER_ANGLES if user_angles else 0)
+        fn = getattr(_lib.load(), "rk_fanuc_dq_from_dx_" + _DTYPES[q.dtype])
+        launch(fn, dev, self._cached_struct(), _lib.ptr(qs), _lib.ptr(ds), n, ld, flags, _lib.ptr(dqs),
+               _lib.ptr(ok))
+        return dq, ok.view(torch.bool)
+
     _STREAM_OUT = {"T": (4, 4), "J": (6, 6), "det": (), "q_ik": (8, 6), "valid": (8,)}
 
     def fk_jac_ik_stream(self, q, *, want=("T", "J", "det", "q_ik", "valid"), out=None,

@@ -7,7 +7,7 @@ class RRRobot(_SerialArm):
 
     qs_lim_deg = ((-360.0, 360.0), (-360.0, 360.0))
     _nq = 2
-    _fk_fn, _ik_fn = "rk_rr_fk_jac_f64", "rk_rr_ik_f64"
+    _fk_fn, _ik_fn = "rk_rr_fk_jac_", "rk_rr_ik_"
     _canonical = (1, -1)
 
     def __init__(self, T_base=None, T_tool=None, lengths=None, save=True):

@@ -13,7 +13,7 @@ class RRRRobot(_SerialArm):
                   (-360.0, 360.0),
                   (-360.0, 360.0))
     _nq = 3
-    _fk_fn, _ik_fn = "rk_rrr_fk_jac_f64", "rk_rrr_ik_f64"
+    _fk_fn, _ik_fn = "rk_rrr_fk_jac_", "rk_rrr_ik_"
     _canonical = ((1, 1), (1, -1), (-1, 1), (-1, -1))
 
     def __init__(self, T_base=None, T_tool=None):

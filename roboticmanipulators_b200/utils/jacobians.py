@@ -115,6 +115,18 @@ class JacobianCalculator():
                            active=[int(bool(a)) for a in self._ind], layout=layout)
         return (T, J) if with_pose else J
 
+    def dq_from_dx_batch(self, values, dx, rows=None, T_base=None, T_tool=None):
+        """Joint rates from Cartesian rates for N samples: solves J[rows, :] dq = dx in the kernel
+        (TrajectoryGenerator.get_dq_from_dx for any chain, utils/trajectory_generator.py:161-188).
+        values CUDA [N, ntok], dx CUDA [N, n_active]; rows = the Jacobian rows that form the square
+        system (default 0 .. n_active-1).  Returns (dq [N, n_active], ok [N] bool)."""
+        from .robo_math import chain_dq_from_dx
+        T_base = self.T_base if T_base is None else T_base
+        T_tool = self.T_tool if T_tool is None else T_tool
+        return chain_dq_from_dx(self._tokens, values, dx, [int(bool(a)) for a in self._ind], rows=rows,
+                                T_base=np.array(T_base, dtype=np.float64),
+                                T_tool=np.array(T_tool, dtype=np.float64))
+
     def calculate_numerically(self, values, T_base=None, T_tool=None):
         """utils/jacobians.py:166-184; returns a 6 x n_active sp.Matrix."""
         import torch

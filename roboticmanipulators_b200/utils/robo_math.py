@@ -323,11 +323,12 @@ class Point3D():
 # --------------------------------------------------------------------------------------
 # C-ABI glue for the generic chain interpreter
 # --------------------------------------------------------------------------------------
-_OPCODE = {"T": 0, "R": 1, "Ti": 2, "Ri": 3}
+_OPCODE = {"T": 0, "R": 1, "Ti": 2, "Ri": 3, "Td": 4, "Rd": 5}
 
 
 def opcode(token):
-    if token not in TOKENS or token.endswith("d"):
+    """kind * 3 + axis of include/rk_b200.h: all 18 tokens of utils/robo_math.py:368-387."""
+    if token not in TOKENS:
         raise ValueError("Unknown token")
     return _OPCODE[token[0] + token[2:]] * 3 + _AXIS[token[1]]
 
@@ -354,30 +355,62 @@ def make_chain_struct(tokens, active=None, src=None, cst=None, T_base=None, T_to
 
 def chain_batch(tokens, values, *, T_base=None, T_tool=None, active=None, src=None, cst=None,
                 layout="auto", want_T=True):
-    """Run rk_chain_fk_jac_f64 on a CUDA tensor of token values [N, nvals]."""
+    """Run rk_chain_fk_jac_f64 / _f32 on a CUDA tensor of token values [N, nvals] (float32 values
+    run the FP32 kernel, anything else is computed in float64)."""
     import torch
     from .. import _batch, _lib
+    from ..robots.robot import launch
     _lib.require_cuda(values, "values")
     if active is not None and len(active) != len(tokens):
         raise ValueError("Size of indices does not match")
     nvals = values.shape[1]
     if src is None and nvals != len(tokens):
         raise ValueError("Transformation and values sizes do not match")
+    dt = torch.float32 if values.dtype == torch.float32 else torch.float64
     if layout == "auto":
         layout = _batch.detect_layout(values, nvals)
-    vs, ld = _batch.prep_input(values, nvals, layout, torch.float64)
+    vs, ld = _batch.prep_input(values, nvals, layout, dt)
     n, dev = vs.shape[0], vs.device
     ch = make_chain_struct(tokens, active, src, cst, T_base, T_tool)
     T = Ts = J = Js = None
     if want_T:
-        T, Ts = _batch.alloc_out(n, (4, 4), layout, torch.float64, dev)
+        T, Ts = _batch.alloc_out(n, (4, 4), layout, dt, dev)
     na = int(sum(1 for a in active if a)) if active is not None else 0
     if na:
-        J, Js = _batch.alloc_out(n, (6, na), layout, torch.float64, dev)
-    with torch.cuda.device(dev):
-        _lib.check(_lib.load().rk_chain_fk_jac_f64(
-            C.byref(ch), _lib.ptr(vs), nvals, n, ld, _batch.flags_of(layout), _lib.ptr(Ts),
-            _lib.ptr(Js), _lib.stream_ptr(dev)))
+        J, Js = _batch.alloc_out(n, (6, na), layout, dt, dev)
+    fn = _lib.load().rk_chain_fk_jac_f64 if dt == torch.float64 else _lib.load().rk_chain_fk_jac_f32
+    launch(fn, dev, C.byref(ch), _lib.ptr(vs), nvals, n, ld, _batch.flags_of(layout), _lib.ptr(Ts),
+           _lib.ptr(Js))
     if active is None:
         return T
     return T, J
+
+
+def chain_dq_from_dx(tokens, values, dx, active, *, rows=None, T_base=None, T_tool=None, src=None,
+                     cst=None):
+    """dq = J[rows, :]^-1 dx for every sample (rk_chain_dq_from_dx_f64): values CUDA [N, nvals],
+    dx CUDA [N, na], na = number of active tokens (<= 6).  Returns (dq [N, na], ok [N] bool)."""
+    import torch
+    from .. import _lib
+    from ..robots.robot import launch
+    _lib.require_cuda(values, "values")
+    _lib.require_cuda(dx, "dx")
+    na = int(sum(1 for a in active if a))
+    if not 1 <= na <= 6:
+        raise ValueError("between 1 and 6 active tokens are needed for a square system")
+    if dx.shape[-1] != na:
+        raise ValueError("dx must have one column per active token")
+    vs = values.to(torch.float64).contiguous()
+    d = dx.to(torch.float64).contiguous()
+    n, dev = vs.shape[0], vs.device
+    ch = make_chain_struct(tokens, active, src, cst, T_base, T_tool)
+    rows_c = None
+    if rows is not None:
+        if len(rows) != na:
+            raise ValueError("rows must name one Jacobian row per active token")
+        rows_c = (C.c_int32 * na)(*[int(r) for r in rows])
+    dq = torch.empty((n, na), dtype=torch.float64, device=dev)
+    ok = torch.empty(n, dtype=torch.uint8, device=dev)
+    launch(_lib.load().rk_chain_dq_from_dx_f64, dev, C.byref(ch), _lib.ptr(vs), vs.shape[1], rows_c,
+           _lib.ptr(d), n, n, _lib.RK_AOS, _lib.ptr(dq), _lib.ptr(ok))
+    return dq, ok.view(torch.bool)

@@ -28,23 +28,26 @@ class TrajectoryGenerator():
         self._control_freq = control_freq
 
     # ------------------------------------------------------------------ batched (GPU)
-    def _p2p(self, qs_0, qs_f, n, v_max, a_max, robot=None, fk=False):
+    def _p2p(self, qs_0, qs_f, n, v_max, a_max, robot=None, fk=False, dtype=torch.float64):
         _lib.require_cuda(qs_0, "qs_0")
         a = qs_0.to(torch.float64).contiguous()
         b = qs_f.to(torch.float64).contiguous()
         N, J = a.shape
         dev = a.device
-        q, dq, ddq = (torch.empty((N, n, J), dtype=torch.float64, device=dev) for _ in range(3))
-        t = torch.empty((N, n), dtype=torch.float64, device=dev)
+        if dtype not in (torch.float64, torch.float32) or (dtype == torch.float32 and not fk):
+            raise ValueError("dtype=torch.float32 is available for the fused FK / Jacobian sampler only")
+        q, dq, ddq = (torch.empty((N, n, J), dtype=dtype, device=dev) for _ in range(3))
+        t = torch.empty((N, n), dtype=dtype, device=dev)
         length = torch.empty(N, dtype=torch.int32, device=dev)
         lib = _lib.load()
         with torch.cuda.device(dev):
             if fk:
                 if J != 3:
                     raise ValueError("fused FK needs the 3-joint RRR robot")
-                T = torch.empty((N, n, 4, 4), dtype=torch.float64, device=dev)
-                Jm = torch.empty((N, n, 6, 3), dtype=torch.float64, device=dev)
-                _lib.check(lib.rk_rrr_p2p_fk_f64(
+                T = torch.empty((N, n, 4, 4), dtype=dtype, device=dev)
+                Jm = torch.empty((N, n, 6, 3), dtype=dtype, device=dev)
+                fn = lib.rk_rrr_p2p_fk_f64 if dtype == torch.float64 else lib.rk_rrr_p2p_fk_f32
+                _lib.check(fn(
                     C.byref(robot._struct()), _lib.ptr(a), _lib.ptr(b), N, int(n), float(v_max),
                     float(a_max), float(self._control_freq), _lib.ptr(q), _lib.ptr(dq),
                     _lib.ptr(ddq), _lib.ptr(t), _lib.ptr(length), _lib.ptr(T), _lib.ptr(Jm),
@@ -56,15 +59,18 @@ class TrajectoryGenerator():
                 _lib.ptr(length), _lib.stream_ptr(dev)))
         return q, dq, ddq, t, length
 
-    def generate_p2p_trajectory_batch(self, qs_0, qs_f, n=100, robot=None):
+    def generate_p2p_trajectory_batch(self, qs_0, qs_f, n=100, robot=None, dtype=torch.float64):
         """Equalised trapezoidal joint trajectories for N (start, goal) pairs.
 
         qs_0, qs_f: CUDA tensors [N, J], J <= 8.  Returns q, dq, ddq [N, n, J], t [N, n]
         and length [N]: the reference produces FEWER than n samples; rows >= length[i] are
         zero padding and length[i] == 0 marks a trajectory for which the reference raises.
         With robot=RRRRobot(...) the per-sample forward kinematics and 6x3 Jacobian are
-        fused into the same launch and T [N,n,4,4], J [N,n,6,3] are returned as well."""
-        return self._p2p(qs_0, qs_f, n, self._dq_max, self._ddq_max, robot, fk=robot is not None)
+        fused into the same launch and T [N,n,4,4], J [N,n,6,3] are returned as well; with
+        dtype=torch.float32 the outputs and that per-sample FK are FP32 while the profile (hence
+        `length`) is still evaluated in FP64, bit-identical to the FP64 call."""
+        return self._p2p(qs_0, qs_f, n, self._dq_max, self._ddq_max, robot, fk=robot is not None,
+                         dtype=dtype)
 
     def generate_lin_trajectory_batch(self, p_0, p_f, n=100, robot=None):
         """Cartesian straight-line trajectories for N (p_0, p_f) pairs ([N,3] CUDA tensors).
@@ -100,10 +106,28 @@ class TrajectoryGenerator():
 
     @staticmethod
     def get_dq_from_dx_batch(qs, dxs, robot):
-        """dq = J_v(q)^-1 dx for [N,3] CUDA tensors through the RRR Jacobian kernel."""
-        bare = type(robot)()
-        _, J = bare.forward_kinematics_batch(qs, jacobian=True, layout="aos")
-        return torch.linalg.solve(J[:, :3, :3], dxs.to(torch.float64).unsqueeze(-1)).squeeze(-1)
+        """dq = J(q)^-1 dx for N samples, the Jacobian formed and the system solved inside one kernel
+        (no library solve).  `robot` selects the Jacobian:
+          * RRRRobot: the 3x3 position block of RzTzRyTxRyTx with the robot's link lengths and identity
+            base / tool, as rrr_robot_jacobians.py:14-46 builds the reference's J_inv; qs, dxs [N,3];
+          * Fanuc165F: the 6x6 Jacobian w.r.t. the user joint angles; qs [N,6], dxs [N,6] twists;
+          * JacobianCalculator: any chain -- qs are the token values [N, ntok], dxs [N, n_active], the
+            first n_active Jacobian rows form the system (see JacobianCalculator.dq_from_dx_batch).
+        Returns dq (same shape as dxs)."""
+        from ..robots.fanuc import Fanuc165F
+        from ..robots.rrr_robot import RRRRobot
+        from .jacobians import JacobianCalculator
+        from .robo_math import chain_dq_from_dx
+        if isinstance(robot, Fanuc165F):
+            return robot.dq_from_dx_batch(qs, dxs)[0]
+        if isinstance(robot, JacobianCalculator):
+            return robot.dq_from_dx_batch(qs, dxs)[0]
+        if isinstance(robot, RRRRobot):
+            ls = [float(v) for v in robot.ls]
+            return chain_dq_from_dx(["Rz", "Tz", "Ry", "Tx", "Ry", "Tx"], qs.to(torch.float64), dxs,
+                                    [1, 0, 1, 0, 1, 0], rows=(0, 1, 2), src=[0, -1, 1, -1, 2, -1],
+                                    cst=[0.0, ls[0], 0.0, ls[1], 0.0, ls[2]])[0]
+        raise TypeError("robot must be an RRRRobot, a Fanuc165F or a JacobianCalculator")
 
     # ------------------------------------------------------------- reference methods
     def generate_joint_poly_trajectory(self, qs_0, qs_f, t_f, t_0=0.0, n=100, plot=True):
@@ -140,15 +164,39 @@ class TrajectoryGenerator():
         q, dq, ddq, t = self._single(qs_0, qs_f, n, self._tg._dq_max, self._tg._ddq_max)
         return list(q.T), list(dq.T), list(ddq.T), t
 
-    def get_dq_from_dx(self, qs, dxs, J_inv=None, ts=None):
-        """trajectory_generator.py:161-188.  qs is [J, L] (as returned by
-        RRRRobot.move_via_points), dxs is [L, 3]; returns dqs [J, L].  J_inv (the
-        reference's symbolic inverse) is accepted and ignored: the numeric RRR Jacobian
-        kernel is used instead."""
-        from ..robots.rrr_robot import RRRRobot
-        q = torch.tensor(np.asarray(qs, dtype=np.float64).T.copy(), device="cuda")
-        dx = torch.tensor(np.asarray(dxs, dtype=np.float64), device="cuda")
-        return self.get_dq_from_dx_batch(q, dx, RRRRobot()).cpu().numpy().T
+    def get_dq_from_dx(self, qs, dxs, J_inv=None, ts=None, robot=None):
+        """trajectory_generator.py:161-188.  qs is [J, L] (as returned by RRRRobot.move_via_points),
+        dxs is [L, J]; returns dqs [J, L].
+
+        The reference takes a SYMBOLIC inverse Jacobian J_inv in the symbols q_0 .. q_{J-1} and
+        evaluates it per sample.  Here:
+          * robot=<RRRRobot | Fanuc165F | JacobianCalculator>: the Jacobian is formed and the system
+            solved on the GPU (get_dq_from_dx_batch) -- the accelerated path;
+          * J_inv given (a sympy Matrix) and no robot: the caller's own expression is evaluated for
+            all samples at once (sympy.lambdify over NumPy arrays on the host: the expression is the
+            caller's, there is no kernel for an arbitrary formula);
+          * neither: the default RRRRobot() of rrr_robot_jacobians.py, on the GPU."""
+        qs = np.asarray(qs, dtype=np.float64)
+        dxs = np.asarray(dxs, dtype=np.float64)
+        if robot is None and J_inv is not None:
+            import sympy as sp
+            nq = qs.shape[0]
+            syms = [sp.symbols(f"q_{i}") for i in range(nq)]
+            f = sp.lambdify(syms, sp.Matrix(J_inv), "numpy")
+            L = qs.shape[1]
+            rows, cols = sp.Matrix(J_inv).shape
+            Ji = np.empty((L, rows, cols))
+            ev = f(*[qs[i] for i in range(nq)])
+            for r in range(rows):
+                for c in range(cols):
+                    Ji[:, r, c] = np.broadcast_to(np.asarray(ev[r][c], dtype=np.float64), (L,))
+            return np.einsum("lrc,lc->rl", Ji, dxs)
+        if robot is None:
+            from ..robots.rrr_robot import RRRRobot
+            robot = RRRRobot()
+        q = torch.tensor(qs.T.copy(), device="cuda")
+        dx = torch.tensor(dxs, device="cuda")
+        return self.get_dq_from_dx_batch(q, dx, robot).cpu().numpy().T
 
     def interpolate(self, p_start, p_finish, n):
         """Linear interpolation between two points (trajectory_generator.py:190-204)."""
