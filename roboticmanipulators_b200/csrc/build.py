@@ -61,7 +61,7 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-cudart", "static"])
+    subprocess.check_call([nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-cudart", "static", "-ldl"])
     return LIB
 
 

@@ -98,7 +98,7 @@ arm_ik_kernel(const __grid_constant__ ArmPT<S> P, const __grid_constant__ ArmBra
 // by the branches is done once (rrr_ik4_pose / rr_ik2_pose).  The arms' IK is position-only, so
 // without a base / tool transform only the translation column of T is read (24 of 128 bytes).
 template <typename S, int NQ, bool SOA>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 8)
 arm_ik_pose_kernel(const __grid_constant__ ArmPT<S> P, const S* __restrict__ T, int64_t n, int64_t ld,
                    S* __restrict__ q_out, uint8_t* __restrict__ valid) {
   constexpr int NB = (NQ == 3) ? 4 : 2;

@@ -16,27 +16,9 @@
 #include <cmath>
 #include <cstring>
 
-#include "rk_common.cuh"
+#include "rk_chain.cuh"
 
 namespace rk {
-
-constexpr int kMaxConst = 16;   // folded constant segments per chain
-
-enum : int { ST_TRANS = 0, ST_ROT = 1, ST_CONST = 2, ST_CONST_T = 3, ST_DTRANS = 4, ST_DROT = 5 };
-
-template <typename S>
-struct ChainProg {
-  int nstep, nvar, na, has_deriv, has_base, has_tool;
-  int nslot;                     // staged values per sample: nvar + one cosine slot per variable rotation
-  int8_t kind[RK_MAX_TOKENS], axis[RK_MAX_TOKENS], neg[RK_MAX_TOKENS], active[RK_MAX_TOKENS];
-  int8_t code[RK_MAX_TOKENS];    // kind * 3 + axis (axis 0 for the constant kinds)
-  int8_t slot[RK_MAX_TOKENS];    // variable steps: index into the staged values; constant steps: pool index
-  int8_t cslot[RK_MAX_TOKENS];   // variable rotation steps: slot of the cosine parked by the first walk
-  int16_t plane[RK_MAX_TOKENS];  // values column of variable slot v
-  int8_t rows[6];                // solve mode: Jacobian rows that form the square system
-  S X[kMaxConst][12];
-  S Tb[12], Tt[12];
-};
 
 // ---- host: compile RkChain -> ChainProg -------------------------------------------------
 static void h_ident(double* X) {
@@ -353,6 +335,10 @@ static int launch_chain(const RkChain* chain, const S* values, int nvals, int64_
   if (J && Pg.na == 0) J = nullptr;
   if (!T && !J) return RK_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  // straight-line code specialised for this chain (compiled once, rk_chain_jit.cu) when NVRTC is
+  // there; the interpreting kernel below otherwise
+  rc = chain_jit_launch<S>(Pg, soa, values, nvals, n, ld, T, J, st);
+  if (rc != RK_ERR_UNSUPPORTED) return rc;
   const size_t smem = (size_t)(9 + (J ? Pg.nslot : Pg.nvar)) * kBlock * sizeof(S);
   if (soa) {
     auto kern = chain_kernel<S, true, 0, 1>;

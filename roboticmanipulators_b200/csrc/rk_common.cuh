@@ -44,6 +44,7 @@ inline bool allow_dynamic_smem(K kernel, size_t bytes) {
 // costs ~2 us and used to be made on every launch (at 1e4 poses the kernel itself runs 1.5 us).
 // Returns resident CTAs on the whole device (SM count x CTAs per SM).  Defined in rk_api.cu.
 int64_t cached_resident_ctas(const void* kernel, int block, size_t smem);
+int sm_count();  // SMs of the current device (rk_api.cu)
 
 template <typename K>
 inline int persistent_grid(K kernel, int block, size_t smem, int64_t work_items) {

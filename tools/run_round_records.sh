@@ -1,18 +1,33 @@
-# Regenerates the bench records and ncu summaries kept under profiles/ (run on a GPU box).
+# Regenerates the bench records and ncu captures kept under profiles/ (run on a GPU box):
+#   gpurun --timeout 1500 -- 'bash tools/run_round_records.sh r02'
+# Every ncu capture follows a plain run of the same command that exited 0; numbers printed under ncu
+# are never bench values.
+R=${1:-r02}
 set -x
-python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
-python bench.py --workload fk_jac_ik_split --no-cpu > gpurun_out/bench_split.json 2> gpurun_out/bench_split.err
-python bench.py --dtype f32 --no-cpu > gpurun_out/bench_f32.json 2> gpurun_out/bench_f32.err
-python bench.py --layout aos --no-cpu > gpurun_out/bench_aos.json 2> gpurun_out/bench_aos.err
-python bench.py --workload traj > gpurun_out/bench_traj.json 2> gpurun_out/bench_traj.err
-python bench.py --workload calib > gpurun_out/bench_calib.json 2> gpurun_out/bench_calib.err
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:fanuc --csv --log-file gpurun_out/launches_fanuc.csv python bench.py --steps 2 --warmup 3 --batch 8388608 --no-cpu > gpurun_out/ncu1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:fanuc_fk_jac_ik8 -s 3 -c 1 -o gpurun_out/prof_fused -f python bench.py --steps 2 --warmup 3 --batch 8388608 --no-cpu > gpurun_out/ncu2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:fanuc -s 6 -c 2 -o gpurun_out/prof_fanuc -f python bench.py --workload fk_jac_ik_split --steps 2 --warmup 3 --batch 8388608 --no-cpu > gpurun_out/ncu2b.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:calib_normal -s 3 -c 1 -o gpurun_out/prof_calib -f python bench.py --steps 2 --warmup 3 --batch 8388608 --no-cpu --workload calib > gpurun_out/ncu3.log 2>&1
-python tools/bench_rows.py > gpurun_out/rows.json 2> gpurun_out/rows.err
-tail -n 2 gpurun_out/ncu2.log; tail -n 2 gpurun_out/ncu3.log
-# then, in the repo: python tools/ncu_summary.py gpurun_out/prof_fanuc.ncu-rep 8388608 > profiles/rNN_fanuc_ncu_full_summary.json
-#                    python tools/ncu_summary.py gpurun_out/prof_fused.ncu-rep 8388608 > profiles/rNN_fused_ncu_full_summary.json
-#                    python tools/ncu_summary.py gpurun_out/prof_calib.ncu-rep 8388608 > profiles/rNN_calib_ncu_full_summary.json
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q > gpurun_out/${R}_pytest.log 2>&1; tail -n 3 gpurun_out/${R}_pytest.log
+python bench.py --steps 20 --warmup 5 > gpurun_out/${R}_bench_default.json 2> gpurun_out/${R}_bench_default.err || tail -n 5 gpurun_out/${R}_bench_default.err
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${R}_bench_reference_arm.json 2> gpurun_out/${R}_bench_ref.err
+for v in "split:--workload fk_jac_ik_split" "f32:--dtype f32" "aos:--layout aos" "ik_aos:--workload ik --layout aos" "ik_f32:--workload ik --dtype f32" "ik_f32_aos:--workload ik --dtype f32 --layout aos" "fk_jac:--workload fk_jac"; do
+  name=${v%%:*}; flags=${v#*:}
+  python bench.py $flags --no-cpu --no-extras --steps 10 > gpurun_out/${R}_bench_$name.json 2> gpurun_out/${R}_bench_$name.err || tail -n 3 gpurun_out/${R}_bench_$name.err
+done
+python tools/bench_rows.py > gpurun_out/${R}_rows.json 2> gpurun_out/${R}_rows.err
+# launch list of the default command (kernel share of the step)
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'fanuc|calib|traj' --csv --log-file gpurun_out/${R}_launches.csv python bench.py --steps 2 --warmup 3 --batch 8388608 --no-cpu > gpurun_out/${R}_ncu_launches.log 2>&1
+# one full capture per kernel
+cap() { # name, kernel regex, skip, bench flags
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -o gpurun_out/${R}_$1 -f python bench.py $4 --steps 2 --warmup 3 --batch 8388608 --no-cpu --no-extras > gpurun_out/${R}_ncu_$1.log 2>&1
+  tail -n 1 gpurun_out/${R}_ncu_$1.log
+}
+cap fused fanuc_fk_jac_ik8 3 ""
+cap fk_jac fanuc_fk_jac_tma 3 "--workload fk_jac"
+cap ik fanuc_ik8_pose 3 "--workload ik"
+cap ik_aos fanuc_ik8_pose_aos 3 "--workload ik --layout aos"
+cap f32fused fanuc_fk_jac_ik8 3 "--dtype f32"
+cap ik_f32 fanuc_ik8_pose 3 "--workload ik --dtype f32"
+cap calib calib_normal 3 "--workload calib"
+cap traj traj_kernel 3 "--workload traj --batch 32768"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'arm_|rk_chain_jit|chain_kernel|traj_kernel|trap_|poly5|calib_' -o gpurun_out/${R}_rows -f python tools/bench_rows.py --warmup 0 --reps 1 --scale 0.25 > gpurun_out/${R}_ncu_rows.log 2>&1
+tail -n 1 gpurun_out/${R}_ncu_rows.log
+ls -la gpurun_out | grep ${R}_ | wc -l
