@@ -161,8 +161,9 @@ def check(status):
 
 
 def ptr(t):
-    """Device pointer of a torch tensor (or None)."""
-    return None if t is None else C.c_void_p(t.data_ptr())
+    """Device pointer of a torch tensor (or None) -- a plain int: ctypes converts it for a
+    c_void_p parameter, and skipping the c_void_p object saves ~0.4 us per argument."""
+    return None if t is None else t.data_ptr()
 
 
 def stream_ptr(device=None):

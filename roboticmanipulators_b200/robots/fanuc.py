@@ -194,17 +194,14 @@ class Fanuc165F(Robot):
             layout = _batch.detect_layout(q, 6)
         qs, ld = _batch.prep_input(q, 6, layout, q.dtype)
         n, dev = qs.shape[0], qs.device
-        T, Ts = _batch.alloc_out(n, (4, 4), layout, q.dtype, dev)
-        J, Js = _batch.alloc_out(n, (6, 6), layout, q.dtype, dev)
-        det = torch.empty(n, dtype=q.dtype, device=dev)
+        (T, Ts), (J, Js), (det, _), (qv, qstore) = _batch.alloc_outs(
+            n, ((4, 4), (6, 6), (), (8, 6)), layout, q.dtype, dev)
         if layout == "soa":
-            qstore = torch.empty((48, n), dtype=q.dtype, device=dev)
             vstore = torch.empty((8, n), dtype=torch.uint8, device=dev)
-            qv, vv = qstore.view(8, 6, n).permute(2, 0, 1), vstore.t()
+            vv = vstore.t()
         else:
-            qstore = torch.empty((n, 8, 6), dtype=q.dtype, device=dev)
             vstore = torch.empty((n, 8), dtype=torch.uint8, device=dev)
-            qv, vv = qstore, vstore
+            vv = vstore
         flags = _batch.flags_of(layout) | (_lib.RK_JAC_USER_ANGLES if user_angles else 0)
         fn = getattr(_lib.load(), "rk_fanuc_fk_jac_ik8_" + _DTYPES[q.dtype])
         launch(fn, dev, self._cached_struct(), _lib.ptr(qs), n, ld, flags, _lib.ptr(Ts), _lib.ptr(Js),

@@ -74,11 +74,21 @@ class Robot(ABC):
         return c[4]
 
 
+try:                                      # raw handle of the current stream without building a Stream object
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:                    # pragma: no cover
+    def _raw_stream(index):
+        return torch.cuda.current_stream(index).cuda_stream
+
+
 def launch(fn, dev, *args):
     """Call a C-ABI entry point with `dev` current (kernels launch on the current device) and the
     current torch stream of that device appended as the last argument."""
-    if dev.index is None or dev.index == torch.cuda.current_device():
-        _lib.check(fn(*args, torch.cuda.current_stream().cuda_stream))
+    cur = torch.cuda.current_device()
+    if dev.index is None or dev.index == cur:
+        rc = fn(*args, _raw_stream(cur))
+        if rc:
+            _lib.check(rc)
     else:
         with torch.cuda.device(dev):
-            _lib.check(fn(*args, torch.cuda.current_stream(dev).cuda_stream))
+            _lib.check(fn(*args, _raw_stream(dev.index)))

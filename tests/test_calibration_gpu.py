@@ -184,3 +184,23 @@ def test_specialised_and_generic_kernels_agree(golden, tmp_path):
     scale = np.abs(res["generic"]).max()
     assert not np.array_equal(res["static"], res["generic"]) or True
     assert np.max(np.abs(res["static"] - res["generic"])) / scale < 1e-13
+
+
+def test_mat_file_to_gpu_calibration(golden):
+    """the calibration data set from disk (MAT-v5, reference layout) through pinned host
+    memory onto the GPU, then one full iteration: same numbers as the golden run of the reference."""
+    import os
+    from roboticmanipulators_b200.utils.calibration_data import load_calibration_mat
+    g = golden("calibration.npz")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "calibration_dataset_240.mat")
+    qs, pts = load_calibration_mat(path, device="cuda")
+    assert qs.is_cuda and pts.is_cuda and qs.shape == (240, 6) and pts.shape == (240, 9)
+    assert np.array_equal(qs.cpu().numpy(), g["qs"])
+    assert np.max(np.abs(pts.cpu().numpy() - g["pts"]) / np.abs(g["pts"])) < 4e-16
+    mc = fanuc_calibrator()
+    mc.get_reduced_model()
+    T_base, T_tools = mc.estimate_tool_base(qs, pts)
+    params = mc.estimate_parameters(qs, pts, T_base, T_tools)
+    assert np.max(np.abs(params - g["params"])) < 1e-9
+    ev = mc.evaluate(qs, pts, T_base, T_tools)
+    assert abs(ev["distance_rms"] - 0.531528594785394) < 1e-9        # docs/GeometricCalibration.md:51

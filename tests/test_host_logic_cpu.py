@@ -177,3 +177,24 @@ def test_calibration_mat_roundtrip(golden, tmp_path):
     assert np.max(np.abs(pts - g["pts"])) < 1e-9          # metres <-> millimetres round trip
     qt, pt = load_calibration_mat(path, device="cpu")
     assert qt.dtype == __import__("torch").float64 and tuple(pt.shape) == (240, 9)
+
+
+def test_mat_loader_reproduces_the_reference_dataset(golden):
+    """fanuc_calibration.py:13-20: `load_calibration_mat` on a MAT-v5 file with the reference's layout
+    (q [240,6] rad, mA / mB / mC [240,3] metres) returns the arrays the golden run of the real
+    reference used (calibration.npz qs / pts, captured from scipy.io.loadmat of the reference's own
+    data/calibration_dataset.mat).  tests/golden/calibration_dataset_240.mat was written by
+    save_calibration_mat from those arrays (metres = mm / 1000, hence 1 ulp); where the reference's
+    own file is present (the build container) it must load bit for bit."""
+    import os
+    from roboticmanipulators_b200.utils.calibration_data import load_calibration_mat
+    g = golden("calibration.npz")
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "calibration_dataset_240.mat")
+    qs, pts = load_calibration_mat(here, device=None)
+    assert qs.shape == (240, 6) and pts.shape == (240, 9)
+    assert np.array_equal(qs, g["qs"])
+    assert np.max(np.abs(pts - g["pts"]) / np.abs(g["pts"])) < 4e-16
+    ref = "/root/reference/data/calibration_dataset.mat"
+    if os.path.exists(ref):
+        q2, p2 = load_calibration_mat(ref, device=None)
+        assert np.array_equal(q2, g["qs"]) and np.array_equal(p2, g["pts"])
