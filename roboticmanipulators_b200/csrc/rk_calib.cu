@@ -591,6 +591,15 @@ struct FanucReducedShape {
   static constexpr int NTRANS = 8;  // == number of translation parameters (one 8-column block)
 };
 
+// Slab of the specialised kernel: the three linear rows of a measurement are 20 wide (stride 21), the
+// three angular rows only hold the rotation / residual / zero columns 8..19 (12 wide, stride 13):
+// 52 KB per CTA instead of 64.5 KB, so FOUR CTAs are resident per SM instead of three.  (ncu: the
+// kernel is latency-bound -- issue 38 %, FP64 pipe 28 %, 12 warps per SM -- so resident warps count.)
+constexpr int kRSB = 13;                                  // row stride of the angular rows
+constexpr int kSlabA = (kMeas / 2) * 3 * kRS6;            // doubles in the linear region
+constexpr int kSlabB = (kMeas / 2) * 3 * kRSB;            // doubles in the angular region
+constexpr int kSlabStatic = kSlabA + kSlabB;
+
 template <class Shape>
 static bool shape_matches(const CalibP& P) {
   if (P.nj != Shape::NJ || P.np != Shape::NP) return false;
@@ -625,14 +634,16 @@ static ColMap make_colmap() {
 // column NP, column NP + 1 is zero.
 template <class Shape, int PI>
 __device__ __forceinline__ void static_param(const CalibP& P, const CalibN& N, const Sfx& S,
-                                             double* __restrict__ rows) {
+                                             double* __restrict__ rows, double* __restrict__ rowsB) {
   constexpr int kRowStep = (kMeas / 2) * kRS6;
+  constexpr int kRowStepB = (kMeas / 2) * kRSB;
   const double ax = P.pax[PI][0], ay = P.pax[PI][1], az = P.pax[PI][2];
   const double a0 = S.Q[0] * ax + S.Q[3] * ay + S.Q[6] * az;  // a' = Q^T a
   const double a1 = S.Q[1] * ax + S.Q[4] * ay + S.Q[7] * az;
   const double a2 = S.Q[2] * ax + S.Q[5] * ay + S.Q[8] * az;
   double* col = rows + Shape::pcol(PI);
   if constexpr (Shape::pkind(PI) == 1) {
+    double* colB = rowsB + (Shape::pcol(PI) - Shape::NTRANS);
     const double dx = S.s[0] - P.porg[PI][0], dy = S.s[1] - P.porg[PI][1], dz = S.s[2] - P.porg[PI][2];
     const double b0 = S.Q[0] * dx + S.Q[3] * dy + S.Q[6] * dz + N.tbar[0];  // b'' = Q^T (s - o) + tbar
     const double b1 = S.Q[1] * dx + S.Q[4] * dy + S.Q[7] * dz + N.tbar[1];
@@ -640,11 +651,11 @@ __device__ __forceinline__ void static_param(const CalibP& P, const CalibN& N, c
     col[0 * kRowStep] = N.R[0][0] * (a1 * b2 - a2 * b1);
     col[1 * kRowStep] = N.R[1][1] * (a2 * b0 - a0 * b2);
     col[2 * kRowStep] = N.R[2][2] * (a0 * b1 - a1 * b0);
-    col[3 * kRowStep] = N.R[3][3] * a0 + N.R[3][4] * a1 + N.R[3][5] * a2;
-    col[4 * kRowStep] = N.R[4][4] * a1 + N.R[4][5] * a2;
-    col[5 * kRowStep] = N.R[5][5] * a2;
+    colB[0 * kRowStepB] = N.R[3][3] * a0 + N.R[3][4] * a1 + N.R[3][5] * a2;
+    colB[1 * kRowStepB] = N.R[4][4] * a1 + N.R[4][5] * a2;
+    colB[2 * kRowStepB] = N.R[5][5] * a2;
   } else {
-    // translation column: the angular rows are zero and, by the column order, never read
+    // translation column: the angular rows are zero and, by the column order, not even stored
     col[0 * kRowStep] = N.R[0][0] * a0;
     col[1 * kRowStep] = N.R[1][1] * a1;
     col[2 * kRowStep] = N.R[2][2] * a2;
@@ -652,17 +663,17 @@ __device__ __forceinline__ void static_param(const CalibP& P, const CalibN& N, c
 }
 template <class Shape, int P0, int P1>
 __device__ __forceinline__ void static_params(const CalibP& P, const CalibN& N, const Sfx& S,
-                                              double* __restrict__ rows) {
+                                              double* __restrict__ rows, double* __restrict__ rowsB) {
   if constexpr (P0 < P1) {
-    static_param<Shape, P0>(P, N, S, rows);
-    static_params<Shape, P0 + 1, P1>(P, N, S, rows);
+    static_param<Shape, P0>(P, N, S, rows, rowsB);
+    static_params<Shape, P0 + 1, P1>(P, N, S, rows, rowsB);
   }
 }
 // joints J, J - 1, ..., 0 of the backward walk
 template <class Shape, bool ROLE_A, int J>
 __device__ __forceinline__ void static_joints(const CalibP& P, const CalibN& N, Sfx& S,
                                               const double (&qv)[RK_CALIB_MAX_JOINTS],
-                                              double* __restrict__ rows) {
+                                              double* __restrict__ rows, double* __restrict__ rowsB) {
   constexpr int SPLIT = Shape::SPLIT;
   if constexpr (!(ROLE_A && J < SPLIT)) {
     if (P.seg_trans[J]) {  // S_j = X_j Rot_{j+1} S_{j+1}; a pure translation at the nominal model
@@ -671,25 +682,30 @@ __device__ __forceinline__ void static_joints(const CalibP& P, const CalibN& N, 
       sfx_premul(S, P.seg[J]);
     }
     if constexpr (ROLE_A ? (J >= SPLIT) : (J < SPLIT))
-      static_params<Shape, Shape::pstart(J), Shape::pstart(J + 1)>(P, N, S, rows);
+      static_params<Shape, Shape::pstart(J), Shape::pstart(J + 1)>(P, N, S, rows, rowsB);
     if constexpr (!(ROLE_A && J == SPLIT)) {  // S <- Rot_j(q_j) S_j  (role A never needs Rot_SPLIT)
       const double v = __dadd_rn(__dmul_rn(qv[J], P.jdir[J]), P.joff[J]);  // model_calibration.py:557
       double sn, cs;
       fast_sincos(v, &sn, &cs);
       sfx_rot<Shape::jaxis(J)>(S, sn, cs);
     }
-    if constexpr (J > 0) static_joints<Shape, ROLE_A, J - 1>(P, N, S, qv, rows);
+    if constexpr (J > 0) static_joints<Shape, ROLE_A, J - 1>(P, N, S, qv, rows, rowsB);
   }
 }
 template <class Shape, bool ROLE_A, int PI>
-__device__ __forceinline__ void static_zero_cols(double* __restrict__ rows) {
+__device__ __forceinline__ void static_zero_cols(double* __restrict__ rows, double* __restrict__ rowsB) {
   constexpr int kRowStep = (kMeas / 2) * kRS6;
+  constexpr int kRowStepB = (kMeas / 2) * kRSB;
   if constexpr (PI < Shape::NP) {
     if constexpr (ROLE_A ? (PI >= Shape::pstart(Shape::SPLIT)) : (PI < Shape::pstart(Shape::SPLIT))) {
 #pragma unroll
-      for (int r = 0; r < 6; ++r) rows[r * kRowStep + Shape::pcol(PI)] = 0.0;
+      for (int r = 0; r < 3; ++r) rows[r * kRowStep + Shape::pcol(PI)] = 0.0;
+      if constexpr (Shape::pkind(PI) == 1) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) rowsB[r * kRowStepB + Shape::pcol(PI) - Shape::NTRANS] = 0.0;
+      }
     }
-    static_zero_cols<Shape, ROLE_A, PI + 1>(rows);
+    static_zero_cols<Shape, ROLE_A, PI + 1>(rows, rowsB);
   }
 }
 
@@ -697,14 +713,18 @@ template <class Shape, bool ROLE_A>
 __device__ __forceinline__ double fill_rows6_static(const CalibP& P, const CalibN& N,
                                                     const double (&qv)[RK_CALIB_MAX_JOINTS],
                                                     const double (&pv)[3 * RK_CALIB_MAX_TOOLS], bool live,
-                                                    double* __restrict__ rows) {
+                                                    double* __restrict__ rows, double* __restrict__ rowsB) {
   constexpr int kRowStep = (kMeas / 2) * kRS6;
-  constexpr int NJ = Shape::NJ, NP = Shape::NP;
+  constexpr int kRowStepB = (kMeas / 2) * kRSB;
+  constexpr int NJ = Shape::NJ, NP = Shape::NP, NB0 = Shape::NTRANS;
   if (!live) {  // past the end of the data: this role's columns are zero
-    static_zero_cols<Shape, ROLE_A, 0>(rows);
+    static_zero_cols<Shape, ROLE_A, 0>(rows, rowsB);
     if (!ROLE_A) {
 #pragma unroll
-      for (int r = 0; r < 6; ++r) rows[r * kRowStep + NP] = 0.0, rows[r * kRowStep + NP + 1] = 0.0;
+      for (int r = 0; r < 3; ++r) {
+        rows[r * kRowStep + NP] = 0.0, rows[r * kRowStep + NP + 1] = 0.0;
+        rowsB[r * kRowStepB + NP - NB0] = 0.0, rowsB[r * kRowStepB + NP + 1 - NB0] = 0.0;
+      }
     }
     return 0.0;
   }
@@ -712,7 +732,7 @@ __device__ __forceinline__ double fill_rows6_static(const CalibP& P, const Calib
 #pragma unroll
   for (int k = 0; k < 9; ++k) S.Q[k] = (k % 4 == 0) ? 1.0 : 0.0;
   S.s[0] = S.s[1] = S.s[2] = 0.0;
-  static_joints<Shape, ROLE_A, NJ - 1>(P, N, S, qv, rows);
+  static_joints<Shape, ROLE_A, NJ - 1>(P, N, S, qv, rows, rowsB);
   if (ROLE_A) return 0.0;
   // role B: S = Rot_0 S_0; T_end = T_base S.  Residual of tool t in the end frame:
   // rho_t = R_end^T (p_meas - p_end) - tool_t   (r = p_meas - T[:3,3], model_calibration.py:420)
@@ -736,8 +756,13 @@ __device__ __forceinline__ double fill_rows6_static(const CalibP& P, const Calib
     double acc = 0.0;
 #pragma unroll
     for (int k = 0; k < 3 * RK_CALIB_MAX_TOOLS; ++k) acc = fma(N.Qt[r][k], rho[k], acc);
-    rows[r * kRowStep + NP] = acc;
-    rows[r * kRowStep + NP + 1] = 0.0;
+    if (r < 3) {
+      rows[r * kRowStep + NP] = acc;
+      rows[r * kRowStep + NP + 1] = 0.0;
+    } else {
+      rowsB[(r - 3) * kRowStepB + NP - NB0] = acc;
+      rowsB[(r - 3) * kRowStepB + NP + 1 - NB0] = 0.0;
+    }
   }
   return rr;
 }
@@ -764,29 +789,31 @@ struct GramDmmaSplit {
       GramDmma::mma(acc[0], v0, v0), GramDmma::mma(acc[1], v0, v1), GramDmma::mma(acc[2], v0, v2);
       GramDmma::mma(acc[3], v1, v1), GramDmma::mma(acc[4], v1, v2), GramDmma::mma(acc[5], v2, v2);
     }
+    const double* slabB = slab + kSlabA;  // angular rows: columns 8..19 only, stride kRSB
 #pragma unroll 2
-    for (int g = kGroups / 2 + warp; g < kGroups; g += kMeas / kWarp) {
+    for (int g = warp; g < kGroups / 2; g += kMeas / kWarp) {
       const int row = (g >> 3) * 32 + (g & 7) + 8 * k;
-      const double* rp = slab + row * kRS6 + c;
-      const double v1 = rp[8];
-      const double v2 = c < 4 ? rp[16] : 0.0;
+      const double* rp = slabB + row * kRSB + c;
+      const double v1 = rp[0];
+      const double v2 = c < 4 ? rp[8] : 0.0;
       GramDmma::mma(acc[3], v1, v1), GramDmma::mma(acc[4], v1, v2), GramDmma::mma(acc[5], v2, v2);
     }
   }
 };
 
 template <class Shape>
-__global__ void __launch_bounds__(kMeas, 3)
+__global__ void __launch_bounds__(kMeas, 4)
 calib_normal_eq6_static_kernel(const __grid_constant__ CalibP P, const __grid_constant__ CalibN N,
                                const __grid_constant__ ColMap CM, const double* __restrict__ q,
                                const double* __restrict__ pts, int64_t m,
                                double* __restrict__ partial, unsigned int* __restrict__ counter,
                                double* __restrict__ out) {
-  extern __shared__ __align__(16) double slab[];  // [(kMeas/2)*6 rows][kRS6]
+  extern __shared__ __align__(16) double slab[];  // linear rows [(kMeas/2)*3][kRS6], angular rows [..][kRSB]
   __shared__ int s_last;
   __shared__ double s_rr[kMeas / kWarp];
   constexpr int kHalf = kMeas / 2;
   constexpr int NP = Shape::NP;
+  static_assert(kSlabStatic >= (kMeas / kWarp) * kPart6, "the slab is reused for the warp partials");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool role_a = tid >= kHalf;  // warp-uniform
   const int ms = tid & (kHalf - 1);
@@ -813,9 +840,10 @@ calib_normal_eq6_static_kernel(const __grid_constant__ CalibP P, const __grid_co
     for (int k = 0; k < 3 * RK_CALIB_MAX_TOOLS; ++k) pv[k] = pn[k];
     __syncthreads();  // previous phase 2 is done with the slab
     if (role_a)
-      fill_rows6_static<Shape, true>(P, N, qv, pv, base + ms < m, slab + ms * kRS6);
+      fill_rows6_static<Shape, true>(P, N, qv, pv, base + ms < m, slab + ms * kRS6, slab + kSlabA + ms * kRSB);
     else
-      rr += fill_rows6_static<Shape, false>(P, N, qv, pv, base + ms < m, slab + ms * kRS6);
+      rr += fill_rows6_static<Shape, false>(P, N, qv, pv, base + ms < m, slab + ms * kRS6,
+                                            slab + kSlabA + ms * kRSB);
     prefetch(base + stride + ms);
     __syncthreads();
     G.accumulate(slab, warp, lane);
@@ -1097,10 +1125,11 @@ int rk_calib_normal_eq_f64(const RkCalibModel* model, const double* q, const dou
   if (cudaMemsetAsync(counter, 0, sizeof(unsigned int), st) != cudaSuccess) return check_launch();
   if (shape_matches<FanucReducedShape>(P) && !g_calib_force_generic) {
     auto kern = calib_normal_eq6_static_kernel<FanucReducedShape>;
-    if (!allow_dynamic_smem(kern, smem)) return RK_ERR_CUDA;
-    int grid = persistent_grid(kern, kMeas, smem, m > 0 ? 2 * m : 1);
+    const size_t smem_s = (size_t)kSlabStatic * sizeof(double);
+    if (!allow_dynamic_smem(kern, smem_s)) return RK_ERR_CUDA;
+    int grid = persistent_grid(kern, kMeas, smem_s, m > 0 ? 2 * m : 1);
     if (grid > kMaxGrid) grid = kMaxGrid;
-    kern<<<grid, kMeas, smem, st>>>(P, N, make_colmap<FanucReducedShape>(), q, pts, m, (double*)workspace,
+    kern<<<grid, kMeas, smem_s, st>>>(P, N, make_colmap<FanucReducedShape>(), q, pts, m, (double*)workspace,
                                     counter, out);
     return check_launch();
   }

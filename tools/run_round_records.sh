@@ -16,18 +16,30 @@ python tools/bench_rows.py > gpurun_out/${R}_rows.json 2> gpurun_out/${R}_rows.e
 # launch list of the default command (kernel share of the step)
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'fanuc|calib|traj' --csv --log-file gpurun_out/${R}_launches.csv python bench.py --steps 2 --warmup 3 --batch 8388608 --no-cpu > gpurun_out/${R}_ncu_launches.log 2>&1
 # one full capture per kernel
-cap() { # name, kernel regex, skip, bench flags
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -o gpurun_out/${R}_$1 -f python bench.py $4 --steps 2 --warmup 3 --batch 8388608 --no-cpu --no-extras > gpurun_out/${R}_ncu_$1.log 2>&1
+# (gpurun copies back at most 64 MiB: every report is summarised on the box and only the two
+# headline reports are kept)
+cap() { # name, kernel regex, skip, bench flags, units per launch, keep
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -o gpurun_out/${R}_$1 -f python bench.py $4 --steps 2 --warmup 3 --no-cpu --no-extras > gpurun_out/${R}_ncu_$1.log 2>&1
   tail -n 1 gpurun_out/${R}_ncu_$1.log
+  python tools/ncu_summary.py gpurun_out/${R}_$1.ncu-rep $5 > gpurun_out/${R}_$1_ncu_full_summary.json
+  [ "$6" = keep ] || rm -f gpurun_out/${R}_$1.ncu-rep
 }
-cap fused fanuc_fk_jac_ik8 3 ""
-cap fk_jac fanuc_fk_jac_tma 3 "--workload fk_jac"
-cap ik fanuc_ik8_pose 3 "--workload ik"
-cap ik_aos fanuc_ik8_pose_aos 3 "--workload ik --layout aos"
-cap f32fused fanuc_fk_jac_ik8 3 "--dtype f32"
-cap ik_f32 fanuc_ik8_pose 3 "--workload ik --dtype f32"
-cap calib calib_normal 3 "--workload calib"
-cap traj traj_kernel 3 "--workload traj --batch 32768"
+cap fused fanuc_fk_jac_ik8 3 "--batch 8388608" 8388608 keep
+cap fk_jac fanuc_fk_jac_tma 3 "--workload fk_jac --batch 8388608" 8388608
+cap ik fanuc_ik8_pose 3 "--workload ik --batch 8388608" 8388608
+cap ik_aos fanuc_ik8_pose_aos 3 "--workload ik --layout aos --batch 8388608" 8388608
+cap f32fused fanuc_fk_jac_ik8 3 "--dtype f32 --batch 8388608" 8388608
+cap ik_f32 fanuc_ik8_pose 3 "--workload ik --dtype f32 --batch 8388608" 8388608
+cap calib calib_normal 3 "--workload calib --batch 8388608" 8388608 keep
+cap traj traj_kernel 3 "--workload traj --batch 32768" 32768000
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'arm_|rk_chain_jit|chain_kernel|traj_kernel|trap_|poly5|calib_' -o gpurun_out/${R}_rows -f python tools/bench_rows.py --warmup 0 --reps 1 --scale 0.25 > gpurun_out/${R}_ncu_rows.log 2>&1
 tail -n 1 gpurun_out/${R}_ncu_rows.log
-ls -la gpurun_out | grep ${R}_ | wc -l
+python tools/ncu_summary.py gpurun_out/${R}_rows.ncu-rep gpurun_out/${R}_rows.json:0.25 > gpurun_out/${R}_rows_ncu_full_summary.json
+rm -f gpurun_out/${R}_rows.ncu-rep
+# what ncu reports for the FP64 pipe at its true peak (the dependent-free DFMA probe): the scale of
+# the fp64 percentages above
+timeout 120 ncu --set full --clock-control none -k regex:dfma_probe -c 1 -o gpurun_out/${R}_dfma -f python -c "
+import sys; sys.path.insert(0, '.')
+import bench_workloads as W; print(W.fp64_probe())" > gpurun_out/${R}_ncu_dfma.log 2>&1
+python tools/ncu_summary.py gpurun_out/${R}_dfma.ncu-rep > gpurun_out/${R}_dfma_ncu_full_summary.json; rm -f gpurun_out/${R}_dfma.ncu-rep
+du -sh gpurun_out
