@@ -173,24 +173,27 @@ class TrajectoryGenerator():
           * robot=<RRRRobot | Fanuc165F | JacobianCalculator>: the Jacobian is formed and the system
             solved on the GPU (get_dq_from_dx_batch) -- the accelerated path;
           * J_inv given (a sympy Matrix) and no robot: the caller's own expression is evaluated for
-            all samples at once (sympy.lambdify over NumPy arrays on the host: the expression is the
-            caller's, there is no kernel for an arbitrary formula);
+            all samples at once on the GPU (sympy.lambdify with torch as the numeric module over CUDA
+            tensors: the formula is the caller's, there is no hand-written kernel for an arbitrary
+            expression);
           * neither: the default RRRRobot() of rrr_robot_jacobians.py, on the GPU."""
         qs = np.asarray(qs, dtype=np.float64)
         dxs = np.asarray(dxs, dtype=np.float64)
         if robot is None and J_inv is not None:
             import sympy as sp
-            nq = qs.shape[0]
+            Jm = sp.Matrix(J_inv)
+            nq, L = qs.shape
             syms = [sp.symbols(f"q_{i}") for i in range(nq)]
-            f = sp.lambdify(syms, sp.Matrix(J_inv), "numpy")
-            L = qs.shape[1]
-            rows, cols = sp.Matrix(J_inv).shape
-            Ji = np.empty((L, rows, cols))
-            ev = f(*[qs[i] for i in range(nq)])
+            qd = torch.tensor(qs, device="cuda")                       # [J, L] on the GPU
+            dxd = torch.tensor(dxs, device="cuda")
+            rows, cols = Jm.shape
+            Ji = torch.empty((L, rows, cols), dtype=torch.float64, device="cuda")
             for r in range(rows):
                 for c in range(cols):
-                    Ji[:, r, c] = np.broadcast_to(np.asarray(ev[r][c], dtype=np.float64), (L,))
-            return np.einsum("lrc,lc->rl", Ji, dxs)
+                    f = sp.lambdify(syms, Jm[r, c], modules="torch")   # the caller's own formula, on the GPU
+                    Ji[:, r, c] = torch.as_tensor(f(*[qd[i] for i in range(nq)]), dtype=torch.float64,
+                                                  device="cuda")
+            return torch.einsum("lrc,lc->rl", Ji, dxd).cpu().numpy()
         if robot is None:
             from ..robots.rrr_robot import RRRRobot
             robot = RRRRobot()

@@ -256,3 +256,26 @@ def test_dq_from_dx_in_kernel(golden):
         gotg, okg = jc.dq_from_dx_batch(dev(vals), dev(dxg), rows=rows)
         errg = np.abs(gotg.cpu().numpy()[goodg] - refg) / (np.abs(refg).max(axis=1, keepdims=True) * condg[goodg, None])
         assert goodg.mean() > 0.5 and np.max(errg) < 1e-13, (seq, goodg.mean(), np.max(errg))
+
+
+def test_get_dq_from_dx_symbolic_inverse_matches_kernel():
+    """The reference's own calling convention -- a symbolic J_inv in q_0..q_2, built as
+    rrr_robot_jacobians.py:14-46 does -- evaluated on the GPU, against the in-kernel solve."""
+    import sympy as sp
+    from roboticmanipulators_b200.robots import RRRRobot
+    from roboticmanipulators_b200.utils.jacobians import JacobianCalculator
+    from roboticmanipulators_b200.utils.trajectory_generator import TrajectoryGenerator
+    jc = JacobianCalculator("RzTzRyTxRyTx", [1, 0, 1, 0, 1, 0], variables=['q_0', 'l_0', 'q_1', 'l_1', 'q_2', 'l_2'],
+                            T_base=sp.eye(4), T_tool=sp.eye(4), simplify=False)
+    J_inv = jc.calculate_numeric()[:3, :3].inv().subs([("l_0", 1.0), ("l_1", 1.0), ("l_2", 1.0)])
+    rng = np.random.default_rng(23)
+    qs = rng.uniform(0.3, 1.2, size=(3, 400))                       # [J, L], away from the singular poses
+    dxs = rng.normal(size=(400, 3))
+    tg = TrajectoryGenerator(1, 20, 1, 10)
+    a = tg.get_dq_from_dx(qs, dxs, J_inv)
+    b = tg.get_dq_from_dx(qs, dxs, robot=RRRRobot())
+    c = tg.get_dq_from_dx(qs, dxs)                                   # default: the RRR arm of the reference
+    ref = O.rrr_dq_from_dx(qs.T, dxs).T
+    assert a.shape == (3, 400) and np.max(np.abs(a - ref) / np.maximum(1, np.abs(ref))) < 1e-9
+    assert np.max(np.abs(b - ref) / np.maximum(1, np.abs(ref))) < 1e-10
+    assert np.array_equal(b, c)
