@@ -184,6 +184,8 @@ class TrajectoryGenerator():
             Jm = sp.Matrix(J_inv)
             nq, L = qs.shape
             syms = [sp.symbols(f"q_{i}") for i in range(nq)]
+            t = sp.symbols("t")        # a J_inv built with f_of_t=True carries q_i(t): same variables
+            Jm = Jm.subs({sp.Function(f"q_{i}")(t): syms[i] for i in range(nq)})
             qd = torch.tensor(qs, device="cuda")                       # [J, L] on the GPU
             dxd = torch.tensor(dxs, device="cuda")
             rows, cols = Jm.shape
