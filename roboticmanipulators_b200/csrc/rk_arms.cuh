@@ -197,6 +197,37 @@ __device__ __forceinline__ bool rrr_ik_branch(const ArmPT<S>& P, const S (&p0)[3
   return rrr_ik_finish(P, r, M::atan2_fast(y, x), m, qo);
 }
 
+// Branch (m, k) = (1, 1) together with the sines / cosines of the solution it returns, formed from
+// the operands of its own atan2 / acos calls (unit vectors + angle addition, as everywhere in the
+// IK): trig = {c0, s0, c1, s1, c12, s12} with c12 = cos(q1 + q2).  A caller that needs the Jacobian
+// AT the returned solution (get_dq_from_dx) then spends no sincos on it.  A failed branch returns
+// the zero vector, hence the trig of zero.
+template <typename S>
+__device__ __forceinline__ bool rrr_ik11_trig(const ArmPT<S>& P, const S (&p0)[3], S (&qo)[3], S (&trig)[6]) {
+  using M = Sc<S>;
+  const S x = p0[0], y = p0[1];
+  const S rxy = M::sqrt(M::add(M::mul(x, x), M::mul(y, y)));                     // :162
+  const RrrK<S> r = rrr_ik_k(P, p0, rxy, 1);
+  const bool ok = rrr_ik_finish(P, r, M::atan2_fast(y, x), 1, qo);
+  const S l1 = P.l[1], l2 = P.l[2];
+  const S c2 = r.reach ? r.cc : S(0.5), s2 = r.sabs;                             // q2 = +acos(cc)
+  const S rg2 = r.xp * r.xp + r.zp * r.zp;
+  const bool rg_ok = rg2 > S(1e-30);
+  const S inv = M::rsqrt_fast(rg_ok ? rg2 : S(1));
+  const S cg = rg_ok ? r.xp * inv : S(1), sg = rg_ok ? r.zp * inv : S(0);
+  // |(l2 s2, l1 + l2 c2)|^2 = l1^2 + l2^2 + 2 l1 l2 c2 = x'^2 + z'^2 (cosine rule): the same 1 / |.|
+  const S cb = rg_ok ? (l1 + l2 * c2) * inv : S(1), sb = rg_ok ? (l2 * s2) * inv : S(0);
+  const S c1 = cg * cb + sg * sb, s1 = sg * cb - cg * sb;                        // q1 = gamma - beta
+  const bool axis = M::abs(r.xp) < P.eps;                                        // :181-187 -> q0 = 0
+  const bool rxy_ok = rxy > S(1e-30);
+  const S irxy = M::rcp_fast(rxy_ok ? rxy : S(1));
+  const S c0 = (axis || !rxy_ok) ? S(1) : x * irxy, s0 = (axis || !rxy_ok) ? S(0) : y * irxy;
+  trig[0] = ok ? c0 : S(1), trig[1] = ok ? s0 : S(0);
+  trig[2] = ok ? c1 : S(1), trig[3] = ok ? s1 : S(0);
+  trig[4] = ok ? c1 * c2 - s1 * s2 : S(1), trig[5] = ok ? s1 * c2 + c1 * s2 : S(0);
+  return ok;
+}
+
 // The canonical 4 branches (m outer, k inner) of one target in one thread: atan2(y, x) once,
 // acos / beta / gamma once per k (beta is odd in m) -- 7 atan2 instead of 16.
 template <typename S>

@@ -203,12 +203,18 @@ traj_kernel(const __grid_constant__ ArmPT<SO> P, const double* __restrict__ q0, 
           const double Tin[12] = {1.0, 0.0, 0.0, qv[0], 0.0, 1.0, 0.0, qv[1], 0.0, 0.0, 1.0, qv[2]};
           double p0[3];
           arm_ik_p0(P, Tin, p0);
-          ok = rrr_ik_branch(P, p0, 1, 1, jq);
-          // get_dq_from_dx: dq = J_v(q)^-1 dx (trajectory_generator.py:161-188)
-          double Tv[16], Jv[18];
-          rrr_fk_jac_pose(bare, jq, Tv, Jv);
-          const double a = Jv[0], b = Jv[1], c = Jv[2], d = Jv[3], f = Jv[4], g = Jv[5],
-                       h = Jv[6], k = Jv[7], l = Jv[8];
+          double tg[6];
+          ok = rrr_ik11_trig(P, p0, jq, tg);
+          // get_dq_from_dx: dq = J_v(q)^-1 dx (trajectory_generator.py:161-188) with the position
+          // Jacobian of the bare arm (identity base / tool, rrr_robot_jacobians.py:19-20) AT the IK's
+          // answer -- written out from the sines / cosines the IK already holds:
+          //   column 0 = z x O_n, column 1 = y1 x (O_n - O_1), column 2 = y1 x (O_n - O_2)
+          const double c0 = tg[0], sn0 = tg[1], c1 = tg[2], s1 = tg[3], c12 = tg[4], s12 = tg[5];
+          const double l1 = bare.l[1], l2 = bare.l[2];
+          const double rho3 = l1 * c1 + l2 * c12, vz = -l1 * s1 - l2 * s12;
+          const double a = -rho3 * sn0, b = c0 * vz, c = -l2 * s12 * c0;
+          const double d = rho3 * c0, f = sn0 * vz, g = -l2 * s12 * sn0;
+          const double h = 0.0, k = -rho3, l = -l2 * c12;
           const double A0 = f * l - g * k, A1 = c * k - b * l, A2 = b * g - c * f;
           const double B0 = g * h - d * l, B1 = a * l - c * h, B2 = c * d - a * g;
           const double C0 = d * k - f * h, C1 = b * h - a * k, C2 = a * f - b * d;
@@ -227,16 +233,37 @@ traj_kernel(const __grid_constant__ ArmPT<SO> P, const double* __restrict__ q0, 
 }
 
 
-// generate_coefficients for a batch of scalar moves: one thread per move.
+// generate_coefficients for a batch of scalar moves: one thread per PAIR of moves with 16-byte
+// accesses when the arrays allow it (2 loads + 2 stores of 8 bytes per move left this kernel
+// latency-bound at 0.79 of HBM: ncu long_scoreboard 10.7 per issue), one move per thread otherwise.
+template <bool VEC2>
 __global__ void __launch_bounds__(kBlock)
 trap_coefficients_kernel(const double* __restrict__ q0, const double* __restrict__ qf, int64_t n,
                          double vmax, double amax, double freq, double* __restrict__ t1,
                          double* __restrict__ tau) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    double a, b;
-    trap_coefficients(q0[i], qf[i], vmax, amax, freq, a, b);
-    t1[i] = a, tau[i] = b;
+  if (VEC2) {
+    const int64_t pairs = n >> 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
+      const double2 a = __ldcs(reinterpret_cast<const double2*>(q0) + i);
+      const double2 b = __ldcs(reinterpret_cast<const double2*>(qf) + i);
+      double2 o1, o2;
+      trap_coefficients(a.x, b.x, vmax, amax, freq, o1.x, o2.x);
+      trap_coefficients(a.y, b.y, vmax, amax, freq, o1.y, o2.y);
+      __stcs(reinterpret_cast<double2*>(t1) + i, o1);
+      __stcs(reinterpret_cast<double2*>(tau) + i, o2);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+      double a, b;
+      trap_coefficients(q0[n - 1], qf[n - 1], vmax, amax, freq, a, b);
+      t1[n - 1] = a, tau[n - 1] = b;
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      double a, b;
+      trap_coefficients(q0[i], qf[i], vmax, amax, freq, a, b);
+      t1[i] = a, tau[i] = b;
+    }
   }
 }
 
@@ -366,9 +393,16 @@ int rk_trap_coefficients_f64(const double* q0, const double* qf, int64_t n, doub
   if (n < 0) return RK_ERR_INVALID_ARG;
   if (n == 0) return RK_OK;
   if (!q0 || !qf || !t1 || !tau) return RK_ERR_INVALID_ARG;
-  int grid = rk::stream_grid(rk::trap_coefficients_kernel, rk::kBlock, 0, n);
-  rk::trap_coefficients_kernel<<<grid, rk::kBlock, 0, (cudaStream_t)stream>>>(
-      q0, qf, n, v_max, a_max, control_freq, t1, tau);
+  const bool vec = n >= 2 && (((uintptr_t)q0 | (uintptr_t)qf | (uintptr_t)t1 | (uintptr_t)tau) & 15) == 0;
+  if (vec) {
+    int grid = rk::stream_grid(rk::trap_coefficients_kernel<true>, rk::kBlock, 0, n / 2);
+    rk::trap_coefficients_kernel<true><<<grid, rk::kBlock, 0, (cudaStream_t)stream>>>(
+        q0, qf, n, v_max, a_max, control_freq, t1, tau);
+  } else {
+    int grid = rk::stream_grid(rk::trap_coefficients_kernel<false>, rk::kBlock, 0, n);
+    rk::trap_coefficients_kernel<false><<<grid, rk::kBlock, 0, (cudaStream_t)stream>>>(
+        q0, qf, n, v_max, a_max, control_freq, t1, tau);
+  }
   return rk::check_launch();
 }
 
