@@ -10,6 +10,7 @@
 // Every reduction ends the same way: CTA partials go to the workspace and the last CTA to finish
 // (atomic ticket) adds them in index order, so results are deterministic.
 #include <cstdlib>
+#include <type_traits>
 
 #include "rk_common.cuh"
 
@@ -910,8 +911,46 @@ calib_normal_eq6_static_kernel(const __grid_constant__ CalibP P, const __grid_co
 // of feeding 9 rows of width 16 to a Gram accumulation (1224 FMAs); the last CTA assembles the
 // caller's dim x dim + dim layout.
 // -------------------------------------------------------------------------------------------
+// Forward chain get_pose(q) with the model's structure static (see FanucReducedShape): joint J's
+// rotation is one straight-line variant and the tables are constant-bank operands.  SHAPE = void
+// selects the generic walk (chain_end) for any other model.
+template <class Shape, int J>
+__device__ __forceinline__ void static_forward(const CalibP& P, const double (&raw)[RK_CALIB_MAX_JOINTS], Fr& F) {
+  if constexpr (J < Shape::NJ) {
+    const double v = __dadd_rn(__dmul_rn(raw[J], P.jdir[J]), P.joff[J]);  // model_calibration.py:557
+    double sn, cs;
+    fast_sincos(v, &sn, &cs);
+    fr_rot<Shape::jaxis(J)>(F, sn, cs);
+    if (P.seg_trans[J]) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        F.p[i] += F.R[i * 3] * P.seg[J][3] + F.R[i * 3 + 1] * P.seg[J][7] + F.R[i * 3 + 2] * P.seg[J][11];
+    } else {
+      fr_mul(F, P.seg[J]);
+    }
+    static_forward<Shape, J + 1>(P, raw, F);
+  }
+}
+
+// flange pose of measurement i: the generic walk, or the static one when SHAPE is a model shape
+template <class SHAPE>
+__device__ __forceinline__ void measurement_pose(const CalibP& P, const double* __restrict__ q, int64_t i, Fr& F) {
+  if constexpr (std::is_void<SHAPE>::value) {
+    double sj[RK_CALIB_MAX_JOINTS], cj[RK_CALIB_MAX_JOINTS];
+    load_joints(P, q, i, true, sj, cj);
+    chain_end(P, sj, cj, F);
+  } else {
+    double raw[RK_CALIB_MAX_JOINTS];
+#pragma unroll
+    for (int j = 0; j < RK_CALIB_MAX_JOINTS; ++j) raw[j] = j < SHAPE::NJ ? __ldcs(q + i * SHAPE::NJ + j) : 0.0;
+    fr_init(F, P.Tb);
+    static_forward<SHAPE, 0>(P, raw, F);
+  }
+}
+
 constexpr int kTbAcc = 33 + 3 * RK_CALIB_MAX_TOOLS;
 
+template <class SHAPE>
 __global__ void __launch_bounds__(kMeas, 3)
 calib_tool_base_stats_kernel(const __grid_constant__ CalibP P, const double* __restrict__ q,
                              const double* __restrict__ pts, int64_t m, double* __restrict__ partial,
@@ -924,13 +963,11 @@ calib_tool_base_stats_kernel(const __grid_constant__ CalibP P, const double* __r
 #pragma unroll
   for (int k = 0; k < kTbAcc; ++k) acc[k] = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * kMeas + tid; i < m; i += (int64_t)gridDim.x * kMeas) {
-    double sj[RK_CALIB_MAX_JOINTS], cj[RK_CALIB_MAX_JOINTS];
     double pv[3 * RK_CALIB_MAX_TOOLS];
 #pragma unroll
     for (int k = 0; k < 3 * RK_CALIB_MAX_TOOLS; ++k) pv[k] = k < 3 * P.nt ? __ldcs(pts + i * 3 * P.nt + k) : 0.0;
-    load_joints(P, q, i, true, sj, cj);
     Fr F;
-    chain_end(P, sj, cj, F);
+    measurement_pose<SHAPE>(P, q, i, F);
     const double px = F.p[0], py = F.p[1], pz = F.p[2];
     acc[0] += px, acc[1] += py, acc[2] += pz;
     acc[3] += px * px, acc[4] += px * py, acc[5] += px * pz;
@@ -1025,6 +1062,7 @@ calib_tool_base_stats_kernel(const __grid_constant__ CalibP P, const double* __r
 }
 
 // evaluate (model_calibration.py:480-505): sums of squares and maxima of the residuals
+template <class SHAPE>
 __global__ void __launch_bounds__(kMeas)
 calib_eval_kernel(const __grid_constant__ CalibP P, const double* __restrict__ q,
                   const double* __restrict__ pts, int64_t m, double* __restrict__ partial,
@@ -1034,13 +1072,11 @@ calib_eval_kernel(const __grid_constant__ CalibP P, const double* __restrict__ q
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double acc[8] = {0.0, 0.0, 0.0, 0.0, -1.0, -1.0, -1.0, -1.0};  // maxima start at -1 (:481)
   for (int64_t i = (int64_t)blockIdx.x * kMeas + tid; i < m; i += (int64_t)gridDim.x * kMeas) {
-    double sj[RK_CALIB_MAX_JOINTS], cj[RK_CALIB_MAX_JOINTS];
     double pv[3 * RK_CALIB_MAX_TOOLS];
 #pragma unroll
     for (int k = 0; k < 3 * RK_CALIB_MAX_TOOLS; ++k) pv[k] = k < 3 * P.nt ? __ldcs(pts + i * 3 * P.nt + k) : 0.0;
-    load_joints(P, q, i, true, sj, cj);
     Fr F;
-    chain_end(P, sj, cj, F);
+    measurement_pose<SHAPE>(P, q, i, F);
 #pragma unroll
     for (int t = 0; t < RK_CALIB_MAX_TOOLS; ++t) {
       if (t >= P.nt) break;
@@ -1150,11 +1186,14 @@ int rk_calib_tool_base_eq_f64(const RkCalibModel* model, const double* q, const 
   int rc = make_calib(model, P, true);
   if (rc != RK_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  int grid = persistent_grid(calib_tool_base_stats_kernel, kMeas, 0, m > 0 ? m : 1);
-  if (grid > kMaxGrid) grid = kMaxGrid;
   unsigned int* counter = reinterpret_cast<unsigned int*>((char*)workspace + kWsCounterOffset);
   if (cudaMemsetAsync(counter, 0, sizeof(unsigned int), st) != cudaSuccess) return check_launch();
-  calib_tool_base_stats_kernel<<<grid, kMeas, 0, st>>>(P, q, pts, m, (double*)workspace, counter, out);
+  auto kern = (shape_matches<FanucReducedShape>(P) && !g_calib_force_generic)
+                  ? calib_tool_base_stats_kernel<FanucReducedShape>
+                  : calib_tool_base_stats_kernel<void>;
+  int grid = persistent_grid(kern, kMeas, 0, m > 0 ? m : 1);
+  if (grid > kMaxGrid) grid = kMaxGrid;
+  kern<<<grid, kMeas, 0, st>>>(P, q, pts, m, (double*)workspace, counter, out);
   return check_launch();
 }
 
@@ -1167,11 +1206,14 @@ int rk_calib_eval_f64(const RkCalibModel* model, const double* q, const double* 
   int rc = rk::make_calib(model, P, false);
   if (rc != RK_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  int grid = rk::persistent_grid(rk::calib_eval_kernel, rk::kMeas, 0, m > 0 ? m : 1);
-  if (grid > rk::kMaxGrid) grid = rk::kMaxGrid;
   unsigned int* counter = reinterpret_cast<unsigned int*>((char*)workspace + rk::kWsCounterOffset);
   if (cudaMemsetAsync(counter, 0, sizeof(unsigned int), st) != cudaSuccess) return rk::check_launch();
-  rk::calib_eval_kernel<<<grid, rk::kMeas, 0, st>>>(P, q, pts, m, (double*)workspace, counter, out);
+  auto kern = (rk::shape_matches<rk::FanucReducedShape>(P) && !rk::g_calib_force_generic)
+                  ? rk::calib_eval_kernel<rk::FanucReducedShape>
+                  : rk::calib_eval_kernel<void>;
+  int grid = rk::persistent_grid(kern, rk::kMeas, 0, m > 0 ? m : 1);
+  if (grid > rk::kMaxGrid) grid = rk::kMaxGrid;
+  kern<<<grid, rk::kMeas, 0, st>>>(P, q, pts, m, (double*)workspace, counter, out);
   return rk::check_launch();
 }
 
