@@ -53,38 +53,19 @@ def alloc_out(n, shape, layout, dtype, device):
     return store, store
 
 
-def alloc_outs(n, shapes, layout, dtype, device):
-    """Several outputs of one call from ONE allocation (call-latency path: an allocation costs ~3 us
-    of host time, a view ~1 us).  shapes: tuple of per-item shapes, None entries are skipped.
-    Returns a list of (logical_view, storage) pairs (None for skipped entries); every storage starts
-    on a 256-byte boundary."""
-    al = 64 if dtype is torch.float32 else 32       # elements per 256 bytes
-    offs, total = [], 0
-    for shp in shapes:
-        if shp is None:
-            offs.append(None)
-            continue
-        ncomp = 1
-        for s_ in shp:
-            ncomp *= s_
-        offs.append((total, ncomp))
-        total += (n * ncomp + al - 1) // al * al
-    slab = torch.empty(total, dtype=dtype, device=device)
-    out = []
-    for shp, off in zip(shapes, offs):
-        if off is None:
-            out.append((None, None))
-            continue
-        o, ncomp = off
-        flat = slab[o:o + n * ncomp]
-        if layout == "soa":
-            store = flat.view(ncomp, n)
-            view = store.view(*shp, n).permute(len(shp), *range(len(shp))) if shp else flat
-        else:
-            store = flat.view(n, *shp)
-            view = store
-        out.append((view, store))
-    return out
+def alloc_view(n, shape, layout, dtype, device):
+    """One output with logical shape [n, *shape] in ONE torch call (call-latency path: measured on the
+    GPU box, an allocation costs ~2.3 us of host time and every Python-level slice / view / permute
+    another 1-2 us -- carving several outputs out of one slab was SLOWER than allocating each).
+    SOA storage is component-major planes [prod(shape), n], returned directly as the strided view
+    with the reference's logical shape; its data_ptr() is the start of the storage."""
+    if layout != "soa" or not shape:
+        return torch.empty((n, *shape), dtype=dtype, device=device)
+    strides, acc = [], n
+    for s_ in reversed(shape):
+        strides.append(acc)
+        acc *= s_
+    return torch.empty_strided((n, *shape), (1, *reversed(strides)), dtype=dtype, device=device)
 
 
 def flags_of(layout):

@@ -840,6 +840,79 @@ fanuc_fk_jac_ik8_kernel(const __grid_constant__ FanucP<S> P, const __grid_consta
   }
 }
 
+// Pose-major arrays, SMALL batches: K1 then K2 in ONE launch, one thread per pose, every value stored
+// where it belongs the moment it exists.  A pose's stores are scattered (no staging through shared
+// memory), which wastes sectors the two staged AOS kernels do not -- so only batches small enough to
+// be launch-bound (n <= kSmallAos poses, ~3 us of kernel) come here: it halves the launch cost of
+// the reference-shaped call (Fanuc165F.fk_jac_ik_batch on [N, 6] -> [N, 4, 4] ...; bench.py
+// `latency_us`).  Same per-pose code, hence the same bits as the two calls.
+constexpr int64_t kSmallAos = 16384;
+
+template <typename S>
+struct AosFkSink {
+  S* Tp;
+  S* Jp;
+  S* dp;
+  S (&Tin)[12];
+  __device__ __forceinline__ void T(int k, S v) {
+    Tp[k] = v;
+    if (k < 12) Tin[k] = v;
+  }
+  __device__ __forceinline__ void J(int k, S v) {
+    if (Jp) Jp[k] = v;
+  }
+  __device__ __forceinline__ void det(S v) {
+    if (dp) *dp = v;
+  }
+};
+template <typename S>
+struct AosIkDirectSink {
+  S* qp;
+  uint8_t* vp;
+  __device__ __forceinline__ void q(int b, int j, S v) { qp[b * 6 + j] = v; }
+  __device__ __forceinline__ void branch(int b, bool okf, const S (&u)[6]) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) qp[b * 6 + j] = okf ? u[j] : S(0);
+    vp[b] = okf ? 1 : 0;
+  }
+  __device__ __forceinline__ void ok(int b, bool f) { vp[b] = f ? 1 : 0; }
+  __device__ __forceinline__ void pair_done(int) {}
+};
+
+template <typename S, bool STD>
+__global__ void __launch_bounds__(kBlock)
+fanuc_fk_jac_ik8_small_aos_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict__ q, int64_t n,
+                                  S* __restrict__ T, S* __restrict__ J, S* __restrict__ det,
+                                  S* __restrict__ q_out, uint8_t* __restrict__ valid) {
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 - (threadIdx.x & 31) >= n) return;  // whole warps only leave (fanuc_ik8_pose votes)
+  const int64_t i = i0 < n ? i0 : n - 1;     // spare lanes redo the last pose and store the same values
+  S qv[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) qv[k] = q[i * 6 + k];
+  S Tin[12];
+  AosFkSink<S> fk{T + i * 16, J ? J + i * 36 : nullptr, det ? det + i : nullptr, Tin};
+  fanuc_fk_jac_emit(P, qv, fk);
+  S R0[9], p0[3];
+  fanuc_ik_t0(P, Tin, R0, p0);
+  AosIkDirectSink<S> sink{q_out + i * 48, valid + i * 8};
+  if (fanuc_ik8_pose<S, STD>(P, R0, p0, sink)) {
+#pragma unroll 1
+    for (int mk = 0; mk < 4; ++mk) {
+      const int wl[2] = {0, 1};
+      S qo[2][6];
+      bool ok[2];
+      fanuc_ik_mk<S, 2>(P, R0, p0, (mk & 2) ? -1 : 1, (mk & 1) ? -1 : 1, wl, qo, ok);
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) sink.q(mk * 2 + w, j, qo[w][j]);
+        sink.ok(mk * 2 + w, ok[w]);
+      }
+    }
+  }
+}
+
 // AOS twin of fanuc_ik8_pose_kernel (the reference's shapes: T [n][4][4] -> q [n][8][6],
 // valid [n][8]).  A warp's 32 poses are one contiguous 4 KB run of T: it arrives by one 2-D TMA
 // load of the [32 poses][16] box with the hardware swizzle (128 B rows for FP64, 64 B for FP32), so
@@ -1335,6 +1408,12 @@ static int launch_fk_jac_ik8(const RkFanuc* robot, const S* q, int64_t n, int64_
                                                             tg.chunk);
       return check_launch();
     }
+  }
+  if (!soa && n <= kSmallAos) {  // launch-bound: one kernel instead of two
+    FanucP<S> P = make_params<S>(robot, flags);
+    auto kern = P.std_limits ? fanuc_fk_jac_ik8_small_aos_kernel<S, true> : fanuc_fk_jac_ik8_small_aos_kernel<S, false>;
+    kern<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(P, q, n, T, J, det, q_out, valid);
+    return check_launch();
   }
   int rc = launch_fk_jac<S>(robot, q, n, ld, flags, T, J, det, stream);
   if (rc != RK_OK) return rc;

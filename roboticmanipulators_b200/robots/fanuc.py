@@ -116,15 +116,15 @@ class Fanuc165F(Robot):
         qs, ld = _batch.prep_input(q, 6, layout, q.dtype)
         n = qs.shape[0]
         dev = qs.device
-        T, Ts = _batch.alloc_out(n, (4, 4), layout, q.dtype, dev)
-        J = Js = det = None
+        T = _batch.alloc_view(n, (4, 4), layout, q.dtype, dev)
+        J = det = None
         if jacobian:
-            J, Js = _batch.alloc_out(n, (6, 6), layout, q.dtype, dev)
+            J = _batch.alloc_view(n, (6, 6), layout, q.dtype, dev)
         if measure:
             det = torch.empty(n, dtype=q.dtype, device=dev)
         flags = _batch.flags_of(layout) | (_lib.RK_JAC_USER_ANGLES if user_angles else 0)
         fn = getattr(_lib.load(), "rk_fanuc_fk_jac_" + _DTYPES[q.dtype])
-        launch(fn, dev, self._cached_struct(), _lib.ptr(qs), n, ld, flags, _lib.ptr(Ts), _lib.ptr(Js),
+        launch(fn, dev, self._cached_struct(), qs.data_ptr(), n, ld, flags, T.data_ptr(), _lib.ptr(J),
                _lib.ptr(det))
         out = (T,)
         if jacobian:
@@ -142,12 +142,12 @@ class Fanuc165F(Robot):
             layout = _batch.detect_layout(q, 6)
         qs, ld = _batch.prep_input(q, 6, layout, q.dtype)
         n, dev = qs.shape[0], qs.device
-        J, Js = _batch.alloc_out(n, (6, 6), layout, q.dtype, dev)
+        J = _batch.alloc_view(n, (6, 6), layout, q.dtype, dev)
         det = torch.empty(n, dtype=q.dtype, device=dev)
         flags = _batch.flags_of(layout) | (_lib.RK_JAC_USER_ANGLES if user_angles else 0)
         fn = getattr(_lib.load(), "rk_fanuc_fk_jac_" + _DTYPES[q.dtype])
-        launch(fn, dev, self._cached_struct(), _lib.ptr(qs), n, ld, flags, None, _lib.ptr(Js),
-               _lib.ptr(det))
+        launch(fn, dev, self._cached_struct(), qs.data_ptr(), n, ld, flags, None, J.data_ptr(),
+               det.data_ptr())
         return J, det
 
     def inverse_kinematics_batch(self, T, branches=CANONICAL_8, *, layout="auto"):
@@ -166,19 +166,13 @@ class Fanuc165F(Robot):
         Ts, ld = _batch.prep_input(T2, 16, layout, T.dtype)
         dev = Ts.device
         nb = len(branches)
-        br = (C.c_int8 * (3 * nb))(*[int(v) for b in branches for v in b])
-        if layout == "soa":
-            qstore = torch.empty((nb * 6, n), dtype=T.dtype, device=dev)
-            vstore = torch.empty((nb, n), dtype=torch.uint8, device=dev)
-            qv = qstore.view(nb, 6, n).permute(2, 0, 1)
-            vv = vstore.t()
-        else:
-            qstore = torch.empty((n, nb, 6), dtype=T.dtype, device=dev)
-            vstore = torch.empty((n, nb), dtype=torch.uint8, device=dev)
-            qv, vv = qstore, vstore
+        # NULL selects the canonical 8 in the library (and skips building the ctypes array)
+        br = None if branches is CANONICAL_8 else (C.c_int8 * (3 * nb))(*[int(v) for b in branches for v in b])
+        qv = _batch.alloc_view(n, (nb, 6), layout, T.dtype, dev)
+        vv = _batch.alloc_view(n, (nb,), layout, torch.uint8, dev)
         fn = getattr(_lib.load(), "rk_fanuc_ik_" + _DTYPES[T.dtype])
-        launch(fn, dev, self._cached_struct(), _lib.ptr(Ts), n, ld, _batch.flags_of(layout), br, nb,
-               _lib.ptr(qstore), _lib.ptr(vstore))
+        launch(fn, dev, self._cached_struct(), Ts.data_ptr(), n, ld, _batch.flags_of(layout), br, nb,
+               qv.data_ptr(), vv.data_ptr())
         return qv, vv.view(torch.bool)
 
     def fk_jac_ik_batch(self, q, *, layout="auto", user_angles=False):
@@ -194,18 +188,16 @@ class Fanuc165F(Robot):
             layout = _batch.detect_layout(q, 6)
         qs, ld = _batch.prep_input(q, 6, layout, q.dtype)
         n, dev = qs.shape[0], qs.device
-        (T, Ts), (J, Js), (det, _), (qv, qstore) = _batch.alloc_outs(
-            n, ((4, 4), (6, 6), (), (8, 6)), layout, q.dtype, dev)
-        if layout == "soa":
-            vstore = torch.empty((8, n), dtype=torch.uint8, device=dev)
-            vv = vstore.t()
-        else:
-            vstore = torch.empty((n, 8), dtype=torch.uint8, device=dev)
-            vv = vstore
+        dt = q.dtype
+        T = _batch.alloc_view(n, (4, 4), layout, dt, dev)
+        J = _batch.alloc_view(n, (6, 6), layout, dt, dev)
+        det = torch.empty(n, dtype=dt, device=dev)
+        qv = _batch.alloc_view(n, (8, 6), layout, dt, dev)
+        vv = _batch.alloc_view(n, (8,), layout, torch.uint8, dev)
         flags = _batch.flags_of(layout) | (_lib.RK_JAC_USER_ANGLES if user_angles else 0)
         fn = getattr(_lib.load(), "rk_fanuc_fk_jac_ik8_" + _DTYPES[q.dtype])
-        launch(fn, dev, self._cached_struct(), _lib.ptr(qs), n, ld, flags, _lib.ptr(Ts), _lib.ptr(Js),
-               _lib.ptr(det), _lib.ptr(qstore), _lib.ptr(vstore))
+        launch(fn, dev, self._cached_struct(), qs.data_ptr(), n, ld, flags, T.data_ptr(), J.data_ptr(),
+               det.data_ptr(), qv.data_ptr(), vv.data_ptr())
         return T, J, det, qv, vv.view(torch.bool)
 
     def dq_from_dx_batch(self, q, dx, *, layout="aos", user_angles=True):
@@ -223,11 +215,11 @@ class Fanuc165F(Robot):
         qs, ld = _batch.prep_input(q, 6, layout, q.dtype)
         ds, _ = _batch.prep_input(dx.reshape(dx.shape[0], 6), 6, layout, q.dtype)
         n, dev = qs.shape[0], qs.device
-        dq, dqs = _batch.alloc_out(n, (6,), layout, q.dtype, dev)
+        dq = _batch.alloc_view(n, (6,), layout, q.dtype, dev)
         ok = torch.empty(n, dtype=torch.uint8, device=dev)
         flags = _batch.flags_of(layout) | (_lib.RK_JAC_USER_ANGLES if user_angles else 0)
         fn = getattr(_lib.load(), "rk_fanuc_dq_from_dx_" + _DTYPES[q.dtype])
-        launch(fn, dev, self._cached_struct(), _lib.ptr(qs), _lib.ptr(ds), n, ld, flags, _lib.ptr(dqs),
+        launch(fn, dev, self._cached_struct(), _lib.ptr(qs), _lib.ptr(ds), n, ld, flags, dq.data_ptr(),
                _lib.ptr(ok))
         return dq, ok.view(torch.bool)
 
