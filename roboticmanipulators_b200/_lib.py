@@ -92,6 +92,7 @@ _SIGNATURES = {
     "rk_chain_fk_jac_f64": (_int, [C.POINTER(RkChain), _vp, _int, _i64, _i64, _int, _vp, _vp, _vp]),
     "rk_chain_fk_jac_f32": (_int, [C.POINTER(RkChain), _vp, _int, _i64, _i64, _int, _vp, _vp, _vp]),
     "rk_chain_jit_status": (C.c_char_p, []),
+    "rk_chain_jit_source": (_i64, [C.POINTER(RkChain), _int, _int, _int, _int, C.c_char_p, _i64]),
     "rk_chain_dq_from_dx_f64": (_int, [C.POINTER(RkChain), _vp, _int, C.POINTER(C.c_int32), _vp, _i64, _i64,
                                        _int, _vp, _vp, _vp]),
     "rk_fanuc_dq_from_dx_f64": (_int, [C.POINTER(RkFanuc), _vp, _vp, _i64, _i64, _int, _vp, _vp, _vp]),

@@ -394,9 +394,27 @@ static int launch_chain_solve(const RkChain* chain, const double* values, int nv
   return RK_ERR_UNSUPPORTED;
 }
 
+template <typename S>
+static int64_t jit_source(const RkChain* chain, int nvals, int flags, int want, char* buf, int64_t cap) {
+  ChainProg<S> Pg;
+  if (compile_chain<S>(chain, nvals, Pg) != RK_OK) return -1;
+  const std::string src = chain_jit_source<S>(Pg, flags & RK_SOA, want & 1, want & 2, want & 4);
+  if (buf && cap > 0) {
+    const size_t m = src.size() < (size_t)cap - 1 ? src.size() : (size_t)cap - 1;
+    memcpy(buf, src.data(), m);
+    buf[m] = 0;
+  }
+  return (int64_t)src.size() + 1;
+}
+
 }  // namespace rk
 
 extern "C" {
+int64_t rk_chain_jit_source(const RkChain* chain, int nvals, int flags, int want, int f32, char* buf, int64_t cap) {
+  if (!chain) return -1;
+  return f32 ? rk::jit_source<float>(chain, nvals, flags, want, buf, cap)
+             : rk::jit_source<double>(chain, nvals, flags, want, buf, cap);
+}
 int rk_chain_fk_jac_f64(const RkChain* chain, const double* values, int nvals, int64_t n, int64_t ld, int flags,
                         double* T, double* J, void* stream) {
   return rk::launch_chain<double>(chain, values, nvals, n, ld, flags, T, J, stream);

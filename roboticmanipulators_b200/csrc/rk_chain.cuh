@@ -1,6 +1,7 @@
 // The compiled form of a token chain (see rk_chain.cu), shared by the interpreting kernel and the
 // run-time specialiser (rk_chain_jit.cu).
 #pragma once
+#include <string>
 #include "rk_common.cuh"
 
 namespace rk {
@@ -31,6 +32,9 @@ struct ChainProg {
 template <typename S>
 int chain_jit_launch(const ChainProg<S>& Pg, bool soa, const S* values, int nvals, int64_t n, int64_t ld, S* T,
                      S* J, cudaStream_t st);
+// the CUDA source the specialiser would compile (diagnostics and the CPU-side build test)
+template <typename S>
+std::string chain_jit_source(const ChainProg<S>& Pg, bool soa, bool wantT, bool wantJ, bool vec2);
 const char* chain_jit_status();  // last NVRTC / driver message (diagnostics)
 
 }  // namespace rk

@@ -96,12 +96,19 @@ const char* kPreludeF64 = R"SRC(
 typedef double S;
 #define LD(p) ld_cs(p)
 #define ST(p, v) st_cs(p, v)
+typedef double2 S2;
+#define LD2(p) ld_cs2(p)
+#define ST2(p, a, b) st_cs2(p, a, b)
+__device__ __forceinline__ double2 ld_cs2(const double* p) { double2 v; asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p)); return v; }
+__device__ __forceinline__ void st_cs2(double* p, double a, double b) { asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" :: "l"(p), "d"(a), "d"(b) : "memory"); }
 __device__ __forceinline__ double ld_cs(const double* p) { double v; asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; }
 __device__ __forceinline__ void st_cs(double* p, double v) { asm volatile("st.global.cs.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory"); }
 // sin and cos together (Cody-Waite by pi/2, degree-11/12 polynomials; <= ~1.5 ulp for |x| <= 1e5):
 // the same routine as fast_sincos of rk_common.cuh
-__device__ __noinline__ void slow_sc(double x, double* s, double* c) { sincos(x, s, c); }
-__device__ __forceinline__ void rk_sincos(double x, double* sp, double* cp) {
+// (results by value and by reference: a pointer to a local would put every sin/cos pair through the
+// stack -- STL + LDL on the main path, measured as the long_scoreboard stall of the first version)
+__device__ __noinline__ double2 slow_sc(double x) { double s, c; sincos(x, &s, &c); return make_double2(s, c); }
+__device__ __forceinline__ void rk_sincos(double x, double& so, double& co) {
   const double kf = rint(x * 0x1.45f306dc9c883p-1);
   const int q = (int)kf;
   double r = fma(-kf, 0x1.921fb54442d18p+0, x);
@@ -126,9 +133,9 @@ __device__ __forceinline__ void rk_sincos(double x, double* sp, double* cp) {
   double c = (q & 1) ? sn : cs;
   if (q & 2) s = -s;
   if ((q + 1) & 2) c = -c;
-  if (!(fabs(x) <= 1.0e5)) slow_sc(x, &s, &c);
-  *sp = s;
-  *cp = c;
+  if (!(fabs(x) <= 1.0e5)) { const double2 sc = slow_sc(x); s = sc.x; c = sc.y; }
+  so = s;
+  co = c;
 }
 )SRC";
 
@@ -136,108 +143,162 @@ const char* kPreludeF32 = R"SRC(
 typedef float S;
 #define LD(p) ld_cs(p)
 #define ST(p, v) st_cs(p, v)
+typedef float2 S2;
+#define LD2(p) ld_cs2(p)
+#define ST2(p, a, b) st_cs2(p, a, b)
+__device__ __forceinline__ float2 ld_cs2(const float* p) { float2 v; asm volatile("ld.global.cs.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p)); return v; }
+__device__ __forceinline__ void st_cs2(float* p, float a, float b) { asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" :: "l"(p), "f"(a), "f"(b) : "memory"); }
 __device__ __forceinline__ float ld_cs(const float* p) { float v; asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v; }
 __device__ __forceinline__ void st_cs(float* p, float v) { asm volatile("st.global.cs.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory"); }
-__device__ __forceinline__ void rk_sincos(float x, float* sp, float* cp) { sincosf(x, sp, cp); }
+__device__ __forceinline__ void rk_sincos(float x, float& so, float& co) { float s, c; sincosf(x, &s, &c); so = s; co = c; }
 )SRC";
 
+// The per-sample work is generated once as text in which every per-sample name ends in '@'; the
+// kernel body instantiates it once (scalar) or twice ('a', 'b': two neighbouring samples per thread,
+// 16-byte loads and stores on the planes -- half the LSU instructions of a plane-bound T-only walk).
+std::string subst(const std::string& text, const char* suffix) {
+  std::string out;
+  out.reserve(text.size() + 64);
+  for (char ch : text) {
+    if (ch == '@') out += suffix;
+    else out.push_back(ch);
+  }
+  return out;
+}
+
+// resident CTAs per SM the register allocation is held to (RK_CHAIN_MINB, tuning knob)
+int min_blocks() {
+  static const int v = [] {
+    const char* e = getenv("RK_CHAIN_MINB");
+    const int m = e ? atoi(e) : 1;  // measured best: no cap (126 / 92 registers for the Fanuc chain)
+    return m < 1 ? 1 : (m > 16 ? 16 : m);
+  }();
+  return v;
+}
+
 template <typename S>
-std::string generate(const ChainProg<S>& Pg, bool soa, bool wantT, bool wantJ) {
+std::string generate(const ChainProg<S>& Pg, bool soa, bool wantT, bool wantJ, bool vec2) {
   std::string src = sizeof(S) == 8 ? kPreludeF64 : kPreludeF32;
+  std::string body;
   auto num = [](long long v) { return std::to_string(v); };
-  auto R = [&](int i, int j) { return "r" + num(i) + num(j); };
-  auto P = [&](int i) { return "p" + num(i); };
+  auto R = [&](int i, int j) { return "r" + num(i) + num(j) + "@"; };
+  auto P = [&](int i) { return "p" + num(i) + "@"; };
+  const std::string per = vec2 ? "256" : "128";   // samples per CTA and trip
   src += "struct Consts { S X[" + num(kMaxConst) + "][12]; S Tb[12]; S Tt[12]; };\n";
   src +=
-      "extern \"C\" __global__ void __launch_bounds__(128) rk_chain_jit(const S* __restrict__ values, int nvals,\n"
+      "extern \"C\" __global__ void __launch_bounds__(128, " + num(min_blocks()) + ") rk_chain_jit(const S* __restrict__ values, int nvals,\n"
       "    long long n, long long ld, S* __restrict__ T, S* __restrict__ J, const Consts C) {\n"
-      "  const long long stride = (long long)gridDim.x * 128;\n"
-      "  long long i = (long long)blockIdx.x * 128 + threadIdx.x;\n";
+      "  const long long stride = (long long)gridDim.x * " + per + ";\n"
+      "  long long i = ((long long)blockIdx.x * 128 + threadIdx.x)" + (vec2 ? " * 2" : "") + ";\n";
   // software pipeline: the next trip's values are in flight while this trip computes (the K1 LSU
   // kernel spent 55 % of its warp time waiting for its six loads before it did the same)
-  auto load_vals = [&](const std::string& dst_prefix, const std::string& idx, bool declare) {
+  auto load_vals = [&](const std::string& idx, bool declare) {
     for (int v = 0; v < Pg.nvar; ++v) {
       const std::string pl = num(Pg.plane[v]);
-      src += std::string("    ") + (declare ? "S " : "") + dst_prefix + num(v) + " = " +
-             (soa ? "LD(values + " + pl + "ll * ld + " + idx + ");\n" : "values[" + idx + " * nvals + " + pl + "];\n");
+      src += std::string("    ") + (declare ? (vec2 ? "S2 " : "S ") : "") + "nv" + num(v) + " = " +
+             (vec2 ? "LD2(values + " + pl + "ll * ld + " + idx + ");\n"
+                   : soa ? "LD(values + " + pl + "ll * ld + " + idx + ");\n"
+                         : "values[" + idx + " * nvals + " + pl + "];\n");
     }
   };
   src += "  if (i >= n) return;\n";
-  load_vals("nv", "i", true);
+  load_vals("i", true);
   src += "  for (; i < n; i += stride) {\n";
-  for (int v = 0; v < Pg.nvar; ++v) src += "    const S v" + num(v) + " = nv" + num(v) + ";\n";
+  for (int v = 0; v < Pg.nvar; ++v) {
+    if (vec2)
+      src += "    const S v" + num(v) + "a = nv" + num(v) + ".x, v" + num(v) + "b = nv" + num(v) + ".y;\n";
+    else
+      src += "    const S v" + num(v) + " = nv" + num(v) + ";\n";
+  }
   src += "    { const long long in = i + stride; if (in < n) {\n";
-  load_vals("nv", "in", false);
+  load_vals("in", false);
   src += "    } }\n";
   // frame
   for (int i = 0; i < 3; ++i) {
     for (int j = 0; j < 3; ++j)
-      src += "    S " + R(i, j) + " = " +
-             (Pg.has_base ? "C.Tb[" + num(i * 4 + j) + "]" : std::string(i == j ? "S(1)" : "S(0)")) + ";\n";
-    src += "    S " + P(i) + " = " + (Pg.has_base ? "C.Tb[" + num(i * 4 + 3) + "]" : std::string("S(0)")) + ";\n";
+      body += "    S " + R(i, j) + " = " +
+              (Pg.has_base ? "C.Tb[" + num(i * 4 + j) + "]" : std::string(i == j ? "S(1)" : "S(0)")) + ";\n";
+    body += "    S " + P(i) + " = " + (Pg.has_base ? "C.Tb[" + num(i * 4 + 3) + "]" : std::string("S(0)")) + ";\n";
   }
   auto mul12 = [&](const std::string& X) {  // F <- F * X (3x4 constant in the parameter block)
-    src += "    {\n";
+    body += "    {\n";
     for (int i = 0; i < 3; ++i) {
       for (int j = 0; j < 3; ++j)
-        src += "      const S t" + num(i) + num(j) + " = " + R(i, 0) + " * " + X + "[" + num(j) + "] + " + R(i, 1) +
-               " * " + X + "[" + num(4 + j) + "] + " + R(i, 2) + " * " + X + "[" + num(8 + j) + "];\n";
-      src += "      " + P(i) + " += " + R(i, 0) + " * " + X + "[3] + " + R(i, 1) + " * " + X + "[7] + " + R(i, 2) +
-             " * " + X + "[11];\n";
+        body += "      const S t" + num(i) + num(j) + " = " + R(i, 0) + " * " + X + "[" + num(j) + "] + " + R(i, 1) +
+                " * " + X + "[" + num(4 + j) + "] + " + R(i, 2) + " * " + X + "[" + num(8 + j) + "];\n";
+      body += "      " + P(i) + " += " + R(i, 0) + " * " + X + "[3] + " + R(i, 1) + " * " + X + "[7] + " + R(i, 2) +
+              " * " + X + "[11];\n";
     }
     for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) src += "      " + R(i, j) + " = t" + num(i) + num(j) + ";\n";
-    src += "    }\n";
+      for (int j = 0; j < 3; ++j) body += "      " + R(i, j) + " = t" + num(i) + num(j) + ";\n";
+    body += "    }\n";
   };
   int col = 0;
   for (int st = 0; st < Pg.nstep; ++st) {
     const int kind = Pg.kind[st], A = Pg.axis[st], I = (A + 1) % 3, Jc = (A + 2) % 3, sl = Pg.slot[st];
     const std::string val = std::string(Pg.neg[st] ? "-" : "") +
-                            (sl >= 0 ? "v" + num(sl) : "C.X[" + num(-1 - sl) + "][0]");
+                            (sl >= 0 ? "v" + num(sl) + "@" : "C.X[" + num(-1 - sl) + "][0]");
     if (Pg.active[st] && wantJ) {  // the frame BEFORE an active token: its screw axis and origin
       const std::string k = num(col);
-      src += "    const S u" + k + "x = " + R(0, A) + ", u" + k + "y = " + R(1, A) + ", u" + k + "z = " + R(2, A) + ";\n";
+      body += "    const S u" + k + "x@ = " + R(0, A) + ", u" + k + "y@ = " + R(1, A) + ", u" + k + "z@ = " + R(2, A) +
+              ";\n";
       if (kind == ST_ROT)
-        src += "    const S o" + k + "x = p0, o" + k + "y = p1, o" + k + "z = p2;\n";
+        body += "    const S o" + k + "x@ = p0@, o" + k + "y@ = p1@, o" + k + "z@ = p2@;\n";
     }
     if (Pg.active[st]) ++col;
     switch (kind) {
       case ST_TRANS:
-        src += "    { const S v = " + val + ";";
-        for (int r = 0; r < 3; ++r) src += " " + P(r) + " = fma(v, " + R(r, A) + ", " + P(r) + ");";
-        src += " }\n";
+        body += "    { const S v = " + val + ";";
+        for (int r = 0; r < 3; ++r) body += " " + P(r) + " = fma(v, " + R(r, A) + ", " + P(r) + ");";
+        body += " }\n";
         break;
       case ST_ROT:
       case ST_DROT:
-        src += "    { S s, c; rk_sincos(" + val + ", &s, &c);\n";
+        body += "    { S s, c; rk_sincos(" + val + ", s, c);\n";
         for (int r = 0; r < 3; ++r) {
-          src += "      { const S a = " + R(r, I) + ", b = " + R(r, Jc) + "; ";
+          body += "      { const S a = " + R(r, I) + ", b = " + R(r, Jc) + "; ";
           if (kind == ST_ROT)
-            src += R(r, I) + " = c * a + s * b; " + R(r, Jc) + " = c * b - s * a; }\n";
+            body += R(r, I) + " = c * a + s * b; " + R(r, Jc) + " = c * b - s * a; }\n";
           else
-            src += R(r, I) + " = c * b - s * a; " + R(r, Jc) + " = -c * a - s * b; " + R(r, A) + " = S(0); " + P(r) +
-                   " = S(0); }\n";
+            body += R(r, I) + " = c * b - s * a; " + R(r, Jc) + " = -c * a - s * b; " + R(r, A) + " = S(0); " + P(r) +
+                    " = S(0); }\n";
         }
-        src += "    }\n";
+        body += "    }\n";
         break;
       case ST_CONST: mul12("C.X[" + num(sl) + "]"); break;
       case ST_CONST_T:
         for (int r = 0; r < 3; ++r)
-          src += "    " + P(r) + " += " + R(r, 0) + " * C.X[" + num(sl) + "][3] + " + R(r, 1) + " * C.X[" + num(sl) +
-                 "][7] + " + R(r, 2) + " * C.X[" + num(sl) + "][11];\n";
+          body += "    " + P(r) + " += " + R(r, 0) + " * C.X[" + num(sl) + "][3] + " + R(r, 1) + " * C.X[" + num(sl) +
+                  "][7] + " + R(r, 2) + " * C.X[" + num(sl) + "][11];\n";
         break;
       default:  // ST_DTRANS
-        for (int r = 0; r < 3; ++r) src += "    " + P(r) + " = " + R(r, A) + ";\n";
+        for (int r = 0; r < 3; ++r) body += "    " + P(r) + " = " + R(r, A) + ";\n";
         for (int i = 0; i < 3; ++i)
-          for (int j = 0; j < 3; ++j) src += "    " + R(i, j) + " = S(0);\n";
+          for (int j = 0; j < 3; ++j) body += "    " + R(i, j) + " = S(0);\n";
     }
   }
   if (Pg.has_tool) mul12("C.Tt");
+  if (wantJ) {  // lever arms of the revolute columns
+    int a = 0;
+    for (int st = 0; st < Pg.nstep; ++st) {
+      if (!Pg.active[st]) continue;
+      const std::string k = num(a++);
+      if (Pg.kind[st] == ST_ROT)
+        body += "    const S dx" + k + "@ = p0@ - o" + k + "x@, dy" + k + "@ = p1@ - o" + k + "y@, dz" + k +
+                "@ = p2@ - o" + k + "z@;\n";
+    }
+  }
+  if (vec2)
+    src += subst(body, "a") + subst(body, "b");
+  else
+    src += subst(body, "");
   auto store = [&](const std::string& base, long long comp, long long ncomp, const std::string& v) {
-    if (soa)
-      src += "    ST(" + base + " + " + num(comp) + "ll * ld + i, " + v + ");\n";
+    if (vec2)
+      src += "    ST2(" + base + " + " + num(comp) + "ll * ld + i, " + subst(v, "a") + ", " + subst(v, "b") + ");\n";
+    else if (soa)
+      src += "    ST(" + base + " + " + num(comp) + "ll * ld + i, " + subst(v, "") + ");\n";
     else
-      src += "    " + base + "[i * " + num(ncomp) + " + " + num(comp) + "] = " + v + ";\n";
+      src += "    " + base + "[i * " + num(ncomp) + " + " + num(comp) + "] = " + subst(v, "") + ";\n";
   };
   if (wantT) {
     for (int i = 0; i < 3; ++i) {
@@ -252,13 +313,11 @@ std::string generate(const ChainProg<S>& Pg, bool soa, bool wantT, bool wantJ) {
     for (int st = 0; st < Pg.nstep; ++st) {
       if (!Pg.active[st]) continue;
       const std::string k = num(a);
-      const char* ax[3] = {"x", "y", "z"};
+      const char* ax[3] = {"x@", "y@", "z@"};
       if (Pg.kind[st] == ST_ROT) {  // [u x (O_n - O_k); u]
-        src += "    { const S dx = p0 - o" + k + "x, dy = p1 - o" + k + "y, dz = p2 - o" + k + "z;\n";
-        store("J", 0 * Pg.na + a, 6 * Pg.na, "u" + k + "y * dz - u" + k + "z * dy");
-        store("J", 1 * Pg.na + a, 6 * Pg.na, "u" + k + "z * dx - u" + k + "x * dz");
-        store("J", 2 * Pg.na + a, 6 * Pg.na, "u" + k + "x * dy - u" + k + "y * dx");
-        src += "    }\n";
+        store("J", 0 * Pg.na + a, 6 * Pg.na, "u" + k + "y@ * dz" + k + "@ - u" + k + "z@ * dy" + k + "@");
+        store("J", 1 * Pg.na + a, 6 * Pg.na, "u" + k + "z@ * dx" + k + "@ - u" + k + "x@ * dz" + k + "@");
+        store("J", 2 * Pg.na + a, 6 * Pg.na, "u" + k + "x@ * dy" + k + "@ - u" + k + "y@ * dx" + k + "@");
         for (int r = 0; r < 3; ++r) store("J", (3 + r) * Pg.na + a, 6 * Pg.na, "u" + k + ax[r]);
       } else {                      // prismatic: [u; 0]
         for (int r = 0; r < 3; ++r) store("J", r * Pg.na + a, 6 * Pg.na, "u" + k + ax[r]);
@@ -341,6 +400,16 @@ int chain_jit_launch(const ChainProg<S>& Pg, bool soa, const S* values, int nval
   // the axes and origins of the active tokens stay in registers until the end of the walk
   if (Pg.na > 12 || Pg.nstep > RK_MAX_TOKENS) return RK_ERR_UNSUPPORTED;
   const bool wantT = T != nullptr, wantJ = J != nullptr && Pg.na > 0;
+  // two samples per thread (8-byte plane accesses for FP32, which are otherwise 128 B per warp and
+  // LSU-instruction bound: 0.84 -> 0.72 ms T+J, 0.33 -> 0.31 ms T on 2^24 samples; FP64 planes are
+  // already 256 B per warp access and measured no faster): RK_CHAIN_VEC2 = 0 never, 1 FP32 walks
+  // (default), 2 every SOA walk
+  static const int vec2_mode = [] {
+    const char* e = getenv("RK_CHAIN_VEC2");
+    return e ? atoi(e) : 1;
+  }();
+  const bool vec2 = soa && vec2_mode > 0 && (vec2_mode > 1 || sizeof(S) == 4) && n % 2 == 0 && ld % 2 == 0 &&
+                    (((uintptr_t)values | (uintptr_t)T | (uintptr_t)J) & 15) == 0;
   int dev = 0;
   cudaGetDevice(&dev);
   CUfunction fn = nullptr;
@@ -350,7 +419,7 @@ int chain_jit_launch(const ChainProg<S>& Pg, bool soa, const S* values, int nval
     key.reserve(16 + 8 * Pg.nstep);
     key.push_back((char)sizeof(S)), key.push_back((char)soa), key.push_back((char)wantT), key.push_back((char)wantJ);
     key.push_back((char)Pg.has_base), key.push_back((char)Pg.has_tool), key.push_back((char)Pg.has_deriv);
-    key.push_back((char)Pg.nstep), key.push_back((char)Pg.nvar);
+    key.push_back((char)Pg.nstep), key.push_back((char)Pg.nvar), key.push_back((char)vec2);
     for (int st2 = 0; st2 < Pg.nstep; ++st2) {
       key.push_back((char)Pg.kind[st2]), key.push_back((char)Pg.axis[st2]), key.push_back((char)Pg.neg[st2]);
       key.push_back((char)Pg.active[st2]), key.push_back((char)Pg.slot[st2]);
@@ -359,7 +428,7 @@ int chain_jit_launch(const ChainProg<S>& Pg, bool soa, const S* values, int nval
     std::lock_guard<std::mutex> lock(g_mu);
     Entry& e = g_cache[{dev, key}];
     if (!e.fn && !e.failed) {
-      e.fn = build(generate(Pg, soa, wantT, wantJ));
+      e.fn = build(generate(Pg, soa, wantT, wantJ, vec2));
       e.failed = e.fn == nullptr;
     }
     fn = e.fn;
@@ -376,9 +445,9 @@ int chain_jit_launch(const ChainProg<S>& Pg, bool soa, const S* values, int nval
   long long nn = n, lld = ld;
   void* args[] = {(void*)&values, (void*)&nvals, (void*)&nn, (void*)&lld, (void*)&T, (void*)&J, (void*)&C};
   // same grid policy as stream_grid: ~8 trips per thread for large batches
-  const int64_t cap = (int64_t)sm_count() * 8;
-  const int64_t need = (n + 128 * 8 - 1) / (128 * 8);
-  int64_t grid = need >= 4 * cap ? need : ((n + 127) / 128 < cap ? (n + 127) / 128 : cap);
+  const int64_t cap = (int64_t)sm_count() * 8, per = vec2 ? 256 : 128;
+  const int64_t need = (n + per * 8 - 1) / (per * 8);
+  int64_t grid = need >= 4 * cap ? need : ((n + per - 1) / per < cap ? (n + per - 1) / per : cap);
   if (grid < 1) grid = 1;
   if (grid > 0x7fffffff) grid = 0x7fffffff;
   if (driver().launchKernel(fn, (unsigned)grid, 1, 1, 128, 1, 1, 0, (CUstream)st, args, nullptr) != CUDA_SUCCESS) {
@@ -388,6 +457,13 @@ int chain_jit_launch(const ChainProg<S>& Pg, bool soa, const S* values, int nval
   }
   return RK_OK;
 }
+
+template <typename S>
+std::string chain_jit_source(const ChainProg<S>& Pg, bool soa, bool wantT, bool wantJ, bool vec2) {
+  return generate(Pg, soa, wantT, wantJ && Pg.na > 0, vec2 && soa);
+}
+template std::string chain_jit_source<double>(const ChainProg<double>&, bool, bool, bool, bool);
+template std::string chain_jit_source<float>(const ChainProg<float>&, bool, bool, bool, bool);
 
 template int chain_jit_launch<double>(const ChainProg<double>&, bool, const double*, int, int64_t, int64_t, double*,
                                       double*, cudaStream_t);

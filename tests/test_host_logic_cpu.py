@@ -198,3 +198,40 @@ def test_mat_loader_reproduces_the_reference_dataset(golden):
     if os.path.exists(ref):
         q2, p2 = load_calibration_mat(ref, device=None)
         assert np.array_equal(q2, g["qs"]) and np.array_equal(p2, g["pts"])
+
+
+def test_chain_specialiser_source_compiles_for_sm100a(tmp_path):
+    """The run-time specialiser (rk_chain_jit.cu) is exercised on the GPU box through NVRTC; here its
+    generated source -- scalar and two-samples-per-thread, FP64 and FP32, derivative tokens and
+    constant segments included -- is compiled with nvcc for sm_100a, so a generator bug shows up
+    without a GPU."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from roboticmanipulators_b200 import _lib
+    from roboticmanipulators_b200.utils.robo_math import make_chain_struct
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not on PATH")
+    lib = _lib.load()
+    Tb = np.eye(4)
+    Tb[:3, 3] = [0.1, 0.2, 0.3]
+    cases = [
+        (["Tz", "Rz", "Tx", "Ry", "Tx", "Ry", "Tx", "Rx", "Ry", "Rx", "Tx"],
+         [0, 1, 0, 1, 0, 1, 0, 1, 1, 1, 0], None, None),
+        (["Rz", "Tx", "Ryd", "Tzi", "Rxi", "Tyd", "Ty"], [1, 0, 0, 0, 0, 0, 1], Tb, Tb),
+    ]
+    for k, (tokens, active, Tb_, Tt_) in enumerate(cases):
+        ch = make_chain_struct(tokens, active, T_base=Tb_, T_tool=Tt_)
+        for f32 in (0, 1):
+            for want in (1, 3, 1 | 4, 3 | 4):
+                need = lib.rk_chain_jit_source(C.byref(ch), len(tokens), _lib.RK_SOA, want, f32, None, 0)
+                assert need > 0
+                buf = C.create_string_buffer(need)
+                assert lib.rk_chain_jit_source(C.byref(ch), len(tokens), _lib.RK_SOA, want, f32, buf, need) == need
+                src = tmp_path / f"jit_{k}_{f32}_{want}.cu"
+                src.write_bytes(buf.value)
+                r = subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-cubin",
+                                    "-o", str(src.with_suffix(".cubin")), str(src)], capture_output=True, text=True)
+                assert r.returncode == 0, r.stderr[-2000:]
+                if want & 4:
+                    assert b"LD2(" in buf.value and b"ST2(" in buf.value

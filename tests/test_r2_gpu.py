@@ -279,3 +279,47 @@ def test_get_dq_from_dx_symbolic_inverse_matches_kernel():
     assert a.shape == (3, 400) and np.max(np.abs(a - ref) / np.maximum(1, np.abs(ref))) < 1e-9
     assert np.max(np.abs(b - ref) / np.maximum(1, np.abs(ref))) < 1e-10
     assert np.array_equal(b, c)
+
+
+def _chain_vec2_check():
+    """T-only and T+J walks over SOA planes, even (two samples per thread when enabled) and odd
+    (scalar kernel) batch sizes, FP64 and FP32, against the oracle."""
+    from roboticmanipulators_b200.utils.jacobians import JacobianCalculator
+    from roboticmanipulators_b200.utils.robo_math import Transformation
+    rng = np.random.default_rng(23)
+    seq, ind = O.FANUC_SEQ, O.FANUC_IND
+    TB = np.eye(4)
+    TB[:3, 3] = [10.0, -20.0, 30.0]
+    for n in (2, 254, 4096 + 2, 100001, 70000):
+        vals = rng.uniform(-3, 3, size=(n, 13))
+        T_ref = O.chain(seq, vals)
+        J_ref = O.jacobian_numerically(seq, ind, vals, TB, np.eye(4))
+        for dt, tol in ((torch.float64, 1e-13), (torch.float32, 2e-5)):
+            planes = dev(vals, dt).t().contiguous()            # [13, n] storage
+            T = Transformation.batch(seq, planes.t(), layout="soa")
+            assert T.shape == (n, 4, 4) and T.stride(0) == 1
+            assert np.max(np.abs(T.double().cpu().numpy() - T_ref)) / np.abs(T_ref).max() < tol
+            jc = JacobianCalculator(seq, ind, T_base=TB)
+            Tj, J = jc.calculate_numerically_batch(planes.t(), with_pose=True, layout="soa")
+            assert np.max(np.abs(Tj.double().cpu().numpy() - TB @ T_ref)) / np.abs(T_ref).max() < tol
+            assert np.max(np.abs(J.double().cpu().numpy() - J_ref)) / np.abs(J_ref).max() < tol
+
+
+def test_chain_two_samples_per_thread():
+    from roboticmanipulators_b200 import _lib
+    _chain_vec2_check()
+    assert _lib.load().rk_chain_jit_status() == b"ok"
+
+
+def test_chain_two_samples_per_thread_with_jacobian():
+    """RK_CHAIN_VEC2=2 selects the two-sample kernel for T+J walks too (read once per process)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, RK_CHAIN_VEC2="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c",
+                        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests');"
+                        "import test_r2_gpu as t; t._chain_vec2_check(); print('ok')" % (root, root)],
+                       env=env, capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
