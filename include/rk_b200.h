@@ -229,10 +229,12 @@ int rk_chain_fk_jac_f32(const RkChain* chain, const float* values, int nvals, in
  * be loaded, and an interpreting kernel otherwise (or with RK_CHAIN_JIT=0 in the environment).
  * Returns "ok", or why the last specialisation was not used. */
 const char* rk_chain_jit_status(void);
-/* The CUDA source of that specialisation (host only, no GPU needed): want = 1 T | 2 J | 4 two samples
- * per thread (SOA planes, two-element vector accesses; chosen automatically for FP32 walks with an
- * even n and ld; RK_CHAIN_VEC2=0/1/2 in the environment = never / FP32 walks / every SOA walk).  Writes at most
- * cap bytes (NUL-terminated) into buf and returns the size needed, or -1 for a bad chain. */
+/* The CUDA source of that specialisation (host only, no GPU needed).  want = 1 T | 2 J | 4 two
+ * samples per thread | 8 the dq = J^-1 dx solve of rk_chain_dq_from_dx_f64 on rows 0..na-1.  Two
+ * samples per thread (SOA planes, two-element vector accesses) is chosen automatically for FP32
+ * walks with an even n and ld; RK_CHAIN_VEC2=0/1/2 in the environment = never / FP32 walks / every
+ * SOA walk.  Writes at most cap bytes (NUL-terminated) into buf and returns the size needed, or -1
+ * for a bad chain. */
 int64_t rk_chain_jit_source(const RkChain* chain, int nvals, int flags, int want, int f32, char* buf,
                             int64_t cap);
 

@@ -385,6 +385,9 @@ static int launch_chain_solve(const RkChain* chain, const double* values, int nv
   const bool soa = (flags & RK_SOA) != 0;
   if (soa && ld < n) return RK_ERR_INVALID_ARG;
   cudaStream_t st = (cudaStream_t)stream;
+  // straight-line specialisation first (rk_chain_jit.cu), the interpreting kernel otherwise
+  rc = chain_jit_solve_launch<double>(Pg, soa, values, nvals, n, ld, dx, dq, ok, st);
+  if (rc != RK_ERR_UNSUPPORTED) return rc;
 #define RK_NA(NA)                                                                                         \
   case NA:                                                                                                \
     return soa ? launch_solve_na<double, true, NA>(Pg, values, nvals, n, ld, dx, dq, ok, st)              \
@@ -398,7 +401,10 @@ template <typename S>
 static int64_t jit_source(const RkChain* chain, int nvals, int flags, int want, char* buf, int64_t cap) {
   ChainProg<S> Pg;
   if (compile_chain<S>(chain, nvals, Pg) != RK_OK) return -1;
-  const std::string src = chain_jit_source<S>(Pg, flags & RK_SOA, want & 1, want & 2, want & 4);
+  if (want & 8)
+    for (int r = 0; r < Pg.na && r < 6; ++r) Pg.rows[r] = (int8_t)r;
+  const std::string src = chain_jit_source<S>(Pg, flags & RK_SOA, want & 1, want & 2, want & 4, want & 8);
+  if (src.empty()) return -1;
   if (buf && cap > 0) {
     const size_t m = src.size() < (size_t)cap - 1 ? src.size() : (size_t)cap - 1;
     memcpy(buf, src.data(), m);

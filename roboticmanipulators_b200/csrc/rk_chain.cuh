@@ -34,7 +34,11 @@ int chain_jit_launch(const ChainProg<S>& Pg, bool soa, const S* values, int nval
                      S* J, cudaStream_t st);
 // the CUDA source the specialiser would compile (diagnostics and the CPU-side build test)
 template <typename S>
-std::string chain_jit_source(const ChainProg<S>& Pg, bool soa, bool wantT, bool wantJ, bool vec2);
+std::string chain_jit_source(const ChainProg<S>& Pg, bool soa, bool wantT, bool wantJ, bool vec2, bool solve);
+// dq = J[Pg.rows, :]^-1 dx per sample, elimination unrolled over the chain's own columns
+template <typename S>
+int chain_jit_solve_launch(const ChainProg<S>& Pg, bool soa, const S* values, int nvals, int64_t n, int64_t ld,
+                           const S* dx, S* dq, uint8_t* ok, cudaStream_t st);
 const char* chain_jit_status();  // last NVRTC / driver message (diagnostics)
 
 }  // namespace rk

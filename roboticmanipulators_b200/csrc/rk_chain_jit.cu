@@ -177,7 +177,8 @@ int min_blocks() {
 }
 
 template <typename S>
-std::string generate(const ChainProg<S>& Pg, bool soa, bool wantT, bool wantJ, bool vec2) {
+std::string generate(const ChainProg<S>& Pg, bool soa, bool wantT, bool wantJ, bool vec2, bool solve = false) {
+  if (solve) wantT = false, wantJ = true, vec2 = false;  // J[rows, :] dq = dx, solved in registers
   std::string src = sizeof(S) == 8 ? kPreludeF64 : kPreludeF32;
   std::string body;
   auto num = [](long long v) { return std::to_string(v); };
@@ -187,7 +188,8 @@ std::string generate(const ChainProg<S>& Pg, bool soa, bool wantT, bool wantJ, b
   src += "struct Consts { S X[" + num(kMaxConst) + "][12]; S Tb[12]; S Tt[12]; };\n";
   src +=
       "extern \"C\" __global__ void __launch_bounds__(128, " + num(min_blocks()) + ") rk_chain_jit(const S* __restrict__ values, int nvals,\n"
-      "    long long n, long long ld, S* __restrict__ T, S* __restrict__ J, const Consts C) {\n"
+      "    long long n, long long ld, S* __restrict__ T, S* __restrict__ J, const Consts C,\n"
+      "    const S* __restrict__ dx, S* __restrict__ dq, unsigned char* __restrict__ ok) {\n"
       "  const long long stride = (long long)gridDim.x * " + per + ";\n"
       "  long long i = ((long long)blockIdx.x * 128 + threadIdx.x)" + (vec2 ? " * 2" : "") + ";\n";
   // software pipeline: the next trip's values are in flight while this trip computes (the K1 LSU
@@ -213,6 +215,10 @@ std::string generate(const ChainProg<S>& Pg, bool soa, bool wantT, bool wantJ, b
   src += "    { const long long in = i + stride; if (in < n) {\n";
   load_vals("in", false);
   src += "    } }\n";
+  if (solve)  // the right-hand side is requested before the walk and needed after it
+    for (int r = 0; r < Pg.na; ++r)
+      src += "    S b" + num(r) + " = " +
+             (soa ? "LD(dx + " + num(r) + "ll * ld + i);\n" : "dx[i * " + num(Pg.na) + " + " + num(r) + "];\n");
   // frame
   for (int i = 0; i < 3; ++i) {
     for (int j = 0; j < 3; ++j)
@@ -308,7 +314,55 @@ std::string generate(const ChainProg<S>& Pg, bool soa, bool wantT, bool wantJ, b
     store("T", 12, 16, "S(0)"), store("T", 13, 16, "S(0)"), store("T", 14, 16, "S(0)");
     store("T", 15, 16, Pg.has_deriv ? "S(0)" : "S(1)");
   }
-  if (wantJ) {
+  if (solve) {
+    // entry (row, column a) of the Jacobian as an expression of the walk's registers
+    const int N = Pg.na;
+    auto entry = [&](int row, int a, int kind) -> std::string {
+      const std::string k = num(a);
+      const char* ax[3] = {"x", "y", "z"};
+      if (kind != ST_ROT) return row < 3 ? "u" + k + ax[row] : std::string("S(0)");
+      if (row >= 3) return "u" + k + ax[row - 3];
+      const int i1 = (row + 1) % 3, i2 = (row + 2) % 3;
+      return "u" + k + ax[i1] + " * d" + ax[i2] + k + " - u" + k + ax[i2] + " * d" + ax[i1] + k;
+    };
+    auto A = [&](int r, int c) { return "a" + num(r) + "_" + num(c); };
+    int a = 0;
+    for (int st = 0; st < Pg.nstep; ++st) {
+      if (!Pg.active[st]) continue;
+      for (int r = 0; r < N; ++r) src += "    S " + A(r, a) + " = " + entry(Pg.rows[r], a, Pg.kind[st]) + ";\n";
+      ++a;
+    }
+    // Gaussian elimination with partial pivoting, the same operation order as gauss_solve<S, N>
+    // of rk_common.cuh (row exchanges are selects, nothing is indexed)
+    src += "    bool good = true;\n";
+    for (int k = 0; k < N; ++k) {
+      for (int r = k + 1; r < N; ++r) {
+        src += "    { const bool sw = fabs(" + A(r, k) + ") > fabs(" + A(k, k) + ");\n";
+        for (int c = k; c < N; ++c)
+          src += "      { const S t = " + A(k, c) + "; " + A(k, c) + " = sw ? " + A(r, c) + " : t; " + A(r, c) +
+                 " = sw ? t : " + A(r, c) + "; }\n";
+        src += "      { const S t = b" + num(k) + "; b" + num(k) + " = sw ? b" + num(r) + " : t; b" + num(r) +
+               " = sw ? t : b" + num(r) + "; } }\n";
+      }
+      src += "    good = good && (" + A(k, k) + " != S(0));\n";
+      src += "    { const S inv = S(1) / " + A(k, k) + ";\n";
+      for (int r = k + 1; r < N; ++r) {
+        src += "      { const S f = " + A(r, k) + " * inv;";
+        for (int c = k + 1; c < N; ++c) src += " " + A(r, c) + " -= f * " + A(k, c) + ";";
+        src += " b" + num(r) + " -= f * b" + num(k) + "; }\n";
+      }
+      src += "    }\n";
+    }
+    for (int k = N - 1; k >= 0; --k) {
+      src += "    { S acc = b" + num(k) + ";";
+      for (int c = k + 1; c < N; ++c) src += " acc -= " + A(k, c) + " * b" + num(c) + ";";
+      src += " b" + num(k) + " = acc / " + A(k, k) + "; }\n";
+    }
+    for (int r = 0; r < N; ++r)
+      src += soa ? "    ST(dq + " + num(r) + "ll * ld + i, b" + num(r) + ");\n"
+                 : "    dq[i * " + num(N) + " + " + num(r) + "] = b" + num(r) + ";\n";
+    src += "    if (ok) ok[i] = good ? 1 : 0;\n";
+  } else if (wantJ) {
     int a = 0;
     for (int st = 0; st < Pg.nstep; ++st) {
       if (!Pg.active[st]) continue;
@@ -390,8 +444,8 @@ const char* chain_jit_status() {
 }
 
 template <typename S>
-int chain_jit_launch(const ChainProg<S>& Pg, bool soa, const S* values, int nvals, int64_t n, int64_t ld, S* T,
-                     S* J, cudaStream_t st) {
+static int jit_run(const ChainProg<S>& Pg, bool soa, const S* values, int nvals, int64_t n, int64_t ld, S* T, S* J,
+                   const S* dx, S* dq, uint8_t* ok, bool solve, cudaStream_t st) {
   static const bool disabled = [] {
     const char* e = getenv("RK_CHAIN_JIT");
     return e && e[0] == '0';
@@ -399,7 +453,7 @@ int chain_jit_launch(const ChainProg<S>& Pg, bool soa, const S* values, int nval
   if (disabled) return RK_ERR_UNSUPPORTED;
   // the axes and origins of the active tokens stay in registers until the end of the walk
   if (Pg.na > 12 || Pg.nstep > RK_MAX_TOKENS) return RK_ERR_UNSUPPORTED;
-  const bool wantT = T != nullptr, wantJ = J != nullptr && Pg.na > 0;
+  const bool wantT = !solve && T != nullptr, wantJ = solve || (J != nullptr && Pg.na > 0);
   // two samples per thread (8-byte plane accesses for FP32, which are otherwise 128 B per warp and
   // LSU-instruction bound: 0.84 -> 0.72 ms T+J, 0.33 -> 0.31 ms T on 2^24 samples; FP64 planes are
   // already 256 B per warp access and measured no faster): RK_CHAIN_VEC2 = 0 never, 1 FP32 walks
@@ -408,7 +462,7 @@ int chain_jit_launch(const ChainProg<S>& Pg, bool soa, const S* values, int nval
     const char* e = getenv("RK_CHAIN_VEC2");
     return e ? atoi(e) : 1;
   }();
-  const bool vec2 = soa && vec2_mode > 0 && (vec2_mode > 1 || sizeof(S) == 4) && n % 2 == 0 && ld % 2 == 0 &&
+  const bool vec2 = !solve && soa && vec2_mode > 0 && (vec2_mode > 1 || sizeof(S) == 4) && n % 2 == 0 && ld % 2 == 0 &&
                     (((uintptr_t)values | (uintptr_t)T | (uintptr_t)J) & 15) == 0;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -420,6 +474,9 @@ int chain_jit_launch(const ChainProg<S>& Pg, bool soa, const S* values, int nval
     key.push_back((char)sizeof(S)), key.push_back((char)soa), key.push_back((char)wantT), key.push_back((char)wantJ);
     key.push_back((char)Pg.has_base), key.push_back((char)Pg.has_tool), key.push_back((char)Pg.has_deriv);
     key.push_back((char)Pg.nstep), key.push_back((char)Pg.nvar), key.push_back((char)vec2);
+    key.push_back((char)solve);
+    if (solve)
+      for (int r = 0; r < Pg.na; ++r) key.push_back((char)Pg.rows[r]);
     for (int st2 = 0; st2 < Pg.nstep; ++st2) {
       key.push_back((char)Pg.kind[st2]), key.push_back((char)Pg.axis[st2]), key.push_back((char)Pg.neg[st2]);
       key.push_back((char)Pg.active[st2]), key.push_back((char)Pg.slot[st2]);
@@ -428,7 +485,7 @@ int chain_jit_launch(const ChainProg<S>& Pg, bool soa, const S* values, int nval
     std::lock_guard<std::mutex> lock(g_mu);
     Entry& e = g_cache[{dev, key}];
     if (!e.fn && !e.failed) {
-      e.fn = build(generate(Pg, soa, wantT, wantJ, vec2));
+      e.fn = build(generate(Pg, soa, wantT, wantJ, vec2, solve));
       e.failed = e.fn == nullptr;
     }
     fn = e.fn;
@@ -443,7 +500,8 @@ int chain_jit_launch(const ChainProg<S>& Pg, bool soa, const S* values, int nval
   memcpy(C.Tb, Pg.Tb, sizeof(C.Tb));
   memcpy(C.Tt, Pg.Tt, sizeof(C.Tt));
   long long nn = n, lld = ld;
-  void* args[] = {(void*)&values, (void*)&nvals, (void*)&nn, (void*)&lld, (void*)&T, (void*)&J, (void*)&C};
+  void* args[] = {(void*)&values, (void*)&nvals, (void*)&nn,  (void*)&lld, (void*)&T,
+                  (void*)&J,      (void*)&C,     (void*)&dx,  (void*)&dq,  (void*)&ok};
   // same grid policy as stream_grid: ~8 trips per thread for large batches
   const int64_t cap = (int64_t)sm_count() * 8, per = vec2 ? 256 : 128;
   const int64_t need = (n + per * 8 - 1) / (per * 8);
@@ -459,11 +517,26 @@ int chain_jit_launch(const ChainProg<S>& Pg, bool soa, const S* values, int nval
 }
 
 template <typename S>
-std::string chain_jit_source(const ChainProg<S>& Pg, bool soa, bool wantT, bool wantJ, bool vec2) {
-  return generate(Pg, soa, wantT, wantJ && Pg.na > 0, vec2 && soa);
+int chain_jit_launch(const ChainProg<S>& Pg, bool soa, const S* values, int nvals, int64_t n, int64_t ld, S* T,
+                     S* J, cudaStream_t st) {
+  return jit_run<S>(Pg, soa, values, nvals, n, ld, T, J, nullptr, nullptr, nullptr, false, st);
 }
-template std::string chain_jit_source<double>(const ChainProg<double>&, bool, bool, bool, bool);
-template std::string chain_jit_source<float>(const ChainProg<float>&, bool, bool, bool, bool);
+template <typename S>
+int chain_jit_solve_launch(const ChainProg<S>& Pg, bool soa, const S* values, int nvals, int64_t n, int64_t ld,
+                           const S* dx, S* dq, uint8_t* ok, cudaStream_t st) {
+  if (Pg.na < 1 || Pg.na > 6) return RK_ERR_UNSUPPORTED;
+  return jit_run<S>(Pg, soa, values, nvals, n, ld, nullptr, nullptr, dx, dq, ok, true, st);
+}
+template int chain_jit_solve_launch<double>(const ChainProg<double>&, bool, const double*, int, int64_t, int64_t,
+                                            const double*, double*, uint8_t*, cudaStream_t);
+
+template <typename S>
+std::string chain_jit_source(const ChainProg<S>& Pg, bool soa, bool wantT, bool wantJ, bool vec2, bool solve) {
+  if (solve && (Pg.na < 1 || Pg.na > 6)) return std::string();
+  return generate(Pg, soa, wantT, wantJ && Pg.na > 0, vec2 && soa, solve);
+}
+template std::string chain_jit_source<double>(const ChainProg<double>&, bool, bool, bool, bool, bool);
+template std::string chain_jit_source<float>(const ChainProg<float>&, bool, bool, bool, bool, bool);
 
 template int chain_jit_launch<double>(const ChainProg<double>&, bool, const double*, int, int64_t, int64_t, double*,
                                       double*, cudaStream_t);

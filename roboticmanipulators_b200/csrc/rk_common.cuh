@@ -1,5 +1,6 @@
 // Shared device helpers for librk_b200 (sm_100a).  No torch, no third-party headers.
 #pragma once
+#include <type_traits>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -507,41 +508,55 @@ __device__ __forceinline__ void xf_mul(const S* A, const S* B, S* C) {
 // partial pivoting.  Every index is static -- the pivot row is brought up by conditional swaps, not
 // by an indexed access -- so A and b never leave the register file.  x overwrites b; returns false
 // when a pivot is exactly zero (the result then holds inf / nan, like a failed np.linalg.inv).
+// (The loops are unrolled by template recursion: with `#pragma unroll` on the triangular loops nvcc
+// 12.9 kept the matrix on the stack and indexed it dynamically -- 384 bytes of local memory and ~230
+// LDL/STL per solve, 3.6 ms per 2^24 Fanuc poses.)
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
 template <typename S, int N>
 __device__ __forceinline__ bool gauss_solve(S (&A)[N][N], S (&b)[N]) {
   bool ok = true;
-#pragma unroll
-  for (int k = 0; k < N; ++k) {
-#pragma unroll
-    for (int r = k + 1; r < N; ++r) {
+  static_for<0, N>([&](auto kc) {
+    constexpr int k = decltype(kc)::value;
+    static_for<k + 1, N>([&](auto rc) {
+      constexpr int r = decltype(rc)::value;
       const bool sw = Sc<S>::abs(A[r][k]) > Sc<S>::abs(A[k][k]);
-#pragma unroll
-      for (int c = k; c < N; ++c) {
+      static_for<k, N>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
         const S t = A[k][c];
         A[k][c] = sw ? A[r][c] : t;
         A[r][c] = sw ? t : A[r][c];
-      }
+      });
       const S t = b[k];
       b[k] = sw ? b[r] : t;
       b[r] = sw ? t : b[r];
-    }
+    });
     ok = ok && (A[k][k] != S(0));
     const S inv = S(1) / A[k][k];
-#pragma unroll
-    for (int r = k + 1; r < N; ++r) {
+    static_for<k + 1, N>([&](auto rc) {
+      constexpr int r = decltype(rc)::value;
       const S f = A[r][k] * inv;
-#pragma unroll
-      for (int c = k + 1; c < N; ++c) A[r][c] -= f * A[k][c];
+      static_for<k + 1, N>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        A[r][c] -= f * A[k][c];
+      });
       b[r] -= f * b[k];
-    }
-  }
-#pragma unroll
-  for (int k = N - 1; k >= 0; --k) {
+    });
+  });
+  static_for<0, N>([&](auto kc) {
+    constexpr int k = N - 1 - decltype(kc)::value;
     S acc = b[k];
-#pragma unroll
-    for (int c = k + 1; c < N; ++c) acc -= A[k][c] * b[c];
+    static_for<k + 1, N>([&](auto cc) {
+      constexpr int c = decltype(cc)::value;
+      acc -= A[k][c] * b[c];
+    });
     b[k] = acc / A[k][k];
-  }
+  });
   return ok;
 }
 

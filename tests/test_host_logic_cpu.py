@@ -223,7 +223,7 @@ def test_chain_specialiser_source_compiles_for_sm100a(tmp_path):
     for k, (tokens, active, Tb_, Tt_) in enumerate(cases):
         ch = make_chain_struct(tokens, active, T_base=Tb_, T_tool=Tt_)
         for f32 in (0, 1):
-            for want in (1, 3, 1 | 4, 3 | 4):
+            for want in (1, 3, 1 | 4, 3 | 4) + ((8,) if not f32 else ()):
                 need = lib.rk_chain_jit_source(C.byref(ch), len(tokens), _lib.RK_SOA, want, f32, None, 0)
                 assert need > 0
                 buf = C.create_string_buffer(need)

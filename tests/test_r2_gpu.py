@@ -323,3 +323,47 @@ def test_chain_two_samples_per_thread_with_jacobian():
                         "import test_r2_gpu as t; t._chain_vec2_check(); print('ok')" % (root, root)],
                        env=env, capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def _chain_dq_case():
+    from roboticmanipulators_b200.utils.jacobians import JacobianCalculator
+    rng = np.random.default_rng(29)
+    outs = []
+    for seq, ind, rows in (("RzTxRyTzRxTy", [1, 1, 1, 1, 1, 1], None),
+                           ("RzTzRyTxRxTy", [1, 0, 1, 1, 1, 0], (0, 1, 2, 4)),
+                           ("RzTzRyTxRy", [1, 0, 1, 0, 1], (0, 2, 4))):
+        jc = JacobianCalculator(seq, ind)
+        vals = rng.uniform(-2, 2, size=(4097, len(ind)))
+        dx = rng.normal(size=(4097, sum(ind)))
+        dq, ok = jc.dq_from_dx_batch(dev(vals), dev(dx), rows=rows)
+        outs.append(dq.cpu().numpy())
+        outs.append(ok.cpu().numpy().astype(np.float64)[:, None])
+    return outs
+
+
+def test_chain_dq_specialised_kernel_matches_interpreter(tmp_path):
+    """rk_chain_dq_from_dx_f64 runs straight-line code generated for the chain (elimination unrolled
+    over its own columns); RK_CHAIN_JIT=0 in a second process selects the interpreting kernel. Same
+    operation order, so the two agree to rounding of the Jacobian entries."""
+    import os
+    import subprocess
+    import sys
+    from roboticmanipulators_b200 import _lib
+    mine = _chain_dq_case()
+    assert _lib.load().rk_chain_jit_status() == b"ok"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = str(tmp_path / "interp.npz")
+    r = subprocess.run([sys.executable, "-c",
+                        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests');"
+                        "import numpy as np, test_r2_gpu as t; np.savez(%r, *t._chain_dq_case())" % (root, root, path)],
+                       env=dict(os.environ, RK_CHAIN_JIT="0"), capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    other = np.load(path)
+    for k, a in enumerate(mine):
+        b = other[f"arr_{k}"]
+        if a.shape[1] == 1:
+            assert np.array_equal(a, b)
+        else:
+            scale = np.maximum(1.0, np.abs(b).max(axis=1, keepdims=True))
+            assert np.median(np.abs(a - b) / scale) < 1e-14
+            assert np.quantile(np.abs(a - b) / scale, 0.99) < 1e-9      # ill-conditioned samples amplify rounding

@@ -80,6 +80,20 @@ def main():
     timed("rr_fk_jac_soa", n, 16 + 128 + 96, lambda: rr.forward_kinematics_batch(q2, jacobian=True, layout="soa"))
     T2 = rr.forward_kinematics_batch(q2, layout="soa")
     timed("rr_ik2_soa", n, 24 + 2 * 16 + 2, lambda: rr.inverse_kinematics_batch(T2, layout="soa"))
+    # FP32 variants (float32 input -> FP32 kernels, half the bytes)
+    f32 = torch.float32
+    q3f = q3.t().to(f32).contiguous().t()
+    timed("rrr_fk_jac_soa_f32", n, (24 + 128 + 144) // 2,
+          lambda: rrr.forward_kinematics_batch(q3f, jacobian=True, layout="soa"))
+    T3f = rrr.forward_kinematics_batch(q3f, layout="soa")
+    timed("rrr_ik4_soa_f32", n, 12 + 4 * 12 + 4, lambda: rrr.inverse_kinematics_batch(T3f, layout="soa"))
+    del T3f, q3f
+    q2f = q2.t().to(f32).contiguous().t()
+    timed("rr_fk_jac_soa_f32", n, (16 + 128 + 96) // 2,
+          lambda: rr.forward_kinematics_batch(q2f, jacobian=True, layout="soa"))
+    T2f = rr.forward_kinematics_batch(q2f, layout="soa")
+    timed("rr_ik2_soa_f32", n, 12 + 2 * 8 + 2, lambda: rr.inverse_kinematics_batch(T2f, layout="soa"))
+    del T2f, q2f
     del T2, q2, q3, q3a
     # --- A6/A7: generic token interpreter on the Fanuc sequence (13 tokens, 6 joints)
     n = int((1 << 24) * S)
@@ -101,12 +115,28 @@ def main():
     timed("chain_fk_jac_fanuc_seq_soa", n, 13 * 8 + 128 + 288,
           lambda: jc.calculate_numerically_batch(vals, layout="soa"))
     timed("chain_fk_fanuc_seq_soa", n, 13 * 8 + 128, lambda: Transformation.batch(seq, vals, layout="soa"))
-    del vals, qm
+    valsf = vals.t().to(f32).contiguous().t()
+    timed("chain_fk_jac_fanuc_seq_soa_f32", n, (13 * 8 + 128 + 288) // 2,
+          lambda: jc.calculate_numerically_batch(valsf, layout="soa"))
+    timed("chain_fk_fanuc_seq_soa_f32", n, (13 * 8 + 128) // 2, lambda: Transformation.batch(seq, valsf, layout="soa"))
+    del valsf
+    # dq = J^-1 dx inside the kernel (TrajectoryGenerator.get_dq_from_dx for any robot)
+    dx6 = rnd((6, n)).t()
+    vals_a, dx6_a = vals.contiguous(), dx6.contiguous()     # this wrapper takes sample-major arrays
+    timed("chain_dq_from_dx_6x6", n, 13 * 8 + 48 + 48 + 1, lambda: jc.dq_from_dx_batch(vals_a, dx6_a))
+    del vals_a, dx6_a
+    fan = Fanuc165F()
+    qf = rnd((6, n), -1.0, 1.0).t()
+    timed("fanuc_dq_from_dx", n, 48 + 48 + 48 + 1, lambda: fan.dq_from_dx_batch(qf, dx6, layout="soa"))
+    del vals, qm, dx6, qf
     # --- A8/A9: trajectories
     tg = TrajectoryGenerator(1, 20, 1, 10, control_freq=10)
     nt, ns = int((1 << 15) * S), 1000
     a6, b6 = rnd((nt, 6), -np.pi, np.pi), rnd((nt, 6), -np.pi, np.pi)
     timed("trap_p2p_6joints", nt * ns, 3 * 48 + 8, lambda: tg.generate_p2p_trajectory_batch(a6, b6, ns))
+    a3, b3 = a6[:, :3].contiguous(), b6[:, :3].contiguous()
+    timed("rrr_p2p_fk_f32", nt * ns, (3 * 24 + 8 + 128 + 144) // 2 + 4,
+          lambda: tg.generate_p2p_trajectory_batch(a3, b3, ns, robot=rrr, dtype=f32))
     p0 = torch.stack([rnd((nt,), 0.5, 1.2), rnd((nt,), -0.6, 0.6), rnd((nt,), 0.2, 1.0)], 1)
     pf = torch.stack([rnd((nt,), 0.5, 1.2), rnd((nt,), -0.6, 0.6), rnd((nt,), 0.2, 1.0)], 1)
     timed("rrr_lin_ik_dq", nt * ns, 24 + 24 + 8 + 24 + 24 + 1,
