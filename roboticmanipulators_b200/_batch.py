@@ -40,19 +40,6 @@ def prep_input(x, ncomp, layout, dtype):
     return x.contiguous(), n
 
 
-def alloc_out(n, shape, layout, dtype, device):
-    """Allocate an output with logical shape [n, *shape]; returns (logical_view, storage)."""
-    ncomp = 1
-    for s in shape:
-        ncomp *= s
-    if layout == "soa":
-        store = torch.empty((ncomp, n), dtype=dtype, device=device)
-        view = store.view(*shape, n).permute(len(shape), *range(len(shape)))
-        return view, store
-    store = torch.empty((n, *shape), dtype=dtype, device=device)
-    return store, store
-
-
 def alloc_view(n, shape, layout, dtype, device):
     """One output with logical shape [n, *shape] in ONE torch call (call-latency path: measured on the
     GPU box, an allocation costs ~2.3 us of host time and every Python-level slice / view / permute

@@ -57,12 +57,10 @@ class _SerialArm(Robot):
             layout = _batch.detect_layout(q, nq)
         qs, ld = _batch.prep_input(q, nq, layout, dt)
         n, dev = qs.shape[0], qs.device
-        T, Ts = _batch.alloc_out(n, (4, 4), layout, dt, dev)
-        J = Js = None
-        if jacobian:
-            J, Js = _batch.alloc_out(n, (6, nq), layout, dt, dev)
+        T = _batch.alloc_view(n, (4, 4), layout, dt, dev)
+        J = _batch.alloc_view(n, (6, nq), layout, dt, dev) if jacobian else None
         launch(getattr(_lib.load(), self._fk_fn + _SFX[dt]), dev, self._cached_struct(), _lib.ptr(qs), n, ld,
-               _batch.flags_of(layout), _lib.ptr(Ts), _lib.ptr(Js))
+               _batch.flags_of(layout), _lib.ptr(T), _lib.ptr(J))
         return (T, J) if jacobian else T
 
     def inverse_kinematics_batch(self, T, branches=None, *, layout="auto"):
@@ -80,16 +78,10 @@ class _SerialArm(Robot):
         for b in branches:
             flat.extend([int(v) for v in (b if isinstance(b, (tuple, list)) else (b,))])
         br = (C.c_int8 * len(flat))(*flat)
-        if layout == "soa":
-            qstore = torch.empty((nb * nq, n), dtype=dt, device=dev)
-            vstore = torch.empty((nb, n), dtype=torch.uint8, device=dev)
-            qv, vv = qstore.view(nb, nq, n).permute(2, 0, 1), vstore.t()
-        else:
-            qstore = torch.empty((n, nb, nq), dtype=dt, device=dev)
-            vstore = torch.empty((n, nb), dtype=torch.uint8, device=dev)
-            qv, vv = qstore, vstore
+        qv = _batch.alloc_view(n, (nb, nq), layout, dt, dev)
+        vv = _batch.alloc_view(n, (nb,), layout, torch.uint8, dev)
         launch(getattr(_lib.load(), self._ik_fn + _SFX[dt]), dev, self._cached_struct(), _lib.ptr(Ts), n, ld,
-               _batch.flags_of(layout), br, nb, _lib.ptr(qstore), _lib.ptr(vstore))
+               _batch.flags_of(layout), br, nb, _lib.ptr(qv), _lib.ptr(vv))
         return qv, vv.view(torch.bool)
 
     def forward_kinematics(self, q_values, plot=True):

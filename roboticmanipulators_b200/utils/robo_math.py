@@ -372,15 +372,12 @@ def chain_batch(tokens, values, *, T_base=None, T_tool=None, active=None, src=No
     vs, ld = _batch.prep_input(values, nvals, layout, dt)
     n, dev = vs.shape[0], vs.device
     ch = make_chain_struct(tokens, active, src, cst, T_base, T_tool)
-    T = Ts = J = Js = None
-    if want_T:
-        T, Ts = _batch.alloc_out(n, (4, 4), layout, dt, dev)
     na = int(sum(1 for a in active if a)) if active is not None else 0
-    if na:
-        J, Js = _batch.alloc_out(n, (6, na), layout, dt, dev)
+    T = _batch.alloc_view(n, (4, 4), layout, dt, dev) if want_T else None
+    J = _batch.alloc_view(n, (6, na), layout, dt, dev) if na else None
     fn = _lib.load().rk_chain_fk_jac_f64 if dt == torch.float64 else _lib.load().rk_chain_fk_jac_f32
-    launch(fn, dev, C.byref(ch), _lib.ptr(vs), nvals, n, ld, _batch.flags_of(layout), _lib.ptr(Ts),
-           _lib.ptr(Js))
+    launch(fn, dev, C.byref(ch), _lib.ptr(vs), nvals, n, ld, _batch.flags_of(layout), _lib.ptr(T),
+           _lib.ptr(J))
     if active is None:
         return T
     return T, J

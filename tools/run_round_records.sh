@@ -32,7 +32,7 @@ cap f32fused fanuc_fk_jac_ik8 3 "--dtype f32 --batch 8388608" 8388608
 cap ik_f32 fanuc_ik8_pose 3 "--workload ik --dtype f32 --batch 8388608" 8388608
 cap calib calib_normal 3 "--workload calib --batch 8388608" 8388608 keep
 cap traj traj_kernel 3 "--workload traj --batch 32768" 32768000
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'arm_|rk_chain_jit|chain_kernel|traj_kernel|trap_|poly5|calib_' -o gpurun_out/${R}_rows -f python tools/bench_rows.py --warmup 0 --reps 1 --scale 0.25 > gpurun_out/${R}_ncu_rows.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'arm_|rk_chain_jit|chain_kernel|traj_kernel|trap_|poly5|calib_|fanuc_dq' -o gpurun_out/${R}_rows -f python tools/bench_rows.py --warmup 0 --reps 1 --scale 0.25 > gpurun_out/${R}_ncu_rows.log 2>&1
 tail -n 1 gpurun_out/${R}_ncu_rows.log
 python tools/ncu_summary.py gpurun_out/${R}_rows.ncu-rep gpurun_out/${R}_rows.json:0.25 > gpurun_out/${R}_rows_ncu_full_summary.json
 rm -f gpurun_out/${R}_rows.ncu-rep
@@ -43,3 +43,4 @@ import sys; sys.path.insert(0, '.')
 import bench_workloads as W; print(W.fp64_probe())" > gpurun_out/${R}_ncu_dfma.log 2>&1
 python tools/ncu_summary.py gpurun_out/${R}_dfma.ncu-rep > gpurun_out/${R}_dfma_ncu_full_summary.json; rm -f gpurun_out/${R}_dfma.ncu-rep
 du -sh gpurun_out
+# python tools/collect_records.py $R   # (here, after the call: copies the records into profiles/, derives the launch and SASS digests)
