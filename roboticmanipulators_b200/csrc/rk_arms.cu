@@ -52,6 +52,49 @@ arm_fk_jac_kernel(const __grid_constant__ ArmPT<S> P, const S* __restrict__ q, i
   }
 }
 
+// FP32 planes, two neighbouring poses per thread: 8-byte accesses (a 4-byte plane access is 128 B per
+// warp request -- the one-pose kernel sat at 0.80 of HBM with `lg_throttle` 3.7 and long_scoreboard
+// 16 cycles per issue), next trip's joints in flight while this one computes.  n and ld even,
+// pointers 8-byte aligned (the launcher checks; the odd tail goes through arm_fk_jac_kernel).
+template <int NQ>
+__global__ void __launch_bounds__(kBlock, 4)
+arm_fk_jac_soa2_kernel(const __grid_constant__ ArmPT<float> P, const float* __restrict__ q, int64_t n,
+                       int64_t ld, float* __restrict__ T, float* __restrict__ J) {
+  constexpr int NJ = 6 * NQ;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 2;
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  float2 qn[NQ];
+#pragma unroll
+  for (int k = 0; k < NQ; ++k)
+    qn[k] = (i < n) ? __ldcs(reinterpret_cast<const float2*>(q + k * ld + i)) : make_float2(0.f, 0.f);
+  for (; i < n; i += stride) {
+    float qa[NQ], qb[NQ];
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) qa[k] = qn[k].x, qb[k] = qn[k].y;
+    const int64_t in = i + stride;
+    if (in < n) {
+#pragma unroll
+      for (int k = 0; k < NQ; ++k) qn[k] = __ldcs(reinterpret_cast<const float2*>(q + k * ld + in));
+    }
+    float Ta[16], Ja[NJ], Tb[16], Jb[NJ];
+    if constexpr (NQ == 3) {
+      rrr_fk_jac_pose(P, qa, Ta, Ja);
+      rrr_fk_jac_pose(P, qb, Tb, Jb);
+    } else {
+      rr_fk_jac_pose(P, qa, Ta, Ja);
+      rr_fk_jac_pose(P, qb, Tb, Jb);
+    }
+    if (T) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) __stcs(reinterpret_cast<float2*>(T + k * ld + i), make_float2(Ta[k], Tb[k]));
+    }
+    if (J) {
+#pragma unroll
+      for (int k = 0; k < NJ; ++k) __stcs(reinterpret_cast<float2*>(J + k * ld + i), make_float2(Ja[k], Jb[k]));
+    }
+  }
+}
+
 struct ArmBranches {
   int8_t mk[2 * 8];
   int nb;
@@ -104,7 +147,19 @@ arm_ik_pose_kernel(const __grid_constant__ ArmPT<S> P, const S* __restrict__ T, 
   constexpr int NB = (NQ == 3) ? 4 : 2;
   const bool full = P.has_base || P.has_tool;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  // software pipeline (identity base / tool, RR arm): the next trip's translation column is in flight
+  // while this trip's atan2 chains run.  Measured per 2^25 targets: RR 0.436 -> 0.415 ms (FP32 0.265
+  // -> 0.237); the RRR arm sits at its 64-register cap and got slower (0.923 -> 0.965), so it loads
+  // in place.
+  constexpr bool PRE = NQ == 2;
+  auto load3 = [&](int64_t at, S (&v)[3]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v[k] = SOA ? __ldcs(T + (4 * k + 3) * ld + at) : T[at * 16 + 4 * k + 3];
+  };
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  S pn[3] = {S(0), S(0), S(0)};
+  if (PRE && !full && i < n) load3(i, pn);
+  for (; i < n; i += stride) {
     S p0[3];
     if (full) {
       S Tin[12];
@@ -112,8 +167,13 @@ arm_ik_pose_kernel(const __grid_constant__ ArmPT<S> P, const S* __restrict__ T, 
       for (int k = 0; k < 12; ++k) Tin[k] = SOA ? __ldcs(T + k * ld + i) : T[i * 16 + k];
       arm_ik_p0(P, Tin, p0);
     } else {
+      if constexpr (PRE) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) p0[k] = SOA ? __ldcs(T + (4 * k + 3) * ld + i) : T[i * 16 + 4 * k + 3];
+        for (int k = 0; k < 3; ++k) p0[k] = pn[k];
+        if (i + stride < n) load3(i + stride, pn);
+      } else {
+        load3(i, p0);
+      }
     }
     S qo[NB][NQ];
     bool ok[NB];
@@ -152,6 +212,20 @@ static int launch_arm_fk(const RkArm* robot, const S* q, int64_t n, int64_t ld, 
   ArmPT<S> P = make_arm_params_t<S>(robot);
   cudaStream_t st = (cudaStream_t)stream;
   if (soa) {
+    if constexpr (sizeof(S) == 4) {
+      const bool pairs = n >= 2 && ld % 2 == 0 && (((uintptr_t)q | (uintptr_t)T | (uintptr_t)J) & 7) == 0;
+      if (pairs) {
+        const int64_t n2 = n & ~(int64_t)1;
+        int grid = stream_grid(arm_fk_jac_soa2_kernel<NQ>, kBlock, 0, n2 / 2);
+        arm_fk_jac_soa2_kernel<NQ><<<grid, kBlock, 0, st>>>(P, q, n2, ld, T, J);
+        if (n2 < n)  // odd tail: one pose
+          arm_fk_jac_kernel<S, NQ, true><<<1, kBlock, 0, st>>>(P, q + n2, 1, ld, T ? T + n2 : nullptr,
+                                                               J ? J + n2 : nullptr);
+        return check_launch();
+      }
+    }
+    // (a prefetching one-pose SOA kernel measured slower in FP64: 1.596 -> 1.625 ms per 2^25, 124
+    // registers; the shared kernel stays)
     int grid = stream_grid(arm_fk_jac_kernel<S, NQ, true>, kBlock, 0, n);
     arm_fk_jac_kernel<S, NQ, true><<<grid, kBlock, 0, st>>>(P, q, n, ld, T, J);
   } else {

@@ -1063,7 +1063,7 @@ calib_tool_base_stats_kernel(const __grid_constant__ CalibP P, const double* __r
 
 // evaluate (model_calibration.py:480-505): sums of squares and maxima of the residuals
 template <class SHAPE>
-__global__ void __launch_bounds__(kMeas)
+__global__ void __launch_bounds__(kMeas, 4)
 calib_eval_kernel(const __grid_constant__ CalibP P, const double* __restrict__ q,
                   const double* __restrict__ pts, int64_t m, double* __restrict__ partial,
                   unsigned int* __restrict__ counter, double* __restrict__ out) {

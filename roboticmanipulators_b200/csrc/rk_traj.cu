@@ -244,9 +244,21 @@ trap_coefficients_kernel(const double* __restrict__ q0, const double* __restrict
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   if (VEC2) {
     const int64_t pairs = n >> 1;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
-      const double2 a = __ldcs(reinterpret_cast<const double2*>(q0) + i);
-      const double2 b = __ldcs(reinterpret_cast<const double2*>(qf) + i);
+    // software pipeline: the next trip's operands are in flight while this trip's square roots and
+    // divisions run (ncu: long_scoreboard was the top stall, 6.8 cycles per issue)
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double2 an = make_double2(0.0, 0.0), bn = an;
+    if (i < pairs) {
+      an = __ldcs(reinterpret_cast<const double2*>(q0) + i);
+      bn = __ldcs(reinterpret_cast<const double2*>(qf) + i);
+    }
+    for (; i < pairs; i += stride) {
+      const double2 a = an, b = bn;
+      const int64_t in = i + stride;
+      if (in < pairs) {
+        an = __ldcs(reinterpret_cast<const double2*>(q0) + in);
+        bn = __ldcs(reinterpret_cast<const double2*>(qf) + in);
+      }
       double2 o1, o2;
       trap_coefficients(a.x, b.x, vmax, amax, freq, o1.x, o2.x);
       trap_coefficients(a.y, b.y, vmax, amax, freq, o1.y, o2.y);

@@ -1,0 +1,33 @@
+"""The example scripts (batched counterparts of the reference's fanuc_kinematics.py,
+fanuc_calibration.py and rrr_robot_planning.py) run end to end and report sane numbers."""
+import os
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "examples"))
+
+
+def test_fanuc_kinematics_example():
+    import fanuc_kinematics_batch as ex
+    out = ex.main(20000, verbose=False)
+    assert out["max_roundtrip_error_mm"] < 1e-6
+    assert 0.60 < out["original_q_recovered"] < 0.66   # as the reference's own IK (see the example's header)
+    assert 2.0 < out["valid_solutions_per_pose"] <= 8.0
+
+
+def test_fanuc_calibration_example():
+    import fanuc_calibration_gpu as ex
+    hist = ex.main(None, 1, refine=False, verbose=False)
+    assert abs(hist[0]["distance_rms"] - 13.1540215624739) < 1e-9      # README.md:103 of the reference
+    assert abs(hist[1]["distance_rms"] - 0.531528594785394) < 1e-8     # docs/GeometricCalibration.md:51
+
+
+def test_rrr_planning_example():
+    import rrr_planning_batch as ex
+    out = ex.main(512, 50, verbose=False)
+    assert out["p2p_goal_error"] < 0.2                 # the last sample is one control period short of q_f
+    assert out["lin_tracking_error"] < 1e-9
+    assert out["lin_ik_success"] > 0.9

@@ -367,3 +367,39 @@ def test_chain_dq_specialised_kernel_matches_interpreter(tmp_path):
             scale = np.maximum(1.0, np.abs(b).max(axis=1, keepdims=True))
             assert np.median(np.abs(a - b) / scale) < 1e-14
             assert np.quantile(np.abs(a - b) / scale, 0.99) < 1e-9      # ill-conditioned samples amplify rounding
+
+
+@pytest.mark.parametrize("nq", [3, 2])
+def test_fp32_arm_fk_two_poses_per_thread_canaries(nq):
+    """rk_rrr_fk_jac_f32 / rk_rr_fk_jac_f32 over SOA planes take two poses per thread (8-byte
+    accesses) when n >= 2 and ld is even, one pose per thread otherwise; odd n finishes with a
+    one-pose launch.  Every size / pitch combination must equal the pose-major call bit for bit and
+    leave the padding and the guards untouched."""
+    import ctypes as C
+    from roboticmanipulators_b200 import _lib
+    from roboticmanipulators_b200.robots import RRRRobot, RRRobot
+    lib = _lib.load()
+    robot = RRRRobot() if nq == 3 else RRRobot()
+    fn = lib.rk_rrr_fk_jac_f32 if nq == 3 else lib.rk_rr_fk_jac_f32
+    st = robot._cached_struct()
+    rng = np.random.default_rng(31)
+    CAN, G, f32 = 4321.0, 64, torch.float32
+    for n, pad in ((1, 0), (1, 1), (2, 0), (3, 1), (3, 2), (64, 0), (65, 1), (65, 0), (4097, 3), (4098, 6), (100001, 1)):
+        q = torch.tensor(rng.uniform(-3, 3, size=(n, nq)), device="cuda", dtype=f32)
+        T_ref, J_ref = robot.forward_kinematics_batch(q, jacobian=True, layout="aos")
+        ld = n + pad
+        qs = torch.full((nq, ld), CAN, dtype=f32, device="cuda")
+        qs[:, :n] = q.t()
+        bufs = {}
+        for name, ncomp in (("T", 16), ("J", 6 * nq)):
+            buf = torch.full((G + ncomp * ld + G,), CAN, dtype=f32, device="cuda")
+            bufs[name] = (buf, buf[G:G + ncomp * ld], ncomp)
+        _lib.check(fn(st, _lib.ptr(qs), n, ld, _lib.RK_SOA, _lib.ptr(bufs["T"][1]), _lib.ptr(bufs["J"][1]),
+                      _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        for name, ref in (("T", T_ref.reshape(n, 16)), ("J", J_ref.reshape(n, 6 * nq))):
+            buf, view, ncomp = bufs[name]
+            assert bool((buf[:G] == CAN).all()) and bool((buf[-G:] == CAN).all()), (n, pad, name)
+            planes = view.view(ncomp, ld)
+            assert bool((planes[:, n:] == CAN).all()), (n, pad, name)
+            assert torch.equal(planes[:, :n].t(), ref), (n, pad, name)

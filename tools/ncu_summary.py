@@ -43,9 +43,9 @@ ROW_KERNELS = [
     ("chain_fk_fanuc_seq_soa", "rk_chain_jit", 1),
     ("chain_fk_jac_fanuc_seq_soa_f32", "rk_chain_jit", 2),
     ("chain_fk_fanuc_seq_soa_f32", "rk_chain_jit", 3),
-    ("rrr_fk_jac_soa_f32", "arm_fk_jac_kernel<float, 3, 1>", 0),
+    ("rrr_fk_jac_soa_f32", "arm_fk_jac_soa2_kernel<3>", 0),
     ("rrr_ik4_soa_f32", "arm_ik_pose_kernel<float, 3, 1>", 0),
-    ("rr_fk_jac_soa_f32", "arm_fk_jac_kernel<float, 2, 1>", 0),
+    ("rr_fk_jac_soa_f32", "arm_fk_jac_soa2_kernel<2>", 0),
     ("rr_ik2_soa_f32", "arm_ik_pose_kernel<float, 2, 1>", 0),
     ("chain_dq_from_dx_6x6", "rk_chain_jit", 4),
     ("fanuc_dq_from_dx", "fanuc_dq_from_dx_kernel<double", 0),
