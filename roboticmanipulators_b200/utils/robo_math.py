@@ -237,21 +237,22 @@ class Transformation(_Getters):
 
     @staticmethod
     def get_angles(R):
-        """Euler extraction (robo_math.py:448-464)."""
-        if R[2, 0] != 1:
-            z = np.arctan2(R[2, 1], R[2, 2])
-            x = np.arctan2(R[1, 0], R[0, 0])
-            if R[2, 2] != 0:
-                y = np.arctan2(R[2, 0], R[2, 2] / np.cos(z))
-            elif R[1, 1] != 0:
-                y = np.arctan2(-np.cos(x) * R[2, 0], R[0, 0])
-            elif R[1, 0] != 0:
-                y = np.arctan2(-np.sin(x) * R[2, 0], R[1, 0])
-        else:
-            y = np.arcsin(R[2, 0])
-            x = 0
-            z = np.arctan2(R[0, 1], R[0, 2])
-        return x, y, z
+        """Angles (x, y, z) read off a rotation block with the reference's case split
+        (robo_math.py:448-464): R[2,0] == 1 is its gimbal case (x := 0); otherwise y comes from the
+        first non-zero of R[2,2], R[1,1], R[1,0], and -- as there -- stays unbound when all three
+        vanish."""
+        r20 = R[2, 0]
+        if r20 == 1:
+            return 0, np.arcsin(r20), np.arctan2(R[0, 1], R[0, 2])
+        about_z = np.arctan2(R[2, 1], R[2, 2])
+        about_x = np.arctan2(R[1, 0], R[0, 0])
+        cases = ((R[2, 2], lambda: np.arctan2(r20, R[2, 2] / np.cos(about_z))),
+                 (R[1, 1], lambda: np.arctan2(-np.cos(about_x) * r20, R[0, 0])),
+                 (R[1, 0], lambda: np.arctan2(-np.sin(about_x) * r20, R[1, 0])))
+        for pivot, about_y in cases:
+            if pivot != 0:
+                return about_x, about_y(), about_z
+        raise UnboundLocalError("cannot access local variable 'y' where it is not associated with a value")
 
     @staticmethod
     def get_Rx_from_degrees(q):

@@ -235,3 +235,30 @@ def test_chain_specialiser_source_compiles_for_sm100a(tmp_path):
                 assert r.returncode == 0, r.stderr[-2000:]
                 if want & 4:
                     assert b"LD2(" in buf.value and b"ST2(" in buf.value
+
+
+def test_get_angles_matches_reference_values():
+    """Transformation.get_angles (robo_math.py:448-464): expected values produced by the reference
+    itself for generic rotations, its gimbal branch (R[2,0] == 1), the R[2,2] == 0 fall-backs, and
+    its unbound-y corner, which raises there and here."""
+    cases = [
+        ([[0.705957417269, -0.702419831123, -0.090722135383], [-0.192210119246, -0.313293905934, 0.930001182023], [-0.681673965369, -0.639103520058, -0.35618435618]],
+         [-0.2658251885952269, -0.7500481162640394, -2.0792411469299323]),
+        ([[-0.229094160879, 0.949412986178, 0.21478092822], [-0.936789830762, -0.274990703048, 0.216344461953], [0.264463000118, -0.151641336426, 0.95239919501]],
+         [-1.8106412608984057, 0.2676470545929161, -0.15789498403708382]),
+        ([[0.941832710923, 0.27957662208, -0.186515567772], [0.174901709248, 0.066162037069, 0.982360410925], [0.286985255261, -0.95784106053, 0.013415141665]],
+         [0.18361198051204158, 0.29107821881298124, -1.556791639416813]),
+        ([[0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [1.0, 0.0, 0.0]],
+         [0.0, 1.5707963267948966, 1.5707963267948966]),
+        ([[0.0, -1.0, 0.0], [0.6, 0.0, -0.8], [0.8, 0.0, 0.6]],
+         [1.5707963267948966, 0.9272952180016123, 0.0]),
+        ([[0.6, 0.0, -0.8], [0.0, 1.0, 0.0], [0.8, 0.0, 0.6]],
+         [0.0, 0.9272952180016123, 0.0]),
+        ([[0.8, 0.0, 0.6], [0.6, 0.0, -0.8], [0.0, 1.0, 0.0]],
+         [0.6435011087932844, -0.0, 1.5707963267948966]),
+    ]
+    for R, want in cases:
+        got = tf.get_angles(np.array(R))
+        assert np.allclose([float(v) for v in got], want, rtol=0, atol=1e-15), (R, got, want)
+    with pytest.raises(UnboundLocalError):
+        tf.get_angles(np.array([[0.6, -0.8, 0.0], [0.0, 0.0, -1.0], [0.8, 0.6, 0.0]]))
