@@ -1402,7 +1402,9 @@ static int launch_fk_jac_ik8(const RkFanuc* robot, const S* q, int64_t n, int64_
       // One group per CTA: this kernel is 94 % writes (109 planes) and runs fastest with short-lived
       // CTAs -- ms per 2^26 poses by groups per CTA: 1: 8.99, 2: 9.36, 4: 9.55, 8: 9.66 (the opposite
       // of the read-heavier IK kernel above); 3 or 5 CTAs per SM instead of 4 and padded plane
-      // strides were also measured and are no better.
+      // strides were also measured and are no better.  Round 2, with the two-buffer tile pipeline:
+      // groups per CTA 1: 9.19 - 9.23, 2: 9.44, 3: 9.62, 4: 9.64 ms; CTA size 32: 9.57, 64: 9.58,
+      // 128: 9.14 - 9.20, 256: 9.36 - 9.39 ms (same box, 1965 MHz).
       const TileGrid tg = tile_grid(kern, smem, ntiles, 1);
       kern<<<tg.grid, kBlock, smem, (cudaStream_t)stream>>>(P, tmq, T, J, det, q_out, valid, n, ld, ntiles,
                                                             tg.chunk);
