@@ -166,14 +166,16 @@ std::string subst(const std::string& text, const char* suffix) {
   return out;
 }
 
-// resident CTAs per SM the register allocation is held to (RK_CHAIN_MINB, tuning knob)
-int min_blocks() {
-  static const int v = [] {
+// resident CTAs per SM the register allocation is held to (RK_CHAIN_MINB overrides).  Measured on the
+// Fanuc sequence, 2^24 samples: the walks are fastest uncapped (T + J 1.41 / 1.42 / 1.45 / 1.48 ms at
+// 1 / 3 / 4 / 5), the dq solve at 4 (0.885 uncapped, 0.881 / 0.819 / 0.951 ms at 3 / 4 / 5).
+int min_blocks(bool solve) {
+  static const int env = [] {
     const char* e = getenv("RK_CHAIN_MINB");
-    const int m = e ? atoi(e) : 1;  // measured best: no cap (126 / 92 registers for the Fanuc chain)
-    return m < 1 ? 1 : (m > 16 ? 16 : m);
+    const int m = e ? atoi(e) : 0;
+    return m < 0 ? 0 : (m > 16 ? 16 : m);
   }();
-  return v;
+  return env ? env : (solve ? 4 : 1);
 }
 
 template <typename S>
@@ -187,7 +189,7 @@ std::string generate(const ChainProg<S>& Pg, bool soa, bool wantT, bool wantJ, b
   const std::string per = vec2 ? "256" : "128";   // samples per CTA and trip
   src += "struct Consts { S X[" + num(kMaxConst) + "][12]; S Tb[12]; S Tt[12]; };\n";
   src +=
-      "extern \"C\" __global__ void __launch_bounds__(128, " + num(min_blocks()) + ") rk_chain_jit(const S* __restrict__ values, int nvals,\n"
+      "extern \"C\" __global__ void __launch_bounds__(128, " + num(min_blocks(solve)) + ") rk_chain_jit(const S* __restrict__ values, int nvals,\n"
       "    long long n, long long ld, S* __restrict__ T, S* __restrict__ J, const Consts C,\n"
       "    const S* __restrict__ dx, S* __restrict__ dq, unsigned char* __restrict__ ok) {\n"
       "  const long long stride = (long long)gridDim.x * " + per + ";\n"

@@ -598,6 +598,23 @@ __device__ __forceinline__ void warp_store_aos_ilp(S* stage, const S (&v)[NC], S
   for (int c = 0; c < NC; ++c) stage[lane * ST + c] = v[c];
   __syncwarp();
   const int total = n_items * NC;
+  if constexpr (sizeof(S) == 4 && NC % 2 == 0) {
+    // FP32 runs: a 4-byte element per lane is 128 B per store instruction; with a full tile and an
+    // 8-byte aligned run every lane writes element PAIRS (rrr_p2p_fk_f32: LSU data pipe 54 %)
+    if (n_items == kWarp && (reinterpret_cast<uintptr_t>(g_warp_base) & 7) == 0) {
+      float2 tmp2[NC / 2];
+#pragma unroll
+      for (int k = 0; k < NC / 2; ++k) {
+        const int idx = 2 * (lane + k * kWarp);
+        const int item = idx / NC, c = idx - item * NC;  // NC even: the pair stays inside one item
+        tmp2[k] = make_float2(stage[item * ST + c], stage[item * ST + c + 1]);
+      }
+#pragma unroll
+      for (int k = 0; k < NC / 2; ++k)
+        reinterpret_cast<float2*>(g_warp_base)[lane + k * kWarp] = tmp2[k];
+      return;
+    }
+  }
   constexpr int CH = NC < 8 ? NC : 8;
 #pragma unroll
   for (int k0 = 0; k0 < NC; k0 += CH) {

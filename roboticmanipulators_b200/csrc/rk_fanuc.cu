@@ -1161,7 +1161,7 @@ fanuc_ik_list_kernel(const __grid_constant__ FanucP<S> P, const __grid_constant_
 // dq = J(q)^-1 dx with the 6x6 Jacobian of K1 (the twist dx = [v; omega]); the Jacobian never
 // leaves the registers, the system is solved in place with partial pivoting.
 template <typename S, bool SOA>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 5)
 fanuc_dq_from_dx_kernel(const __grid_constant__ FanucP<S> P, const S* __restrict__ q, const S* __restrict__ dx,
                         int64_t n, int64_t ld, S* __restrict__ dq, uint8_t* __restrict__ ok) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;

@@ -144,7 +144,7 @@ __device__ __forceinline__ Equalized<NJ> equalize(const double* __restrict__ q0,
 // coefficients, sample counts, sample times, q / dq / ddq -- is always evaluated in FP64 in the
 // reference's operation order (counts must be bit-exact), and rounded to SO on the way out.
 template <int NJ, int MODE, typename SO>
-__global__ void __launch_bounds__(kBlock, MODE == 2 ? 5 : (MODE == 1 ? 2 : 3))
+__global__ void __launch_bounds__(kBlock, MODE == 2 ? 5 : (MODE == 1 ? (sizeof(SO) == 4 ? 4 : 2) : 3))
 traj_kernel(const __grid_constant__ ArmPT<SO> P, const double* __restrict__ q0, const double* __restrict__ qf,
             int64_t ntraj, int nsteps, double vmax, double amax, double freq, SO* __restrict__ q,
             SO* __restrict__ dq, SO* __restrict__ ddq, SO* __restrict__ t,
