@@ -311,7 +311,7 @@ class FanucWorkload:
             return round(float(np.median(ts)) * 1e6, 1)
         out["scalar_forward_kinematics"] = median_us(lambda: self.robot.forward_kinematics([0.1] * 6, plot=False))
         T = self.robot.forward_kinematics([0.1] * 6, plot=False)
-        out["scalar_inverse_kinematics"] = median_us(lambda: self.robot.inverse_kinematics(T, m=1))
+        out["scalar_inverse_kinematics"] = median_us(lambda: self.robot.inverse_kinematics(T, m=-1, k=1, w=1))
         return out
 
     def cpu(self, args):
