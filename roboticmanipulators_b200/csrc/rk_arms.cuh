@@ -228,8 +228,10 @@ __device__ __forceinline__ bool rrr_ik11_trig(const ArmPT<S>& P, const S (&p0)[3
   return ok;
 }
 
-// The canonical 4 branches (m outer, k inner) of one target in one thread: atan2(y, x) once,
-// acos / beta / gamma once per k (beta is odd in m) -- 7 atan2 instead of 16.
+// The canonical 4 branches (m outer, k inner) of one target in one thread: atan2(y, x) once; k only
+// flips the sign of x' = k r_xy, which enters cos(q2) through x'^2 -- (-x)^2 == x^2 bit for bit -- so
+// acos and beta are shared by both k as well (beta is odd in m) and only gamma = atan2(z', +-r_xy) is
+// taken twice: 5 atan2 per target instead of 16 (7 before the k = -1 pass reused the k = +1 values).
 template <typename S>
 __device__ __forceinline__ void rrr_ik4_pose(const ArmPT<S>& P, const S (&p0)[3], S (&qo)[4][3],
                                              bool (&ok)[4]) {
@@ -237,9 +239,13 @@ __device__ __forceinline__ void rrr_ik4_pose(const ArmPT<S>& P, const S (&p0)[3]
   const S x = p0[0], y = p0[1];
   const S rxy = M::sqrt(M::add(M::mul(x, x), M::mul(y, y)));
   const S q0 = M::atan2_fast(y, x);
+  RrrK<S> r = rrr_ik_k(P, p0, rxy, 1);
 #pragma unroll
   for (int ki = 0; ki < 2; ++ki) {
-    const RrrK<S> r = rrr_ik_k(P, p0, rxy, ki ? -1 : 1);
+    if (ki) {  // k = -1: the same triangle seen from x' = -r_xy
+      r.xp = -rxy;                                                               // :162
+      r.gamma = M::atan2_fast(r.zp, r.xp);                                       // :179
+    }
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi) ok[mi * 2 + ki] = rrr_ik_finish(P, r, q0, mi ? -1 : 1, qo[mi * 2 + ki]);
   }
