@@ -1,2 +1,7 @@
-python -m pytest tests/test_r2_gpu.py tests/test_arms_chain_gpu.py tests/test_traj_gpu.py -m gpu -x -q 2>&1 | tail -3
-python tools/bench_rows.py > gpurun_out/rows_new.json 2> gpurun_out/rows_new.err; tail -3 gpurun_out/rows_new.err
+R=r02
+python -m pytest tests -m gpu -q > gpurun_out/${R}_pytest.log 2>&1; tail -n 3 gpurun_out/${R}_pytest.log
+python tools/bench_rows.py > gpurun_out/${R}_rows.json 2> gpurun_out/${R}_rows.err
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'arm_|rk_chain_jit|chain_kernel|traj_kernel|trap_|poly5|calib_|fanuc_dq' -o gpurun_out/${R}_rows -f python tools/bench_rows.py --warmup 0 --reps 1 --scale 0.25 > gpurun_out/${R}_ncu_rows.log 2>&1
+tail -n 1 gpurun_out/${R}_ncu_rows.log
+python tools/ncu_summary.py gpurun_out/${R}_rows.ncu-rep gpurun_out/${R}_rows.json:0.25 > gpurun_out/${R}_rows_ncu_full_summary.json
+rm -f gpurun_out/${R}_rows.ncu-rep
