@@ -319,3 +319,67 @@ def test_host_stream_matches_device_batch(dtype):
             assert np.max(np.abs(d) / scale) < (1e-9 if dtype == torch.float64 else 2e-3), (n, chunk, name)
     with pytest.raises(Exception):
         robot.fk_jac_ik_stream(q.cuda())
+
+
+def test_concurrent_host_threads_and_streams():
+    """Four host threads, each on its own CUDA stream, call the library at the same time (Fanuc fused
+    call, a generic chain -- first use compiles its kernel under the cache lock --, the calibration
+    evaluation with its per-(device, stream) workspace); every thread must get the serial answers."""
+    import threading
+    from roboticmanipulators_b200.robots.fanuc import Fanuc165F
+    from roboticmanipulators_b200.utils.jacobians import JacobianCalculator
+    rng = np.random.default_rng(41)
+    c = O.FanucConst()
+    robot = Fanuc165F()
+    n = 30000
+    qs = [torch.tensor(rng.uniform(c.lim[:, 0], c.lim[:, 1], size=(n, 6)), device="cuda") for _ in range(4)]
+    seq, ind = "RzTyRxTzRyTx", [1, 0, 1, 1, 1, 0]          # a structure no other test has compiled yet
+    vals = [torch.tensor(rng.uniform(-2, 2, size=(n, 6)), device="cuda") for _ in range(4)]
+    # one calibrator shared by all threads: its workspace (ticket counter + CTA partials) is per stream
+    from test_host_logic_cpu import fanuc_calibrator
+    from test_oracle_golden import T_BASE_0, T_TOOLS_0
+    mc = fanuc_calibrator()
+    mc.get_reduced_model()
+    m = 200000
+    cq = [torch.tensor(rng.uniform(-1.0, 1.0, size=(m, 6)), device="cuda") for _ in range(4)]
+    cp = [torch.tensor(rng.uniform(-1500, 1500, size=(m, 9)), device="cuda") for _ in range(4)]
+    serial = []
+    for k in range(4):
+        sums = mc.residual_sums(cq[k], cp[k], T_BASE_0, T_TOOLS_0, process_group=False)
+        serial.append((robot.fk_jac_ik_batch(qs[k]), sums.clone()))
+    torch.cuda.synchronize()
+    results, errors = [None] * 4, []
+
+    def work(k):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                out = None
+                for _ in range(5):
+                    out = robot.fk_jac_ik_batch(qs[k])
+                jc = JacobianCalculator(seq, ind)
+                T, J = jc.calculate_numerically_batch(vals[k], with_pose=True)
+                dq, ok = jc.dq_from_dx_batch(vals[k], vals[k][:, :4], rows=(0, 1, 2, 4))
+                sums = None
+                for _ in range(5):
+                    sums = mc.residual_sums(cq[k], cp[k], T_BASE_0, T_TOOLS_0, process_group=False).clone()
+            st.synchronize()
+            results[k] = (out, (T, J, dq, ok), sums)
+        except Exception as e:                               # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for k in range(4):
+        for a, b in zip(results[k][0], serial[k][0]):
+            assert torch.equal(a, b)
+        jc = JacobianCalculator(seq, ind)
+        T, J = jc.calculate_numerically_batch(vals[k], with_pose=True)
+        dq, ok = jc.dq_from_dx_batch(vals[k], vals[k][:, :4], rows=(0, 1, 2, 4))
+        for a, b in zip(results[k][1], (T, J, dq, ok)):
+            assert torch.equal(a, b)
+        assert torch.equal(results[k][2], serial[k][1])
