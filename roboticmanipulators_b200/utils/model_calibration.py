@@ -204,6 +204,16 @@ class ModelCalibrator(object):
         if parameters is None:
             parameters = self._parameters
         pvals = self._nominal_values(parameters)
+        Tb = np.eye(4) if T_base is None else np.array(T_base, dtype=np.float64)
+        tools = [np.eye(4)] if not T_tools else [np.array(t, dtype=np.float64) for t in T_tools]
+        # the same linearisation point again (evaluate after estimate, repeated evaluations): the
+        # ~0.2 ms token walk below is skipped; the key holds every number the struct is built from
+        key = (tuple(pvals), Tb.tobytes(), tuple(t.tobytes() for t in tools),
+               np.asarray(self.qs_directions, dtype=np.float64).tobytes(),
+               np.asarray(self.qs_offsets, dtype=np.float64).tobytes(), tuple(self._r_tokens), tuple(self._r_j_ind))
+        cached = getattr(self, "_compiled", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
         m = _lib.RkCalibModel()
         toks, jind = self._r_tokens, self._r_j_ind
         if not jind or jind[0] != 1:
@@ -232,14 +242,13 @@ class ModelCalibrator(object):
                 X = X @ elementary_np(tok, pvals[p])
                 p += 1
         _lib.fill(m.seg[j], _lib.xf12(X))
-        Tb = np.eye(4) if T_base is None else np.array(T_base, dtype=np.float64)
         _lib.fill(m.T_base, _lib.xf12(Tb))
-        tools = [np.eye(4)] if not T_tools else [np.array(t, dtype=np.float64) for t in T_tools]
         if len(tools) > _lib.RK_CALIB_MAX_TOOLS:
             raise ValueError("too many tools")
         m.ntools = len(tools)
         for t, Tt in enumerate(tools):
             _lib.fill(m.tool_p[t], Tt[:3, 3])
+        self._compiled = (key, m)
         return m
 
     def _device_data(self, qs, pts, ntools=None):
