@@ -1,3 +1,6 @@
+# Partial refresh of the round records (run on a GPU box): the GPU test-suite, tools/bench_rows.py and
+# its ncu pass -- the part of tools/run_round_records.sh that the non-headline kernels need.
+#   gpurun --timeout 1500 -- 'bash tools/run_rows_records.sh'   then   python tools/collect_records.py r02
 R=r02
 python -m pytest tests -m gpu -q > gpurun_out/${R}_pytest.log 2>&1; tail -n 3 gpurun_out/${R}_pytest.log
 python tools/bench_rows.py > gpurun_out/${R}_rows.json 2> gpurun_out/${R}_rows.err
