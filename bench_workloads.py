@@ -262,6 +262,23 @@ class FanucWorkload:
 
         sec_link = timed(lambda: link(full), steps)
         sec_link_ik = timed(lambda: link(("q_ik", "valid")), steps)
+        # BASELINE config 2 end to end: targets on the host -> the 8 canonical IK answers on the host
+        # (Fanuc165F.inverse_kinematics_stream: 128 B up, 392 B down per target), and its link bound
+        hT = torch.empty((n, 4, 4), dtype=dt_t, pin_memory=True)
+        hT.copy_(self.robot.forward_kinematics_batch(hq.cuda(), layout="aos"))
+        ik_out = {"q_ik": outs["q_ik"], "valid": outs["valid"]}
+        sec_iks = timed(lambda: self.robot.inverse_kinematics_stream(hT, out=ik_out), steps)
+        dT = torch.empty((n, 4, 4), dtype=dt_t, device="cuda")
+
+        def link_iks():
+            with torch.cuda.stream(s_up):
+                dT.copy_(hT, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                for k in ("q_ik", "valid"):
+                    outs[k].copy_(douts[k], non_blocking=True)
+            s_up.synchronize(), s_dn.synchronize()
+
+        sec_link_iks = timed(link_iks, steps)
         total = n * steps * world
         return {
             "value": total / sec, "unit": self.unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -275,6 +292,11 @@ class FanucWorkload:
             "selected_outputs": {"want": ["q_ik", "valid"], "value": total / sec_ik,
                                  "d2h_bytes_per_step": n * (48 * esz + 8),
                                  "link_value": total / sec_link_ik, "frac": sec_link_ik / sec_ik},
+            "ik_stream": {"api": "Fanuc165F.inverse_kinematics_stream (rk_fanuc_ik8_host): targets T on the "
+                                 "host in, q_ik + valid on the host out",
+                          "value": total / sec_iks, "unit": "targets/s", "h2d_bytes_per_step": n * 16 * esz,
+                          "d2h_bytes_per_step": n * (48 * esz + 8), "link_value": total / sec_link_iks,
+                          "frac": sec_link_iks / sec_iks},
         }
 
     def latency_us(self):

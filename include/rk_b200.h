@@ -155,6 +155,14 @@ int rk_fanuc_fk_jac_ik8_host_f64(RkHostPipe* pipe, const RkFanuc* robot, const d
 int rk_fanuc_fk_jac_ik8_host_f32(RkHostPipe* pipe, const RkFanuc* robot, const float* q, int64_t n,
                                  int64_t ld, int flags, float* T, float* J, float* det, float* q_out,
                                  uint8_t* valid);
+/* Inverse kinematics only on HOST arrays (BASELINE config 2; reference: one
+ * Fanuc165F.inverse_kinematics call per target and branch, robots/fanuc.py:196-302): targets
+ * T [n][4][4] (RK_SOA: 16 planes of pitch ld) up, the 8 canonical solutions q_out [n][8][6] and
+ * valid [n][8] down, through the same pipe -- 128 B up and 392 B down per target in FP64. */
+int rk_fanuc_ik8_host_f64(RkHostPipe* pipe, const RkFanuc* robot, const double* T, int64_t n, int64_t ld,
+                          int flags, double* q_out, uint8_t* valid);
+int rk_fanuc_ik8_host_f32(RkHostPipe* pipe, const RkFanuc* robot, const float* T, int64_t n, int64_t ld,
+                          int flags, float* q_out, uint8_t* valid);
 
 /* ------------------------------------------------------------------------------------
  * RRRRobot / RRRobot  (reference: robots/rrr_robot.py, robots/rr_robot.py)

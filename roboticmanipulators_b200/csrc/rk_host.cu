@@ -136,6 +136,47 @@ static int run_host(RkHostPipe* h, const RkFanuc* robot, const S* q, int64_t n, 
   return RK_OK;
 }
 
+// Inverse kinematics only (BASELINE config 2: targets in, the 8 canonical solutions out): 128 B up,
+// 392 B down per pose in FP64 -- the same three-stream ring, the slot's T / q_ik / valid areas.
+template <typename S, typename IkFn>
+static int run_host_ik(RkHostPipe* h, const RkFanuc* robot, const S* T, int64_t n, int64_t ld, int flags,
+                       S* q_out, uint8_t* valid, IkFn ikfn) {
+  if (!h || !robot || n < 0) return RK_ERR_INVALID_ARG;
+  if (n == 0) return RK_OK;
+  if (!T || !q_out || !valid) return RK_ERR_INVALID_ARG;
+  const bool soa = (flags & RK_SOA) != 0;
+  if (soa && ld < n) return RK_ERR_INVALID_ARG;
+  int cur = 0;
+  RK_TRY(cudaGetDevice(&cur));
+  if (cur != h->device) return RK_ERR_INVALID_ARG;
+  const int64_t C = h->chunk;
+  RK_TRY(cudaEventRecord(h->ev_t0, h->s_in));
+  int64_t lo = 0;
+  for (int64_t i = 0; lo < n; ++i, lo += C) {
+    const int slot = (int)(i % h->nslots);
+    const int64_t cnt = (n - lo) < C ? (n - lo) : C;
+    SlotView<S> v(h->slab + (size_t)slot * h->slot_bytes, C);
+    if (i >= h->nslots) RK_TRY(cudaStreamWaitEvent(h->s_in, h->ev_k[slot], 0));
+    RK_TRY(copy_chunk<S>(v.T, T, kNT, cnt, lo, ld, C, soa, true, h->s_in));
+    RK_TRY(cudaEventRecord(h->ev_in[slot], h->s_in));
+    RK_TRY(cudaStreamWaitEvent(h->s_k, h->ev_in[slot], 0));
+    if (i >= h->nslots) RK_TRY(cudaStreamWaitEvent(h->s_k, h->ev_out[slot], 0));
+    const int rc = ikfn(robot, v.T, cnt, C, flags, nullptr, 8, v.qik, v.valid, (void*)h->s_k);
+    if (rc != RK_OK) return rc;
+    RK_TRY(cudaEventRecord(h->ev_k[slot], h->s_k));
+    RK_TRY(cudaStreamWaitEvent(h->s_out, h->ev_k[slot], 0));
+    RK_TRY(copy_chunk<S>(q_out, v.qik, kNQ, cnt, lo, ld, C, soa, false, h->s_out));
+    RK_TRY(copy_chunk<uint8_t>(valid, v.valid, kNV, cnt, lo, ld, C, soa, false, h->s_out));
+    RK_TRY(cudaEventRecord(h->ev_out[slot], h->s_out));
+  }
+  RK_TRY(cudaEventRecord(h->ev_t1, h->s_out));
+  RK_TRY(cudaStreamSynchronize(h->s_out));
+  RK_TRY(cudaStreamSynchronize(h->s_k));
+  RK_TRY(cudaStreamSynchronize(h->s_in));
+  cudaEventElapsedTime(&h->last_ms, h->ev_t0, h->ev_t1);
+  return RK_OK;
+}
+
 }  // namespace rk
 
 extern "C" {
@@ -196,6 +237,15 @@ int rk_fanuc_fk_jac_ik8_host_f32(RkHostPipe* pipe, const RkFanuc* robot, const f
                                  int flags, float* T, float* J, float* det, float* q_out, uint8_t* valid) {
   return rk::run_host<float>(pipe, robot, q, n, ld, flags, T, J, det, q_out, valid, rk_fanuc_fk_jac_f32,
                              rk_fanuc_fk_jac_ik8_f32);
+}
+
+int rk_fanuc_ik8_host_f64(RkHostPipe* pipe, const RkFanuc* robot, const double* T, int64_t n, int64_t ld, int flags,
+                          double* q_out, uint8_t* valid) {
+  return rk::run_host_ik<double>(pipe, robot, T, n, ld, flags, q_out, valid, rk_fanuc_ik_f64);
+}
+int rk_fanuc_ik8_host_f32(RkHostPipe* pipe, const RkFanuc* robot, const float* T, int64_t n, int64_t ld, int flags,
+                          float* q_out, uint8_t* valid) {
+  return rk::run_host_ik<float>(pipe, robot, T, n, ld, flags, q_out, valid, rk_fanuc_ik_f32);
 }
 
 }  // extern "C"

@@ -299,6 +299,40 @@ class Fanuc165F(Robot):
                           ptrs["T"], ptrs["J"], ptrs["det"], ptrs["q_ik"], ptrs["valid"]))
         return {k: res[k] for k in want}
 
+    def inverse_kinematics_stream(self, T, *, out=None, chunk=1 << 16, slots=3, device=None):
+        """inverse_kinematics_batch (the 8 canonical branches) on HOST arrays: targets T [N,4,4]
+        (NumPy or CPU torch, float64 / float32; page-locked for full link speed) are streamed
+        through the GPU in chunks on three streams -- 128 B up and 392 B down per target in
+        float64.  `out` may hold preallocated (pinned) "q_ik" [N,8,6] / "valid" [N,8] tensors.
+        Returns (q_ik, valid) host tensors, complete when the call returns."""
+        if isinstance(T, np.ndarray):
+            T = torch.from_numpy(T)
+        if not isinstance(T, torch.Tensor) or T.is_cuda:
+            raise _lib.RkError("inverse_kinematics_stream takes HOST arrays; use inverse_kinematics_batch "
+                               "for CUDA tensors")
+        if T.dtype not in _DTYPES:
+            raise TypeError("T must be float64 or float32")
+        n = T.shape[0]
+        T = T.reshape(n, 16).contiguous()
+        res = {}
+        for name, shape, dt in (("q_ik", (n, 8, 6), T.dtype), ("valid", (n, 8), torch.uint8)):
+            t = None if out is None else out.get(name)
+            if t is not None:
+                if t.dtype == torch.bool:
+                    t = t.view(torch.uint8)
+                if t.dtype != dt or t.is_cuda or tuple(t.shape) != shape or not t.is_contiguous():
+                    raise ValueError(f"out[{name!r}] must be a contiguous host tensor of shape {shape}, {dt}")
+            else:
+                t = torch.empty(shape, dtype=dt, pin_memory=True)
+            res[name] = t
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        pipe = self._host_pipe(dev, int(chunk), int(slots))
+        fn = getattr(_lib.load(), "rk_fanuc_ik8_host_" + _DTYPES[T.dtype])
+        with torch.cuda.device(dev):
+            _lib.check(fn(pipe, self._cached_struct(), C.c_void_p(T.data_ptr()), n, n, _lib.RK_AOS,
+                          C.c_void_p(res["q_ik"].data_ptr()), C.c_void_p(res["valid"].data_ptr())))
+        return res["q_ik"], res["valid"].view(torch.bool)
+
     def _host_pipe(self, dev, chunk, slots):
         """The (device, chunk, slots) staging pipe of this process, created on first use."""
         key = (dev.index, chunk, slots)

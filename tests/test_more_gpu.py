@@ -383,3 +383,30 @@ def test_concurrent_host_threads_and_streams():
         for a, b in zip(results[k][1], (T, J, dq, ok)):
             assert torch.equal(a, b)
         assert torch.equal(results[k][2], serial[k][1])
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_ik_host_stream_matches_device_batch(dtype):
+    """Fanuc165F.inverse_kinematics_stream (rk_fanuc_ik8_host_*): targets on the host, streamed in
+    chunks, give the bits of inverse_kinematics_batch on the device -- ragged sizes, chunk sizes that
+    do not divide n, pinned and pageable inputs, preallocated outputs, unreachable targets."""
+    from roboticmanipulators_b200.robots import Fanuc165F
+    robot, c = Fanuc165F(), O.FanucConst()
+    rng = np.random.default_rng(33)
+    for n, chunk in ((1, 64), (33, 32), (1000, 256), (70001, 1 << 14)):
+        q = torch.tensor(rng.uniform(c.lim[:, 0], c.lim[:, 1], size=(n, 6))).to(dtype)
+        T = robot.forward_kinematics_batch(q.cuda(), layout="aos")
+        T[::7, :3, 3] *= 3.0                                  # mostly out of reach: all-zero answers, valid = 0
+        q_ref, v_ref = robot.inverse_kinematics_batch(T, layout="aos")
+        for hT in (T.cpu().pin_memory(), T.cpu().numpy()):
+            q_ik, valid = robot.inverse_kinematics_stream(hT, chunk=chunk)
+            assert not q_ik.is_cuda and q_ik.shape == (n, 8, 6) and valid.dtype == torch.bool
+            assert torch.equal(q_ik, q_ref.cpu()) and torch.equal(valid, v_ref.cpu()), (n, chunk)
+        outs = {"q_ik": torch.full((n, 8, 6), -5.0, dtype=dtype).pin_memory(),
+                "valid": torch.ones((n, 8), dtype=torch.bool).pin_memory()}
+        q_ik, valid = robot.inverse_kinematics_stream(T.cpu().pin_memory(), out=outs, chunk=chunk)
+        assert q_ik.data_ptr() == outs["q_ik"].data_ptr()
+        assert torch.equal(q_ik, q_ref.cpu()) and torch.equal(valid, v_ref.cpu())
+        assert float(valid[::7].float().mean()) < 0.5 * max(float(valid.float().mean()), 1e-9) or n < 100
+    with pytest.raises(Exception):
+        robot.inverse_kinematics_stream(T)                    # a CUDA tensor is not a host array
