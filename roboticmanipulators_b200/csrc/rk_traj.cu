@@ -179,9 +179,22 @@ traj_kernel(const __grid_constant__ ArmPT<SO> P, const double* __restrict__ q0, 
       SO qo[NJ], dqo[NJ], ddqo[NJ];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) qo[j] = (SO)qv[j], dqo[j] = (SO)dqv[j], ddqo[j] = (SO)ddqv[j];
-      if (q) warp_store_aos_ilp<SO, NJ>(stage, qo, q + s0 * NJ, cnt, lane);
-      if (dq) warp_store_aos_ilp<SO, NJ>(stage, dqo, dq + s0 * NJ, cnt, lane);
-      if (MODE != 2 && ddq) warp_store_aos_ilp<SO, NJ>(stage, ddqo, ddq + s0 * NJ, cnt, lane);
+      if constexpr (MODE == 2) {
+        // 3-wide rows: every lane writes its own 24 bytes (three strided 8-byte stores that the L2
+        // merges into full sectors); the staged transpose costs ~30 instructions per array here and
+        // this kernel is issue-bound: 1.184 -> 1.142 ms per 2^15 x 1000 samples
+        if (lane < cnt) {
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            if (q) q[(s0 + lane) * NJ + j] = qo[j];
+            if (dq) dq[(s0 + lane) * NJ + j] = dqo[j];
+          }
+        }
+      } else {
+        if (q) warp_store_aos_ilp<SO, NJ>(stage, qo, q + s0 * NJ, cnt, lane);
+        if (dq) warp_store_aos_ilp<SO, NJ>(stage, dqo, dq + s0 * NJ, cnt, lane);
+        if (ddq) warp_store_aos_ilp<SO, NJ>(stage, ddqo, ddq + s0 * NJ, cnt, lane);
+      }
       if (t && lane < cnt) t[s0 + lane] = (SO)tout;
       if constexpr (MODE == 1) {
         SO Tv[16], Jv[18];
@@ -224,8 +237,13 @@ traj_kernel(const __grid_constant__ ArmPT<SO> P, const double* __restrict__ q0, 
           jdq[1] = (B0 * dqv[0] + B1 * dqv[1] + B2 * dqv[2]) * inv;
           jdq[2] = (C0 * dqv[0] + C1 * dqv[1] + C2 * dqv[2]) * inv;
         }
-        if (o1) warp_store_aos_ilp<double, 3>(stage, jq, o1 + s0 * 3, cnt, lane);
-        if (o2) warp_store_aos_ilp<double, 3>(stage, jdq, o2 + s0 * 3, cnt, lane);
+        if (lane < cnt) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            if (o1) o1[(s0 + lane) * 3 + j] = jq[j];
+            if (o2) o2[(s0 + lane) * 3 + j] = jdq[j];
+          }
+        }
         if (valid && lane < cnt) valid[s0 + lane] = ok ? 1 : 0;
       }
     }
