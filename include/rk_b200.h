@@ -74,6 +74,14 @@ typedef struct RkFanuc {
   int32_t has_tool;     /* 0: T_tool is the identity                                */
 } RkFanuc;
 
+/* Host-only convenience for callers without the Python layer: fills `out` the way
+ * Fanuc165F.__init__ does (robots/fanuc.py:43-111, robots/robot.py:39-57).  lengths[7],
+ * offsets[6], directions[6]: NULL = the reference's defaults; T_base / T_tool: row-major 4x4
+ * (16 doubles, last row ignored), NULL = identity.  d, dq and the radian limits are computed as
+ * the reference computes them; the inverse transforms are those of the affine part. */
+int rk_fanuc_init(RkFanuc* out, const double* lengths, const double* offsets,
+                  const double* directions, const double* T_base, const double* T_tool);
+
 /* Batched Fanuc165F.forward_kinematics (robots/fanuc.py:151-179) fused with the 6x6
  * geometric Jacobian of JacobianCalculator.calculate_numerically / calculate_scew on
  * the sequence TzRzTzTxRyTxRyTzTxRxRyRxTx (utils/jacobians.py:166-240, driver

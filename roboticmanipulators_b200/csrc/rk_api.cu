@@ -1,4 +1,7 @@
 // Library-level entry points: version, error strings, FP64 peak probe.
+#include <cmath>
+#include <cstring>
+
 #include "rk_common.cuh"
 
 #include <map>
@@ -175,6 +178,65 @@ int rk_probe_atan2(const double* y, const double* x, int64_t n, double* out, voi
   if (!y || !x || !out) return RK_ERR_INVALID_ARG;
   rk::atan2_probe_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(y, x, n, out);
   return rk::check_launch();
+}
+
+// Host-only: the constants of Fanuc165F.__init__ (robots/fanuc.py:43-111) for callers without the
+// Python layer.  NULL selects the reference's defaults.
+static void rk_affine_inverse(const double* T12, double* out12) {
+  const double a = T12[0], b = T12[1], c = T12[2], d = T12[4], e = T12[5], f = T12[6], g = T12[8], h = T12[9],
+               i = T12[10];
+  const double A = e * i - f * h, B = f * g - d * i, Cc = d * h - e * g;
+  const double det = a * A + b * B + c * Cc;
+  const double r = 1.0 / det;
+  const double inv[9] = {A * r,  (c * h - b * i) * r, (b * f - c * e) * r,
+                         B * r,  (a * i - c * g) * r, (c * d - a * f) * r,
+                         Cc * r, (b * g - a * h) * r, (a * e - b * d) * r};
+  for (int rI = 0; rI < 3; ++rI) {
+    for (int cI = 0; cI < 3; ++cI) out12[rI * 4 + cI] = inv[rI * 3 + cI];
+    out12[rI * 4 + 3] = -(inv[rI * 3] * T12[3] + inv[rI * 3 + 1] * T12[7] + inv[rI * 3 + 2] * T12[11]);
+  }
+}
+
+int rk_fanuc_init(RkFanuc* out, const double* lengths, const double* offsets, const double* directions,
+                  const double* T_base, const double* T_tool) {
+  if (!out) return RK_ERR_INVALID_ARG;
+  static const double kLen[7] = {346.0, 324.0, 312.0, 1075.0, 225.0, 1280.0, 215.0};  // fanuc.py:73
+  static const double kHalfPi = 1.5707963267948966;
+  static const double kOff[6] = {0.0, -kHalfPi, kHalfPi, 0.0, 0.0, 0.0};                // :79-80
+  static const double kDir[6] = {1.0, 1.0, -1.0, -1.0, -1.0, -1.0};                     // :86
+  static const double kLimDeg[6][2] = {{-185.0, 185.0}, {-60.0, 76.0},   {-156.0, 156.0},
+                                       {-360.0, 360.0}, {-125.0, 125.0}, {-360.0, 360.0}};  // :36-41
+  memset(out, 0, sizeof(*out));
+  for (int k = 0; k < 7; ++k) out->l[k] = lengths ? lengths[k] : kLen[k];
+  for (int k = 0; k < 6; ++k) {
+    out->offsets[k] = offsets ? offsets[k] : kOff[k];
+    out->directions[k] = directions ? directions[k] : kDir[k];
+    out->lim_lo[k] = kLimDeg[k][0] * (3.141592653589793 / 180.0);  // np.deg2rad (:110-111)
+    out->lim_hi[k] = kLimDeg[k][1] * (3.141592653589793 / 180.0);
+  }
+  const volatile double l4l4 = out->l[4] * out->l[4], l5l5 = out->l[5] * out->l[5];  // no contraction
+  out->d = sqrt(l4l4 + l5l5);                                                         // :98
+  out->dq = atan2(out->l[4], out->l[5]);                                              // :99
+  out->eps = 1e-5;                                                                    // robot.py:17
+  const double kI[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  const double* src[2] = {T_base, T_tool};
+  double* dst[2] = {out->T_base, out->T_tool};
+  double* dsti[2] = {out->T_base_inv, out->T_tool_inv};
+  int32_t* has[2] = {&out->has_base, &out->has_tool};
+  for (int t = 0; t < 2; ++t) {
+    bool ident = true;
+    for (int k = 0; k < 12; ++k) {
+      dst[t][k] = src[t] ? src[t][k] : kI[k];  // the first three rows of the row-major 4x4
+      ident = ident && dst[t][k] == kI[k];
+    }
+    if (ident) {
+      for (int k = 0; k < 12; ++k) dsti[t][k] = kI[k];
+    } else {
+      rk_affine_inverse(dst[t], dsti[t]);
+    }
+    *has[t] = ident ? 0 : 1;
+  }
+  return RK_OK;
 }
 
 }  // extern "C"

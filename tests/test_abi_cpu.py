@@ -106,3 +106,56 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(L, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(L.RkError, match="no CPU fallback"):
         L.load()
+
+
+def test_c_initialiser_matches_the_python_struct():
+    """rk_fanuc_init (plain-C callers) fills RkFanuc exactly like Fanuc165F._struct: byte for byte
+    for the stock robot, and for custom lengths / offsets / directions with base and tool transforms
+    (inverses to rounding: the Python layer uses numpy.linalg.inv)."""
+    import ctypes as C
+    import numpy as np
+    from roboticmanipulators_b200 import _lib
+    from roboticmanipulators_b200.robots.fanuc import Fanuc165F
+    lib = _lib.load()
+    st = _lib.RkFanuc()
+    assert lib.rk_fanuc_init(C.byref(st), None, None, None, None, None) == 0
+    ref = Fanuc165F()._struct()
+    assert bytes(st) == bytes(ref)
+
+    def arr(x):
+        a = np.ascontiguousarray(x, dtype=np.float64)
+        return a, a.ctypes.data_as(C.POINTER(C.c_double))
+    lengths = (300.0, 310.0, 290.0, 1000.0, 200.0, 1300.0, 230.0)
+    offsets = np.array([0.1, -1.4, 1.6, 0.2, -0.1, 0.3])
+    directions = np.array([1.0, -1.0, -1.0, 1.0, -1.0, 1.0])
+    c, s = np.cos(0.3), np.sin(0.3)
+    Tb = np.array([[c, -s, 0, 100.0], [s, c, 0, -50.0], [0, 0, 1, 25.0], [0, 0, 0, 1]])
+    Tt = np.array([[1, 0, 0, 10.0], [0, c, -s, 0.0], [0, s, c, 120.0], [0, 0, 0, 1]])
+    keep = [arr(lengths), arr(offsets), arr(directions), arr(Tb), arr(Tt)]
+    assert lib.rk_fanuc_init(C.byref(st), *[k[1] for k in keep]) == 0
+    ref = Fanuc165F(T_base=Tb, T_tool=Tt, lengths=lengths, offsets=offsets, directions=directions)._struct()
+    for name, _ in _lib.RkFanuc._fields_:
+        a, b = getattr(st, name), getattr(ref, name)
+        a = np.array(a[:]) if hasattr(a, "__len__") else np.array(a)
+        b = np.array(b[:]) if hasattr(b, "__len__") else np.array(b)
+        if name.endswith("_inv"):
+            assert np.allclose(a, b, rtol=1e-14, atol=1e-12), name
+        else:
+            assert np.array_equal(a, b), name
+    assert lib.rk_fanuc_init(None, None, None, None, None, None) != 0
+
+
+def test_c_demo_compiles_against_the_header(tmp_path):
+    """examples/c_abi_demo.c is plain C99 against include/rk_b200.h and links with the library and
+    cudart only (it is run on the GPU box by tests/test_examples_gpu.py)."""
+    import shutil
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if shutil.which("gcc") is None or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime.h")):
+        pytest.skip("gcc / CUDA headers not available")
+    exe = tmp_path / "c_abi_demo"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-I", os.path.join(root, "include"), "-I", os.path.join(cuda, "include"),
+                        os.path.join(root, "examples", "c_abi_demo.c"), "-L", os.path.join(root, "roboticmanipulators_b200"),
+                        "-lrk_b200", "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lm", "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]

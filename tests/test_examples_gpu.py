@@ -31,3 +31,24 @@ def test_rrr_planning_example():
     assert out["p2p_goal_error"] < 0.2                 # the last sample is one control period short of q_f
     assert out["lin_tracking_error"] < 1e-9
     assert out["lin_ik_success"] > 0.9
+
+
+def test_c_abi_demo_runs(tmp_path):
+    """The plain-C program of examples/c_abi_demo.c (rk_fanuc_init + the fused SOA call + the
+    host-array streaming call, no Python, no torch) builds with gcc and passes its own checks."""
+    import shutil
+    import subprocess
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if shutil.which("gcc") is None or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime.h")):
+        pytest.skip("gcc / CUDA headers not available")
+    exe = tmp_path / "c_abi_demo"
+    libdir = os.path.join(ROOT, "roboticmanipulators_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+                        os.path.join(ROOT, "examples", "c_abi_demo.c"), "-L", libdir, "-lrk_b200",
+                        "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lm", "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    env = dict(os.environ, LD_LIBRARY_PATH=libdir + ":" + os.path.join(cuda, "lib64") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([str(exe), "50000"], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    assert "0 differing validity flags" in r.stdout
