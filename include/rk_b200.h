@@ -184,6 +184,12 @@ typedef struct RkArm {
   int32_t has_base, has_tool;
 } RkArm;
 
+/* Host-only: RkArm as RRRRobot() (njoints = 3) / RRRobot() (njoints = 2) build it -- link lengths
+ * (1, 1, 1) / (0.8, 0.8) unless `lengths[njoints]` is given, +-360 degree limits, epsilon 1e-5; T_base / T_tool
+ * row-major 4x4 or NULL = identity. */
+int rk_arm_init(RkArm* out, int njoints, const double* lengths, const double* T_base,
+                const double* T_tool);
+
 /* RRRRobot.forward_kinematics (rrr_robot.py:96-120), chain RzTzRyTxRyTx, + the 6x3
  * Jacobian of rrr_robot_jacobians.py:49-64.  q[n][3] -> T[n][4][4], J[n][6][3]. */
 int rk_rrr_fk_jac_f64(const RkArm* robot, const double* q, int64_t n, int64_t ld, int flags,

@@ -79,6 +79,8 @@ _SIGNATURES = {
     "rk_host_pipe_last_ms": (C.c_float, [_vp]),
     "rk_fanuc_init": (_int, [C.POINTER(RkFanuc), C.POINTER(C.c_double), C.POINTER(C.c_double),
                             C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "rk_arm_init": (_int, [C.POINTER(RkArm), _int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                          C.POINTER(C.c_double)]),
     "rk_fanuc_fk_jac_ik8_host_f64": (_int, [_vp, C.POINTER(RkFanuc), _vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp]),
     "rk_fanuc_fk_jac_ik8_host_f32": (_int, [_vp, C.POINTER(RkFanuc), _vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp]),
     "rk_fanuc_ik8_host_f64": (_int, [_vp, C.POINTER(RkFanuc), _vp, _i64, _i64, _int, _vp, _vp]),

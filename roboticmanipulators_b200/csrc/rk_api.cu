@@ -239,4 +239,36 @@ int rk_fanuc_init(RkFanuc* out, const double* lengths, const double* offsets, co
   return RK_OK;
 }
 
+// The same for the RRR (njoints = 3, rrr_robot.py:36-39) and RR (njoints = 2, rr_robot.py:36,61-65) arms:
+// link lengths (1, 1, 1) / (0.8, 0.8) unless given, +-360 degree limits.
+int rk_arm_init(RkArm* out, int njoints, const double* lengths, const double* T_base, const double* T_tool) {
+  if (!out || (njoints != 2 && njoints != 3)) return RK_ERR_INVALID_ARG;
+  memset(out, 0, sizeof(*out));
+  for (int k = 0; k < njoints; ++k) {
+    out->l[k] = lengths ? lengths[k] : (njoints == 3 ? 1.0 : 0.8);  // rrr_robot.py:36, rr_robot.py:61-65
+    out->lim_lo[k] = -360.0 * (3.141592653589793 / 180.0);
+    out->lim_hi[k] = 360.0 * (3.141592653589793 / 180.0);
+  }
+  out->eps = 1e-5;
+  const double kI[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  const double* src[2] = {T_base, T_tool};
+  double* dst[2] = {out->T_base, out->T_tool};
+  double* dsti[2] = {out->T_base_inv, out->T_tool_inv};
+  int32_t* has[2] = {&out->has_base, &out->has_tool};
+  for (int t = 0; t < 2; ++t) {
+    bool ident = true;
+    for (int k = 0; k < 12; ++k) {
+      dst[t][k] = src[t] ? src[t][k] : kI[k];
+      ident = ident && dst[t][k] == kI[k];
+    }
+    if (ident) {
+      for (int k = 0; k < 12; ++k) dsti[t][k] = kI[k];
+    } else {
+      rk_affine_inverse(dst[t], dsti[t]);
+    }
+    *has[t] = ident ? 0 : 1;
+  }
+  return RK_OK;
+}
+
 }  // extern "C"

@@ -159,3 +159,20 @@ def test_c_demo_compiles_against_the_header(tmp_path):
                         "-lrk_b200", "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lm", "-o", str(exe)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_c_arm_initialiser_matches_the_python_structs():
+    """rk_arm_init == RRRRobot()._struct() / RRRobot()._struct(), byte for byte."""
+    import ctypes as C
+    from roboticmanipulators_b200 import _lib
+    from roboticmanipulators_b200.robots import RRRRobot, RRRobot
+    lib = _lib.load()
+    st = _lib.RkArm()
+    assert lib.rk_arm_init(C.byref(st), 3, None, None, None) == 0
+    assert bytes(st) == bytes(RRRRobot()._struct())
+    assert lib.rk_arm_init(C.byref(st), 2, None, None, None) == 0
+    assert bytes(st) == bytes(RRRobot()._struct())
+    ls = np.array([0.5, 1.25])
+    assert lib.rk_arm_init(C.byref(st), 2, ls.ctypes.data_as(C.POINTER(C.c_double)), None, None) == 0
+    assert bytes(st) == bytes(RRRobot(lengths=(0.5, 1.25))._struct())
+    assert lib.rk_arm_init(C.byref(st), 4, None, None, None) != 0
