@@ -52,3 +52,19 @@ def test_c_abi_demo_runs(tmp_path):
     r = subprocess.run([str(exe), "50000"], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, (r.stdout, r.stderr)
     assert "0 differing validity flags" in r.stdout
+
+
+def test_rr_synthetic_calibration_example():
+    """A model the structure-specialised kernels do not know (RR arm, 3 parameters) through the
+    generic calibration kernels: one iteration recovers the 0.1 link error to the noise floor; a
+    second one follows the reference's blend rule (model_calibration.py:442-446) exactly."""
+    import numpy as np
+    import rr_synthetic_calibration_gpu as ex
+    sigma = 0.001
+    hist, params = ex.main(50000, 1, sigma=sigma, verbose=False)
+    floor = sigma * np.sqrt(3)                            # the tool / base fit was made before the link fit
+    assert 0.95 * floor < hist[0]["distance_rms"] < 1.15 * floor
+    assert abs(params[0] - 0.1) < 5e-3 and np.all(np.abs(params[1:]) < 1e-3)
+    hist2, params2 = ex.main(50000, 2, sigma=sigma, verbose=False)
+    assert abs(params2[0] - 0.95 * params[0]) < 1e-3      # (1 - s) pi + s dpi with s = 0.05, |dpi| << pi
+    assert hist2[1]["distance_rms"] > hist2[0]["distance_rms"]
