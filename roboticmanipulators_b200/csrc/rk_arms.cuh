@@ -231,7 +231,7 @@ __device__ __forceinline__ bool rrr_ik11_trig(const ArmPT<S>& P, const S (&p0)[3
 // The canonical 4 branches (m outer, k inner) of one target in one thread: atan2(y, x) once; k only
 // flips the sign of x' = k r_xy, which enters cos(q2) through x'^2 -- (-x)^2 == x^2 bit for bit -- so
 // acos and beta are shared by both k as well (beta is odd in m) and only gamma = atan2(z', +-r_xy) is
-// taken twice: 5 atan2 per target instead of 16 (7 before the k = -1 pass reused the k = +1 values).
+// needed twice, and the second one is the supplement of the first: 4 atan2 per target instead of 16.
 template <typename S>
 __device__ __forceinline__ void rrr_ik4_pose(const ArmPT<S>& P, const S (&p0)[3], S (&qo)[4][3],
                                              bool (&ok)[4]) {
@@ -244,7 +244,9 @@ __device__ __forceinline__ void rrr_ik4_pose(const ArmPT<S>& P, const S (&p0)[3]
   for (int ki = 0; ki < 2; ++ki) {
     if (ki) {  // k = -1: the same triangle seen from x' = -r_xy
       r.xp = -rxy;                                                               // :162
-      r.gamma = M::atan2_fast(r.zp, r.xp);                                       // :179
+      // gamma = atan2(z', -r_xy) (:179) is the supplement of the k = +1 angle: sign(z') pi - gamma+
+      // (exact for z' = +-0 and r_xy = 0, within an ulp of pi otherwise) -- the fifth atan2 goes
+      r.gamma = M::sub(copysign(M::pi(), r.zp), r.gamma);
     }
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi) ok[mi * 2 + ki] = rrr_ik_finish(P, r, q0, mi ? -1 : 1, qo[mi * 2 + ki]);
