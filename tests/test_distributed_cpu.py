@@ -90,3 +90,26 @@ def test_two_rank_normal_equation_allreduce():
         for k, v in want.items():                               # the reference's evaluate() on all 240 rows
             assert abs(metrics[k] - v) < 1e-9, (k, metrics[k], v)
     assert np.array_equal(results[0][1], results[1][1])        # bit-identical across ranks
+
+
+def test_reference_arm_under_torchrun_prints_one_line():
+    """`bench.py --impl reference` launched the way the driver launches it for N > 1 (torchrun, one
+    rank per GPU): rank 0 alone times the CPU path and prints ONE JSON line with the contract's
+    keys; the other ranks exit 0 without output.  Needs no GPU."""
+    import json
+    import subprocess
+    port = _free_port()
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"),
+                        "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["higher_is_better"] is True
+    assert d["unit"] == "poses/s" and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["config"]["workload"] == "fanuc165f_fk_jac_det_ik8"
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["e2e"]["value"] == d["value"]
