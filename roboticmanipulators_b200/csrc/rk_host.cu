@@ -70,11 +70,21 @@ static cudaError_t copy_chunk(E* dst, const E* src, int ncomp, int64_t cnt, int6
   return cudaMemcpy2DAsync(d, dpitch, s, spitch, (size_t)cnt * sizeof(E), ncomp, kind, st);
 }
 
+// A failing call must not leave copies in flight on the caller's host arrays: the three streams are
+// drained before the error is returned.
+static void drain(RkHostPipe* h) {
+  if (!h) return;
+  if (h->s_out) cudaStreamSynchronize(h->s_out);
+  if (h->s_k) cudaStreamSynchronize(h->s_k);
+  if (h->s_in) cudaStreamSynchronize(h->s_in);
+}
+
 #define RK_TRY(expr)                 \
   do {                               \
     cudaError_t e_ = (expr);         \
     if (e_ != cudaSuccess) {         \
       g_last_cuda = e_;              \
+      drain(h);                      \
       cudaGetLastError();            \
       return RK_ERR_CUDA;            \
     }                                \
@@ -115,7 +125,10 @@ static int run_host(RkHostPipe* h, const RkFanuc* robot, const S* q, int64_t n, 
     else
       rc = fk(robot, v.q, cnt, C, flags, T ? v.T : nullptr, J ? v.J : nullptr, det ? v.det : nullptr,
               (void*)h->s_k);
-    if (rc != RK_OK) return rc;
+    if (rc != RK_OK) {
+      drain(h);
+      return rc;
+    }
     RK_TRY(cudaEventRecord(h->ev_k[slot], h->s_k));
     // download what was asked for
     RK_TRY(cudaStreamWaitEvent(h->s_out, h->ev_k[slot], 0));
@@ -162,7 +175,10 @@ static int run_host_ik(RkHostPipe* h, const RkFanuc* robot, const S* T, int64_t 
     RK_TRY(cudaStreamWaitEvent(h->s_k, h->ev_in[slot], 0));
     if (i >= h->nslots) RK_TRY(cudaStreamWaitEvent(h->s_k, h->ev_out[slot], 0));
     const int rc = ikfn(robot, v.T, cnt, C, flags, nullptr, 8, v.qik, v.valid, (void*)h->s_k);
-    if (rc != RK_OK) return rc;
+    if (rc != RK_OK) {
+      drain(h);
+      return rc;
+    }
     RK_TRY(cudaEventRecord(h->ev_k[slot], h->s_k));
     RK_TRY(cudaStreamWaitEvent(h->s_out, h->ev_k[slot], 0));
     RK_TRY(copy_chunk<S>(q_out, v.qik, kNQ, cnt, lo, ld, C, soa, false, h->s_out));
