@@ -15,6 +15,7 @@ this repo) with three non-arithmetic shims:
 
 Usage:  python tests/golden/make_golden.py [--only fanuc,jac,...] [--jobs 8]
         python tests/golden/make_golden.py --only config1 [--config1-n 10000]   (config-1 set, ~10 min)
+        python tests/golden/make_golden.py --only general [--general-n 2000]    (all-custom robot, ~3 min)
 """
 import argparse
 import os
@@ -93,6 +94,15 @@ def _fanuc(tag):
     if tag not in _ROBOTS:
         if tag == "default":
             _ROBOTS[tag] = Fanuc165F(save=False)
+        elif tag == "general":
+            # everything non-stock at once: lengths, offsets, directions, rotating base and tool
+            from utils.robo_math import Transformation as tf
+            Tb = tf("TxTyTzRzRyRx", [-350, 420, 150, -0.4, 0.15, 0.25])
+            Tt = tf("TxTyTzRyRz", [60, -40, 210, 0.35, -0.2])
+            _ROBOTS[tag] = Fanuc165F(T_base=np.array(Tb.transformation, dtype=float),
+                                     T_tool=np.array(Tt.transformation, dtype=float), save=False,
+                                     lengths=CUSTOM_LENGTHS, offsets=np.array(CUSTOM_OFFSETS),
+                                     directions=np.array(CUSTOM_DIRECTIONS))
         elif tag == "custom":
             # non-stock link lengths, joint offsets and directions (fanuc.py:72-96)
             _ROBOTS[tag] = Fanuc165F(save=False, lengths=CUSTOM_LENGTHS,
@@ -222,6 +232,30 @@ def gen_fanuc_custom(pool, out_dir, n_rand):
            "d": np.array(robot.d), "dq": np.array(robot.dq)}
     print("fanuc custom", len(q), flush=True, file=sys.__stdout__)
     np.savez_compressed(os.path.join(out_dir, "fanuc_custom.npz"), **res)
+
+
+def _w_general(q):
+    return _w_fanuc_fk_ik(("general", q))
+
+
+def gen_fanuc_general(pool, out_dir, n):
+    """FK + 12-branch IK through the REAL reference for a robot with NOTHING at its default: custom
+    link lengths, joint offsets and directions, rotating base and tool transforms; n joint vectors
+    uniform in the joint limits (seed 11)."""
+    rng = np.random.default_rng(11)
+    q = _rng_in_limits(rng, FANUC_LIM_DEG, n)
+    T = np.zeros((n, 3, 4))
+    ik = np.zeros((n, 12, 6))
+    for i, (Ti, iki) in enumerate(pool.imap(_w_general, list(q), chunksize=8)):
+        T[i], ik[i] = Ti[:3], iki
+        if (i + 1) % 500 == 0:
+            print("general", i + 1, "/", n, flush=True, file=sys.__stdout__)
+    robot = _fanuc("general")
+    np.savez_compressed(os.path.join(out_dir, "fanuc_general.npz"), q=q, T34=T, ik12=ik,
+                        branches12=np.array(ALL_12), lengths=np.array(CUSTOM_LENGTHS),
+                        offsets=np.array(CUSTOM_OFFSETS), directions=np.array(CUSTOM_DIRECTIONS, dtype=float),
+                        T_base=np.array(robot.T_base, dtype=float), T_tool=np.array(robot.T_tool, dtype=float))
+    print("general done", n, flush=True, file=sys.__stdout__)
 
 
 def gen_fanuc(pool, out_dir, n_rand):
@@ -672,6 +706,8 @@ def main():
     ap.add_argument("--out", default=HERE)
     ap.add_argument("--config1-n", type=int, default=10000,
                     help="poses of the config-1 set (only with --only config1; ~10 min on 8 cores)")
+    ap.add_argument("--general-n", type=int, default=2000,
+                    help="poses of the all-custom robot set (only with --only general; ~3 min on 8 cores)")
     args = ap.parse_args()
     only = set(args.only.split(","))
     dst = prepare_reference()
@@ -695,6 +731,8 @@ def main():
         gen_fanuc_jac(pool, args.out, args.n_rand // 2)
     if "config1" in only:
         gen_config1(pool, args.out, args.config1_n)
+    if "general" in only:
+        gen_fanuc_general(pool, args.out, args.general_n)
     pool.close()
     if "calib" in only:
         gen_calibration(args.out, args.calib_rows)

@@ -528,3 +528,42 @@ def test_config1_against_the_real_reference(golden, layout):
     q8, v8 = robot.inverse_kinematics_batch(torch.tensor(Tg, device="cuda"), layout=layout)
     ikcond.assert_ik_close(q8.cpu().numpy(), v8.cpu().numpy(), ik12[:, idx8], v_ref[:, idx8], det8,
                            base=2e-12, min_well=0.98)
+
+
+@pytest.mark.parametrize("layout", ["aos", "soa"])
+def test_general_robot_against_the_real_reference(golden, layout):
+    """A robot with nothing at its default -- custom link lengths, joint offsets and directions,
+    rotating base and tool -- on 4000 uniform-in-limits joint vectors whose FK and 12-branch IK came
+    from the REAL reference (tests/golden/fanuc_general.npz, make_golden.py --only general): the
+    kernels' general path (no sign-flip shortcuts for the user angles, T_base / T_tool products and
+    their inverses) to the same gates as config 1, in FP64 and in FP32."""
+    from roboticmanipulators_b200.robots.fanuc import Fanuc165F, ALL_12
+    g = golden("fanuc_general.npz")
+    q, T34, ik12 = g["q"], g["T34"], g["ik12"]
+    n = len(q)
+    robot = Fanuc165F(T_base=g["T_base"], T_tool=g["T_tool"], lengths=tuple(g["lengths"]), offsets=g["offsets"],
+                      directions=g["directions"])
+    c = O.FanucConst(T_base=g["T_base"], T_tool=g["T_tool"], lengths=g["lengths"], offsets=g["offsets"],
+                     directions=g["directions"])
+    T = robot.forward_kinematics_batch(torch.tensor(q, device="cuda"), layout=layout).cpu().numpy()
+    assert np.max(np.abs(T[:, :3, :3] - T34[:, :, :3])) < 1e-12
+    pscale = np.maximum(1.0, np.abs(T34[:, :, 3]).max(axis=1))[:, None]
+    assert np.max(np.abs(T[:, :3, 3] - T34[:, :, 3]) / pscale) < 1e-12
+    Tg = np.zeros((n, 4, 4))
+    Tg[:, :3], Tg[:, 3, 3] = T34, 1.0
+    v_ref = np.any(ik12 != 0.0, axis=2)
+    _, v_o, det_o = ikcond.ik_details(Tg, ALL_12, c)
+    assert np.array_equal(v_o, v_ref)
+    qik, vik = robot.inverse_kinematics_batch(torch.tensor(Tg, device="cuda"), ALL_12, layout=layout)
+    qik, vik = qik.cpu().numpy(), vik.cpu().numpy()
+    assert np.array_equal(vik, v_ref), int((vik != v_ref).sum())
+    assert ikcond.assert_ik_close(qik, vik, ik12, v_ref, det_o, base=2e-12, min_well=0.97) > 0.97
+    # the canonical 8 through the pose kernels and the fused call on q
+    idx8 = [list(ALL_12).index(b) for b in O.CANONICAL_8]
+    det8 = {k: v[:, idx8] for k, v in det_o.items()}
+    q8, v8 = robot.inverse_kinematics_batch(torch.tensor(Tg, device="cuda"), layout=layout)
+    assert np.array_equal(v8.cpu().numpy(), v_ref[:, idx8])
+    ikcond.assert_ik_close(q8.cpu().numpy(), v8.cpu().numpy(), ik12[:, idx8], v_ref[:, idx8], det8,
+                           base=2e-12, min_well=0.97)
+    # FP32: masks away from the thresholds, values to the conditioned 1e-5 gate
+    _check_ik_f32(robot, c, Tg, layout)

@@ -307,3 +307,28 @@ def test_config1_oracle_against_the_real_reference(golden):
     assert 0.3 < v_ref.mean() < 0.5
     frac = ikcond.assert_ik_close(ik12, v_ref, q_o, v_o, det)
     assert frac > 0.98
+
+
+def test_general_robot_oracle_against_the_real_reference(golden):
+    """A robot with NOTHING at its default (custom link lengths, joint offsets and directions,
+    rotating base and tool transforms), 4000 uniform-in-limits joint vectors through the REAL
+    reference (make_golden.py --only general): FK to 1e-12 scaled, all 4.8e4 validity decisions of
+    the 12 (m, k, w) combinations exact, every IK value within the conditioned bound."""
+    import ikcond
+    g = golden("fanuc_general.npz")
+    q, T34, ik12 = g["q"], g["T34"], g["ik12"]
+    n = len(q)
+    assert n == 4000
+    c = O.FanucConst(T_base=g["T_base"], T_tool=g["T_tool"], lengths=g["lengths"], offsets=g["offsets"],
+                     directions=g["directions"])
+    T = O.fanuc_fk(q, c)
+    assert np.max(np.abs(T[:, :3, :3] - T34[:, :, :3])) < 1e-12
+    assert np.max(np.abs(T[:, :3, 3] - T34[:, :, 3]) / np.maximum(1, np.abs(T34[:, :, 3]).max(1, keepdims=True))) < 1e-12
+    Tg = np.zeros((n, 4, 4))
+    Tg[:, :3], Tg[:, 3, 3] = T34, 1.0
+    br = [tuple(int(v) for v in b) for b in g["branches12"]]
+    q_o, v_o, det = ikcond.ik_details(Tg, br, c)
+    v_ref = np.any(ik12 != 0.0, axis=2)
+    assert 0.05 < v_ref.mean() < 0.6
+    frac = ikcond.assert_ik_close(ik12, v_ref, q_o, v_o, det)
+    assert frac > 0.97
