@@ -469,7 +469,7 @@ def _w_rr_bt(q):
     return T, out
 
 
-def gen_arms_base_tool(pool, out_dir, n_rand):
+def gen_arms_base_tool(pool, out_dir, n_rand, name="arms_base_tool.npz"):
     """RRR and RR (lengths 0.5, 1.25) with rotating T_base / T_tool (robot.py:39-57)."""
     rng = np.random.default_rng(6)
     Tb, Tt = _arm_bt()
@@ -481,7 +481,7 @@ def gen_arms_base_tool(pool, out_dir, n_rand):
            "rrr_q": q3, "rrr_T": np.array([x[0] for x in r3]), "rrr_ik4": np.array([x[1] for x in r3]),
            "rrr_branches": np.array([(1, 1), (1, -1), (-1, 1), (-1, -1)]),
            "rr_q": q2, "rr_T": np.array([x[0] for x in r2]), "rr_ik2": np.array([x[1] for x in r2])}
-    np.savez_compressed(os.path.join(out_dir, "arms_base_tool.npz"), **res)
+    np.savez_compressed(os.path.join(out_dir, name), **res)
     print("arms base/tool done", flush=True, file=sys.__stdout__)
 
 
@@ -733,6 +733,8 @@ def main():
         gen_config1(pool, args.out, args.config1_n)
     if "general" in only:
         gen_fanuc_general(pool, args.out, args.general_n)
+    if "armslarge" in only:   # the same recipe as armsbt at 3000 joint vectors per arm (~2 min)
+        gen_arms_base_tool(pool, args.out, 3000, name="arms_base_tool_large.npz")
     pool.close()
     if "calib" in only:
         gen_calibration(args.out, args.calib_rows)

@@ -173,10 +173,12 @@ def test_arm_ik_special_targets(layout):
             assert np.nanmax(np.abs(qb[:, b].cpu().numpy() - q_ref)[~folded]) < 1e-6, m
 
 
-def test_arms_base_tool_against_reference_golden(golden):
-    """RRR / RR behind rotating T_base and T_tool against vectors from the real reference."""
+@pytest.mark.parametrize("name", ["arms_base_tool.npz", "arms_base_tool_large.npz"])
+def test_arms_base_tool_against_reference_golden(golden, name):
+    """RRR / RR behind rotating T_base and T_tool against vectors from the real reference (57 joint
+    vectors per arm, and 3001 from the same recipe)."""
     from roboticmanipulators_b200.robots import RRRRobot, RRRobot
-    g = golden("arms_base_tool.npz")
+    g = golden(name)
     Tb, Tt = g["T_base"], g["T_tool"]
     rrr = RRRRobot(T_base=Tb, T_tool=Tt)
     rr = RRRobot(T_base=Tb, T_tool=Tt, lengths=tuple(g["rr_lengths"]), save=False)

@@ -160,9 +160,11 @@ def test_rrr_rr(golden):
             assert np.max(np.abs(q - g[f"{nm}_ik2"][:, b])) < 1e-9
 
 
-def test_arms_with_base_and_tool(golden):
-    """RRR / RR behind rotating T_base and T_tool (robot.py:39-57), from the real reference."""
-    g = golden("arms_base_tool.npz")
+@pytest.mark.parametrize("name", ["arms_base_tool.npz", "arms_base_tool_large.npz"])
+def test_arms_with_base_and_tool(golden, name):
+    """RRR / RR behind rotating T_base and T_tool (robot.py:39-57), from the real reference (57
+    joint vectors per arm, and the same recipe at 3001: make_golden.py --only armslarge)."""
+    g = golden(name)
     Tb, Tt = g["T_base"], g["T_tool"]
     assert scaled(O.rrr_fk(g["rrr_q"], Tb, Tt), g["rrr_T"]) < 1e-14
     for b, (m, k) in enumerate(g["rrr_branches"]):
