@@ -572,6 +572,44 @@ def gen_trajectories(out_dir):
     print("trajectories done", flush=True, file=sys.__stdout__)
 
 
+def gen_trajectories_large(out_dir, count=480):
+    """`count` random point-to-point moves through the REAL reference's equalised trapezoid profiles
+    (TrajectoryGenerator._generate_equalized_profiles, trajectory_generator.py:71-92), grouped by
+    (n, control_freq) so that a batched call reproduces a whole group: sample COUNTS, times and
+    q / dq / ddq are compared bit for bit.  Padded to n samples; `length` 0 = the reference raised."""
+    from utils.trajectory_generator import TrajectoryGenerator
+    rng = np.random.default_rng(14)
+    res = {}
+    groups = [(n, cf) for n in (40, 64, 100) for cf in (0, 10)]
+    per = count // len(groups)
+    for gi, (n, cf) in enumerate(groups):
+        q0 = rng.uniform(-np.pi, np.pi, size=(per, 3))
+        qf = rng.uniform(-np.pi, np.pi, size=(per, 3))
+        qf[0] = q0[0] + rng.uniform(-2e-3, 2e-3, size=3)        # short moves: few samples or an error
+        qf[1] = q0[1] + np.array([1e-2, -3.0, 0.5])
+        q = np.zeros((per, n, 3))
+        dq, ddq, t = np.zeros_like(q), np.zeros_like(q), np.zeros((per, n))
+        length = np.zeros(per, dtype=np.int32)
+        for i in range(per):
+            tgen = TrajectoryGenerator(1, 20, 1, 10, control_freq=cf)
+            tgen._tg.set_frequency(cf)
+            tgen._tg.set_limits(1, 20)
+            try:
+                qs, dqs, ddqs, ts = tgen._generate_equalized_profiles(list(q0[i]), list(qf[i]), n)
+            except (IndexError, ValueError):
+                continue
+            L = len(ts)
+            length[i] = L
+            q[i, :L], dq[i, :L], ddq[i, :L], t[i, :L] = np.array(qs).T, np.array(dqs).T, np.array(ddqs).T, ts
+        res[f"g{gi}_spec"] = np.array([n, cf])
+        res[f"g{gi}_q0"], res[f"g{gi}_qf"] = q0, qf
+        res[f"g{gi}_q"], res[f"g{gi}_dq"], res[f"g{gi}_ddq"], res[f"g{gi}_t"] = q, dq, ddq, t
+        res[f"g{gi}_len"] = length
+    res["groups"] = np.array(len(groups))
+    np.savez_compressed(os.path.join(out_dir, "trajectories_large.npz"), **res)
+    print("trajectories large done", flush=True, file=sys.__stdout__)
+
+
 def gen_calibration(out_dir, rows):
     """fanuc_calibration.py:11-91 on the real dataset (or its first `rows`)."""
     import io
@@ -719,6 +757,8 @@ def main():
         gen_generic_chain(args.out)
     if "traj" in only:
         gen_trajectories(args.out)
+    if "trajlarge" in only:
+        gen_trajectories_large(args.out)
     if "rrr" in only:
         gen_rrr_rr(pool, args.out, args.n_rand)
     if "armsbt" in only:

@@ -334,3 +334,16 @@ def test_general_robot_oracle_against_the_real_reference(golden):
     assert 0.05 < v_ref.mean() < 0.6
     frac = ikcond.assert_ik_close(ik12, v_ref, q_o, v_o, det)
     assert frac > 0.97
+
+
+def test_p2p_trajectories_large_bit_exact(golden):
+    """480 random point-to-point moves through the REAL reference (make_golden.py --only trajlarge),
+    six (n, control_freq) groups, a third of the short-n ones raising there: the oracle reproduces
+    every sample count, time and q / dq / ddq bit for bit."""
+    g = golden("trajectories_large.npz")
+    for gi in range(int(g["groups"])):
+        n, cf = (int(v) for v in g[f"g{gi}_spec"])
+        q, dq, ddq, t, L = O.p2p_batch(g[f"g{gi}_q0"], g[f"g{gi}_qf"], n, 1, 20, cf)
+        assert np.array_equal(L, g[f"g{gi}_len"]), (n, cf)
+        assert np.array_equal(q, g[f"g{gi}_q"]) and np.array_equal(dq, g[f"g{gi}_dq"])
+        assert np.array_equal(ddq, g[f"g{gi}_ddq"]) and np.array_equal(t, g[f"g{gi}_t"])

@@ -171,3 +171,23 @@ def test_quintic_profiles(golden):
     qb, _, _ = tg.generate_joint_poly_trajectory_batch(dev(q_0), dev(q_f), 2.0, 0.0, 50)
     assert np.max(np.abs(qb[0].cpu().numpy() - g["planning_qs"])) < 1e-12
     assert np.max(np.abs(tg.generate_joint_poly_trajectory(q_0[0], q_f[0], 2, n=50, plot=False) - g["planning_qs"])) < 1e-12
+
+
+def test_p2p_large_golden_bit_exact(golden):
+    """The same 480 real-reference moves (tests/golden/trajectories_large.npz) through the batched
+    kernel, one launch per (n, control_freq) group: counts, times, q / dq / ddq bit-identical, the
+    moves the reference raises on come back with length 0 and zero rows."""
+    from roboticmanipulators_b200.robots import RRRRobot
+    from roboticmanipulators_b200.utils.trajectory_generator import TrajectoryGenerator
+    g = golden("trajectories_large.npz")
+    for gi in range(int(g["groups"])):
+        n, cf = (int(v) for v in g[f"g{gi}_spec"])
+        tg = TrajectoryGenerator(1, 20, 1, 10, control_freq=cf)
+        q, dq, ddq, t, L = tg.generate_p2p_trajectory_batch(dev(g[f"g{gi}_q0"]), dev(g[f"g{gi}_qf"]), n)
+        assert np.array_equal(L.cpu().numpy(), g[f"g{gi}_len"]), (n, cf)
+        for got, name in ((q, "q"), (dq, "dq"), (ddq, "ddq"), (t, "t")):
+            assert np.array_equal(got.cpu().numpy(), g[f"g{gi}_{name}"]), (n, cf, name)
+        # the fused FK variant walks the same profile
+        q2, _, _, _, L2, T, J = tg.generate_p2p_trajectory_batch(dev(g[f"g{gi}_q0"]), dev(g[f"g{gi}_qf"]), n,
+                                                                 robot=RRRRobot())
+        assert torch.equal(q2, q) and torch.equal(L2, L)
