@@ -388,6 +388,42 @@ def gen_generic_chain(out_dir):
     print("generic chain done", flush=True, file=sys.__stdout__)
 
 
+def gen_generic_chain_random(out_dir, ncases=28):
+    """Random token sequences (3 - 12 tokens, translations and rotations about every axis, inverse
+    tokens as passive elements, random joint masks, with and without base / tool) through the REAL
+    reference's Transformation and JacobianCalculator.calculate_numerically: every structure is a
+    different specialised kernel on the GPU side."""
+    import sympy as sp
+    from utils.robo_math import Transformation as tf
+    from utils.jacobians import JacobianCalculator
+    rng = np.random.default_rng(21)
+    T_base = np.array(tf("TxTyTzRzRx", [0.4, -0.3, 0.2, 0.5, -0.25]).transformation, dtype=float)
+    T_tool = np.array(tf("TzRyTx", [0.15, 0.35, -0.1]).transformation, dtype=float)
+    plain = ["Tx", "Ty", "Tz", "Rx", "Ry", "Rz"]
+    res = {"n_cases": np.array(ncases), "T_base": T_base, "T_tool": T_tool}
+    for c in range(ncases):
+        ntok = int(rng.integers(3, 13))
+        toks, ind = [], []
+        for _ in range(ntok):
+            t = plain[int(rng.integers(0, 6))]
+            if rng.uniform() < 0.15:
+                toks.append(t + "i"), ind.append(0)            # inverse tokens are never joints
+            else:
+                toks.append(t), ind.append(int(rng.uniform() < 0.55))
+        if not any(ind):
+            ind[[i for i, t in enumerate(toks) if not t.endswith("i")][0]] = 1
+        seq, with_bt = "".join(toks), bool(c % 2)
+        vals = rng.uniform(-2, 2, size=(8, ntok))
+        kw = dict(T_base=sp.Matrix(T_base), T_tool=sp.Matrix(T_tool)) if with_bt else {}
+        jc = JacobianCalculator(seq, ind, **kw)
+        res[f"c{c}_seq"], res[f"c{c}_ind"], res[f"c{c}_bt"] = np.array(seq), np.array(ind), np.array(with_bt)
+        res[f"c{c}_vals"] = vals
+        res[f"c{c}_T"] = np.array([np.array(tf(seq, list(v)).transformation, dtype=float) for v in vals])
+        res[f"c{c}_J"] = np.array([np.array(jc.calculate_numerically(list(v)), dtype=float) for v in vals])
+    np.savez_compressed(os.path.join(out_dir, "generic_chain_random.npz"), **res)
+    print("generic chain random done", flush=True, file=sys.__stdout__)
+
+
 def _w_rrr(args):
     q = args
     from robots.rrr_robot import RRRRobot
@@ -755,6 +791,8 @@ def main():
         gen_poly(args.out)
     if "chain" in only:
         gen_generic_chain(args.out)
+    if "chainrandom" in only:
+        gen_generic_chain_random(args.out)
     if "traj" in only:
         gen_trajectories(args.out)
     if "trajlarge" in only:

@@ -347,3 +347,17 @@ def test_p2p_trajectories_large_bit_exact(golden):
         assert np.array_equal(L, g[f"g{gi}_len"]), (n, cf)
         assert np.array_equal(q, g[f"g{gi}_q"]) and np.array_equal(dq, g[f"g{gi}_dq"])
         assert np.array_equal(ddq, g[f"g{gi}_ddq"]) and np.array_equal(t, g[f"g{gi}_t"])
+
+
+def test_random_chains_against_the_real_reference(golden):
+    """28 random token sequences (3 - 12 tokens, inverse tokens as passive elements, random joint
+    masks, half of them behind base / tool) through the REAL reference (make_golden.py --only
+    chainrandom): product and Jacobian (matrix-derivative and screw form) of the oracle."""
+    g = golden("generic_chain_random.npz")
+    for c in range(int(g["n_cases"])):
+        seq, ind = str(g[f"c{c}_seq"]), [int(i) for i in g[f"c{c}_ind"]]
+        kw = dict(T_base=g["T_base"], T_tool=g["T_tool"]) if bool(g[f"c{c}_bt"]) else {}
+        vals = g[f"c{c}_vals"]
+        assert scaled(O.chain(seq, vals), g[f"c{c}_T"]) < 1e-14, seq
+        assert scaled(O.jacobian_numerically(seq, ind, vals, **kw), g[f"c{c}_J"]) < 1e-13, seq
+        assert scaled(O.jacobian_screw(seq, ind, vals, **kw), g[f"c{c}_J"]) < 1e-13, seq
