@@ -15,7 +15,8 @@ this repo) with three non-arithmetic shims:
 
 Usage:  python tests/golden/make_golden.py [--only fanuc,jac,...] [--jobs 8]
         python tests/golden/make_golden.py --only config1 [--config1-n 10000]   (config-1 set, ~10 min)
-        python tests/golden/make_golden.py --only general [--general-n 2000]    (all-custom robot, ~3 min)
+        python tests/golden/make_golden.py --only general --general-n 4000      (all-custom robot, ~3 min)
+        python tests/golden/make_golden.py --only armslarge,trajlarge,chainrandom   (the *_large / random sets, < 1 min)
 """
 import argparse
 import os
