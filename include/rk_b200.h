@@ -246,9 +246,10 @@ int rk_chain_fk_jac_f64(const RkChain* chain, const double* values, int nvals, i
                         int64_t ld, int flags, double* T, double* J, void* stream);
 int rk_chain_fk_jac_f32(const RkChain* chain, const float* values, int nvals, int64_t n,
                         int64_t ld, int flags, float* T, float* J, void* stream);
-/* rk_chain_fk_jac_* runs straight-line code specialised for the chain's STRUCTURE (compiled once per
- * structure with NVRTC for sm_100a and cached; constants stay run-time parameters) when libnvrtc can
- * be loaded, and an interpreting kernel otherwise (or with RK_CHAIN_JIT=0 in the environment).
+/* rk_chain_fk_jac_* and rk_chain_dq_from_dx_f64 run straight-line code specialised for the chain's
+ * STRUCTURE (compiled once per structure with NVRTC for sm_100a and cached; constants stay run-time
+ * parameters) when libnvrtc can be loaded, and an interpreting kernel otherwise (or with
+ * RK_CHAIN_JIT=0 in the environment).
  * Returns "ok", or why the last specialisation was not used. */
 const char* rk_chain_jit_status(void);
 /* The CUDA source of that specialisation (host only, no GPU needed).  want = 1 T | 2 J | 4 two
