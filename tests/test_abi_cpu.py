@@ -81,6 +81,27 @@ def test_argument_validation_without_gpu():
     assert lib.rk_chain_fk_jac_f64(C.byref(ch), None, 0, 0, 0, 0, None, None, None) == -3
     assert lib.rk_trap_p2p_f64(None, None, 4, 9, 10, 1.0, 1.0, 0.0, None, None, None, None,
                                C.c_void_p(8), None) == -3
+    # host-array entry points: no pipe / no robot / negative size are rejected before any CUDA call
+    assert lib.rk_fanuc_fk_jac_ik8_host_f64(None, C.byref(st), None, 4, 4, 0, None, None, None, None, None) == -1
+    assert lib.rk_fanuc_ik8_host_f64(None, C.byref(st), None, 4, 4, 0, None, None) == -1
+    assert lib.rk_fanuc_ik8_host_f32(None, None, None, -1, 0, 0, None, None) == -1
+    pipe = C.c_void_p()
+    assert lib.rk_host_pipe_create(C.byref(pipe), 16, 3) == -1          # chunk < 32 poses
+    assert lib.rk_host_pipe_create(C.byref(pipe), 4096, 1) == -1        # fewer than two slots
+    assert lib.rk_host_pipe_create(None, 4096, 3) == -1
+    assert lib.rk_host_pipe_destroy(None) == 0
+    # dq = J^-1 dx: the row list and the chain are validated on the host
+    ch2 = L.RkChain()
+    ch2.ntok = 2
+    ch2.op[0], ch2.op[1] = 5, 0                                         # Rz, Tx
+    ch2.active[0], ch2.active[1] = 1, 1
+    ch2.src[0], ch2.src[1] = 0, 1
+    rows_bad = (C.c_int32 * 2)(0, 0)                                    # the same row twice
+    assert lib.rk_chain_dq_from_dx_f64(C.byref(ch2), None, 2, rows_bad, None, 4, 4, 0, None, None, None) == -1
+    rows_oob = (C.c_int32 * 2)(0, 6)
+    assert lib.rk_chain_dq_from_dx_f64(C.byref(ch2), None, 2, rows_oob, None, 4, 4, 0, None, None, None) == -1
+    assert lib.rk_chain_dq_from_dx_f64(C.byref(ch2), None, 2, None, None, 0, 0, 0, None, None, None) == 0
+    assert lib.rk_chain_dq_from_dx_f64(None, None, 2, None, None, 4, 4, 0, None, None, None) == -1
 
 
 def test_no_cpu_fallback():
